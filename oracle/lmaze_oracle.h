@@ -1,0 +1,125 @@
+/*
+ * lmaze_oracle.h -- CPU restatement of gkm2708/gym-lmaze's step()/reset() hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library, and only as the
+ * checker or the CPU baseline -- never as the thing shipped.  The product
+ * (gym_lmaze_b200/) does not link, import or fall back to anything in oracle/.
+ *
+ * Parity pin: the reference ships NO tests, golden vectors or fixtures
+ * (SURVEY.md section 8c).  This restatement is therefore pinned against outputs
+ * of the unmodified reference itself, executed in the build container under a
+ * `gym` stub: tests/golden/gen_golden.py wrote the fixtures in tests/golden/
+ * (exhaustive v0 transition table, all position->obs renders, seeded traces,
+ * v3 tables) and tests/test_oracle_golden.py checks every one of them; where
+ * /root/reference is present tests/test_oracle_vs_reference.py also steps the
+ * live reference beside this code.
+ *
+ * All file:line citations are into the reference checkout.
+ */
+#ifndef LMAZE_ORACLE_H
+#define LMAZE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMZO_V0 0
+#define LMZO_V3 3
+#define LMZO_MAX_G 18
+
+/* One environment, holding the same mutable fields the reference keeps on `self`. */
+typedef struct lmzo_env {
+  int variant;            /* LMZO_V0 / LMZO_V3 */
+  int G;                  /* realgrid          (lmaze_env.py:17, lmaze_env_v3.py:72) */
+  int E;                  /* expansionRatio    (lmaze_env.py:18, lmaze_env_v3.py:73) */
+  int C;                  /* obs channels      (lmaze_env.py:20, lmaze_env_v3.py:87-89) */
+  int step_limit;         /* 100 both variants (lmaze_env.py:247, lmaze_env_v3.py:99)  */
+  int random_ball;        /* RANDOM_BALL       (lmaze_env.py:25, lmaze_env_v3.py:103)  */
+  int random_goal;        /* RANDOM_GOAL, v3   (lmaze_env_v3.py:104) */
+  char grid[LMZO_MAX_G * LMZO_MAX_G];         /* row-major cell letters */
+  float state[4 * LMZO_MAX_G * LMZO_MAX_G];   /* self.state layers (v0: 4 layers; v3: 2 used) */
+  float goal_image[LMZO_MAX_G * LMZO_MAX_G];  /* v3 image_global_goal (lmaze_env_v3.py:170,182) */
+  int ball_x, ball_y;     /* ball_x0, ball_y0 (row, col) */
+  int goal_x, goal_y;
+  double reward;          /* Python float in the reference */
+  int64_t step_count;     /* stepCount */
+  int64_t goal_count;     /* goalCount, v0 only; survives reset (lmaze_env.py:24,195) */
+} lmzo_env;
+
+/* Episode statistics, integers only (order-independent sums). */
+enum {
+  LMZO_STAT_STEPS = 0, LMZO_STAT_EPISODES, LMZO_STAT_GOALS, LMZO_STAT_TIMEOUTS,
+  LMZO_STAT_WALL_BUMPS, LMZO_STAT_MOVES, LMZO_STAT_STALE, LMZO_STAT_EPLEN_SUM,
+  LMZO_NUM_STATS
+};
+
+int  lmzo_abi_version(void);
+
+/* Layout access (lmaze_env.py:37-48, lmaze_env_v3.py:26-43).  Returns G, fills cells[G*G]. */
+int  lmzo_layout(int variant, char *cells);
+/* Sizes: obs floats per env. */
+int64_t lmzo_obs_floats(int variant);
+
+/* Constructor state minus the first reset (lmaze_env.py:14-50, lmaze_env_v3.py:22-131). */
+int  lmzo_init(lmzo_env *e, int variant);
+
+/* reset() with the rejection-sampled coordinates supplied by the caller.
+ * v0: (sx,sy) is the ball spawn; gx,gy ignored.            lmaze_env.py:64-111
+ * v3: (gx,gy) goal then (sx,sy) ball; pass gx<0 to keep the
+ *     current goal (RANDOM_GOAL False).                     lmaze_env_v3.py:134-182
+ * Returns 0, or -1 if the reference's rejection loop would not have accepted
+ * the supplied cell. */
+int  lmzo_reset(lmzo_env *e, int sx, int sy, int gx, int gy);
+
+/* step(): action codes 0..3 move, anything else is the reference's unmatched
+ * branch (offset 0,0).  For v3 the code k stands for the string str(k)
+ * (lmaze_env_v3.py:236-247).  Returns done (0/1); reward is left in e->reward.
+ * `cls_out` (may be NULL) receives the branch taken: 0 W, 1 B/else, 2 X/goal, 3 none(S). */
+int  lmzo_step(lmzo_env *e, int64_t action, int *cls_out);
+
+/* isEpisodeFinished() / the done expression (lmaze_env.py:246-249, lmaze_env_v3.py:398). */
+int  lmzo_done(const lmzo_env *e);
+
+/* The observation the reference returns: channel assembly + nested xE upsample
+ * (lmaze_env.py:113-139,208-234; lmaze_env_v3.py:184-206,281-301). obs = C*G*E*G*E floats. */
+void lmzo_render(const lmzo_env *e, float *obs);
+
+/* ---- Philox-4x32-10 counter RNG: NOT from the reference (which uses CPython's
+ * MT19937, lmaze_env.py:74-75).  It restates the device RNG spec in DESIGN.md so
+ * RNG-driven spawns/actions of the CUDA path can be replayed on the CPU. ---- */
+void lmzo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Spawn for (seed, global env id, episode index).  v0: ball only.  v3: goal + ball. */
+void lmzo_rng_spawn(int variant, uint64_t seed, uint64_t env_id, uint32_t episode,
+                    int *sx, int *sy, int *gx, int *gy);
+/* Rollout action for (seed, global env id, global rollout step t). */
+int  lmzo_rng_action(uint64_t seed, uint64_t env_id, uint64_t t);
+
+/* ---- Vectorised driver: the batched semantics of the framework composed from
+ * the single-env restatement above.  For each env i: step; record f32 reward and
+ * done; if done and autoreset, reset (spawn from `spawn` if non-NULL, else the
+ * Philox spec, bumping episode[i]); render into obs (if non-NULL).
+ * spawn layout: int32 [N][4] = sx, sy, gx, gy.
+ * actions: int64 [N].  stats: int64[LMZO_NUM_STATS], accumulated.  threads<=1 => serial; else a pthread pool over contiguous env ranges. */
+void lmzo_vec_step(lmzo_env *envs, int64_t n, const int64_t *actions, const int32_t *spawn,
+                   uint64_t seed, uint64_t env_id0, uint32_t *episode, int autoreset,
+                   float *obs, float *reward, uint8_t *done, int64_t *stats, int threads);
+void lmzo_vec_reset(lmzo_env *envs, int64_t n, int variant, const int32_t *spawn,
+                    uint64_t seed, uint64_t env_id0, uint32_t *episode, float *obs, int threads);
+
+/* ---- array plumbing used by the ctypes wrapper (oracle/oracle.py) ---- */
+int64_t lmzo_sizeof_env(void);
+lmzo_env *lmzo_env_at(lmzo_env *envs, int64_t i);
+/* pos: int32 [N][4] = x, y, goal_x, goal_y */
+void lmzo_vec_export(const lmzo_env *envs, int64_t n, int32_t *pos, int64_t *step_count,
+                     int64_t *goal_count, double *reward);
+/* Put one env into an arbitrary reachable mid-episode state (incl. ball on the goal cell). */
+int  lmzo_env_force(lmzo_env *e, int variant, int sx, int sy, int gx, int gy,
+                    int64_t step_count, double reward, int64_t goal_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

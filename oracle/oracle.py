@@ -1,0 +1,187 @@
+"""ctypes wrapper around oracle/liblmaze_oracle.so (test infrastructure only).
+
+Importers: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl
+reference legs.  The product package never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblmaze_oracle.so")
+
+V0, V3 = 0, 3
+NUM_STATS = 8
+STAT_NAMES = ("steps", "episodes", "goals", "timeouts", "wall_bumps", "moves", "stale", "eplen_sum")
+OBS_SHAPE = {V0: (4, 84, 84), V3: (3, 72, 72)}
+# f32 bit patterns of the only rewards the reference can emit
+REWARD_BITS = {"neg_zero": 0x80000000, "wall": 0xBF800000, "move": 0xBC23D70A, "goal": 0x42C80000}
+
+
+def build(force=False):
+    """Compile the oracle with the system gcc (no-op if the .so is newer than its sources)."""
+    srcs = [os.path.join(_HERE, f) for f in ("lmaze_oracle.c", "lmaze_oracle.h")]
+    if (not force and os.path.isfile(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "CC=gcc"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(_LIB_PATH):
+        build()
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, i32, i64, u32, u64, dbl = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64,
+                                   ctypes.c_uint32, ctypes.c_uint64, ctypes.c_double)
+    ip = ctypes.POINTER(ctypes.c_int)
+    L.lmzo_abi_version.restype = ctypes.c_int
+    L.lmzo_layout.argtypes = [ctypes.c_int, ctypes.c_char_p]
+    L.lmzo_layout.restype = ctypes.c_int
+    L.lmzo_obs_floats.argtypes = [ctypes.c_int]
+    L.lmzo_obs_floats.restype = i64
+    L.lmzo_init.argtypes = [vp, ctypes.c_int]
+    L.lmzo_reset.argtypes = [vp] + [ctypes.c_int] * 4
+    L.lmzo_reset.restype = ctypes.c_int
+    L.lmzo_step.argtypes = [vp, i64, ip]
+    L.lmzo_step.restype = ctypes.c_int
+    L.lmzo_done.argtypes = [vp]
+    L.lmzo_done.restype = ctypes.c_int
+    L.lmzo_render.argtypes = [vp, vp]
+    L.lmzo_render.restype = None
+    L.lmzo_philox4x32_10.argtypes = [vp, vp, vp]
+    L.lmzo_philox4x32_10.restype = None
+    L.lmzo_rng_spawn.argtypes = [ctypes.c_int, u64, u64, u32, ip, ip, ip, ip]
+    L.lmzo_rng_spawn.restype = None
+    L.lmzo_rng_action.argtypes = [u64, u64, u64]
+    L.lmzo_rng_action.restype = ctypes.c_int
+    L.lmzo_vec_step.argtypes = [vp, i64, vp, vp, u64, u64, vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+    L.lmzo_vec_step.restype = None
+    L.lmzo_vec_reset.argtypes = [vp, i64, ctypes.c_int, vp, u64, u64, vp, vp, ctypes.c_int]
+    L.lmzo_vec_reset.restype = None
+    L.lmzo_sizeof_env.restype = i64
+    L.lmzo_env_at.argtypes = [vp, i64]
+    L.lmzo_env_at.restype = vp
+    L.lmzo_vec_export.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.lmzo_vec_export.restype = None
+    L.lmzo_env_force.argtypes = [vp, ctypes.c_int] + [ctypes.c_int] * 4 + [i64, dbl, i64]
+    L.lmzo_env_force.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def layout(variant):
+    """Rows of the maze as a list of strings."""
+    L = lib()
+    G = L.lmzo_layout(variant, None)
+    buf = ctypes.create_string_buffer(G * G)
+    L.lmzo_layout(variant, buf)
+    cells = buf.raw.decode("ascii")
+    return [cells[i * G:(i + 1) * G] for i in range(G)]
+
+
+def philox(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().lmzo_philox4x32_10(_ptr(c), _ptr(k), _ptr(out))
+    return out
+
+
+def rng_spawn(variant, seed, env_id, episode):
+    v = [ctypes.c_int() for _ in range(4)]
+    lib().lmzo_rng_spawn(variant, seed, env_id, episode, *[ctypes.byref(x) for x in v])
+    return tuple(x.value for x in v)  # sx, sy, gx, gy
+
+
+def rng_action(seed, env_id, t):
+    return lib().lmzo_rng_action(seed, env_id, t)
+
+
+class OracleVec(object):
+    """N independent oracle envs with the framework's batched semantics.
+
+    step(): per env -- reference step; record f32 reward + done; if done and
+    autoreset, reference reset at the injected (or Philox-spec) cells; then the
+    reference render.  Mirrors gym_lmaze_b200.envs.LmazeVecCuda so parity tests can
+    drive both with the same calls.
+    """
+
+    def __init__(self, variant, n, seed=0, env_id0=0, autoreset=True, threads=1):
+        self.L = lib()
+        self.variant, self.n, self.seed, self.env_id0 = variant, int(n), int(seed), int(env_id0)
+        self.autoreset, self.threads = bool(autoreset), int(threads)
+        self.env_bytes = self.L.lmzo_sizeof_env()
+        self._mem = np.zeros(self.n * self.env_bytes, dtype=np.uint8)  # zero => lazily lmzo_init'ed
+        for i in range(self.n):
+            self.L.lmzo_init(self._env(i), variant)
+        self.episode = np.zeros(self.n, dtype=np.uint32)
+        self.stats = np.zeros(NUM_STATS, dtype=np.int64)
+        self.obs_shape = OBS_SHAPE[variant]
+
+    def _env(self, i):
+        return self._mem.ctypes.data + i * self.env_bytes
+
+    @staticmethod
+    def _spawn_arr(spawn, n):
+        if spawn is None:
+            return None
+        s = np.ascontiguousarray(spawn, dtype=np.int32)
+        assert s.shape == (n, 4), s.shape
+        return s
+
+    def reset(self, spawn=None, want_obs=True):
+        s = self._spawn_arr(spawn, self.n)
+        obs = np.empty((self.n,) + self.obs_shape, dtype=np.float32) if want_obs else None
+        self.L.lmzo_vec_reset(_ptr(self._mem), self.n, self.variant, _ptr(s), self.seed, self.env_id0,
+                              _ptr(self.episode), _ptr(obs), self.threads)
+        return obs
+
+    def step(self, actions, spawn=None, want_obs=True, obs_out=None):
+        a = np.ascontiguousarray(actions, dtype=np.int64)
+        assert a.shape == (self.n,)
+        s = self._spawn_arr(spawn, self.n)
+        obs = obs_out if obs_out is not None else (
+            np.empty((self.n,) + self.obs_shape, dtype=np.float32) if want_obs else None)
+        reward = np.empty(self.n, dtype=np.float32)
+        done = np.empty(self.n, dtype=np.uint8)
+        self.L.lmzo_vec_step(_ptr(self._mem), self.n, _ptr(a), _ptr(s), self.seed, self.env_id0,
+                             _ptr(self.episode), int(self.autoreset), _ptr(obs), _ptr(reward), _ptr(done),
+                             _ptr(self.stats), self.threads)
+        return obs, reward, done
+
+    def export(self):
+        pos = np.empty((self.n, 4), dtype=np.int32)
+        sc = np.empty(self.n, dtype=np.int64)
+        gc = np.empty(self.n, dtype=np.int64)
+        rw = np.empty(self.n, dtype=np.float64)
+        self.L.lmzo_vec_export(_ptr(self._mem), self.n, _ptr(pos), _ptr(sc), _ptr(gc), _ptr(rw))
+        return pos, sc, gc, rw
+
+    def force(self, i, sx, sy, gx=-1, gy=-1, step_count=0, reward=-0.0, goal_count=0):
+        rc = self.L.lmzo_env_force(self._env(i), self.variant, sx, sy, gx, gy, step_count, reward, goal_count)
+        if rc != 0:
+            raise ValueError("oracle rejected forced state %r" % ((i, sx, sy, gx, gy),))
+
+    # single-env access for table tests
+    def step_one(self, i, action):
+        cls = ctypes.c_int()
+        d = self.L.lmzo_step(self._env(i), int(action), ctypes.byref(cls))
+        return d, cls.value
+
+    def render_one(self, i):
+        obs = np.empty(self.obs_shape, dtype=np.float32)
+        self.L.lmzo_render(self._env(i), _ptr(obs))
+        return obs

@@ -1,0 +1,180 @@
+"""CPU tier: the C restatement (oracle/) against the golden fixtures that
+tests/golden/gen_golden.py produced from the UNMODIFIED reference."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+INVALID = 7
+
+
+def f64(bits):
+    return np.int64(bits).view(np.float64)
+
+
+def unpack(bits, shape):
+    n = int(np.prod(shape))
+    return np.unpackbits(bits)[:n].reshape(shape).astype(np.float32)
+
+
+def test_layouts_match_reference(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "layouts.npz"))
+    for name, variant in (("v0", oracle_mod.V0), ("v3", oracle_mod.V3)):
+        rows = oracle_mod.layout(variant)
+        assert rows == [str(r) for r in z[name]]
+        assert hashlib.md5("/".join(rows).encode()).hexdigest() == str(z[name + "_md5"])
+    # md5 of the v0 rows
+    assert str(z["v0_md5"]).startswith("b2b870fa")
+
+
+def test_v0_transition_table_exhaustive(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v0_table.npz"))
+    tab = np.concatenate([z["table"], z["edge"]])
+    assert z["table"].shape == (72 * 5 * 4, 11)
+    o = oracle_mod.OracleVec(oracle_mod.V0, 1, autoreset=False)
+    for (x, y, a, prb, sb, nx, ny, rb, d, gd, sa) in tab:
+        o.force(0, int(x), int(y), step_count=int(sb), reward=float(f64(prb)), goal_count=3)
+        dd, _ = o.step_one(0, int(a))
+        pos, sc, gc, rw = o.export()
+        assert (pos[0, 0], pos[0, 1]) == (nx, ny)
+        assert rw.view(np.int64)[0] == rb          # f64 bit pattern, incl. -0.0 (Q2) and stale reward (Q1)
+        assert dd == d and sc[0] == sa and gc[0] - 3 == gd
+
+
+def test_v0_renders_all_positions(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v0_table.npz"))
+    o = oracle_mod.OracleVec(oracle_mod.V0, 1, autoreset=False)
+    for (x, y), bits in zip(z["positions"], z["renders"]):
+        o.force(0, int(x), int(y))
+        got = o.render_one(0)
+        assert got.dtype == np.float32 and got.shape == (4, 84, 84)
+        assert np.array_equal(got, unpack(bits, (4, 84, 84)))
+    # channel sums quoted in SURVEY.md T0
+    assert got.sum(axis=(1, 2)).tolist() == [49.0, 3528.0, 49.0, 3430.0]
+
+
+def test_v0_reset_semantics(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v0_table.npz"))
+    bx, by, rbits, sc, gc, gx, gy = z["reset_info"]
+    o = oracle_mod.OracleVec(oracle_mod.V0, 1, autoreset=False)
+    o.force(0, 4, 4, step_count=55, reward=-1.0, goal_count=5)
+    obs = o.reset(spawn=[[bx, by, -1, -1]])
+    pos, s, g, rw = o.export()
+    assert tuple(pos[0]) == (bx, by, gx, gy) and s[0] == sc and g[0] == gc
+    assert rw.view(np.int64)[0] == rbits and rbits == np.float64(-0.0).view(np.int64)
+    assert np.array_equal(obs[0], unpack(z["reset_obs"], (4, 84, 84)))
+    # the reference rejected (2,2) [wall] and (5,5) [goal] before accepting (10,10)
+    assert tuple(z["reject_info"][:2]) == (10, 10)
+    L = oracle_mod.lib()
+    e = o._env(0)
+    assert L.lmzo_reset(e, 2, 2, -1, -1) == -1 and L.lmzo_reset(e, 5, 5, -1, -1) == -1
+    assert L.lmzo_reset(e, 10, 10, -1, -1) == 0
+
+
+@pytest.mark.parametrize("variant_name", ["v0", "v3"])
+def test_traces(oracle_mod, golden_dir, variant_name):
+    variant = oracle_mod.V0 if variant_name == "v0" else oracle_mod.V3
+    shape = oracle_mod.OBS_SHAPE[variant]
+    z = np.load(os.path.join(golden_dir, variant_name + "_traces.npz"))
+    ne = int(z["n_envs"])
+    o = oracle_mod.OracleVec(variant, ne, autoreset=True)
+    sp0 = np.stack([z["e%d_spawn0" % e] for e in range(ne)])
+    if variant == oracle_mod.V0:
+        sp0 = np.concatenate([sp0, -np.ones_like(sp0)], axis=1)
+    o.reset(spawn=sp0)
+    T = len(z["e0_actions"])
+    for t in range(T):
+        acts = np.array([z["e%d_actions" % e][t] for e in range(ne)])
+        spawn = np.stack([z["e%d_spawn" % e][t] for e in range(ne)])
+        if variant == oracle_mod.V0:
+            spawn = np.concatenate([spawn, -np.ones_like(spawn)], axis=1)
+        dones_ref = np.array([z["e%d_done" % e][t] for e in range(ne)])
+        spawn = np.where(dones_ref[:, None] > 0, spawn, 1)      # unused rows: any value
+        # pre-reset positions are checked through a non-resetting twin below; here: outputs
+        obs, rew, done = o.step(acts, spawn=spawn)
+        for e in range(ne):
+            ref_r = np.float32(f64(z["e%d_reward_bits" % e][t]))
+            assert rew[e].view(np.uint32) == ref_r.view(np.uint32), (t, e)
+            assert done[e] == dones_ref[e], (t, e)
+            assert np.array_equal(obs[e], unpack(z["e%d_obs" % e][t], shape)), (t, e)
+            if not done[e]:
+                pos = o.export()[0][e]
+                assert tuple(pos[:z["e%d_pos" % e].shape[1]]) == tuple(z["e%d_pos" % e][t]), (t, e)
+                assert o.export()[1][e] == z["e%d_step_count" % e][t]
+    assert o.stats[1] == sum(int(z["e%d_done" % e].sum()) for e in range(ne))
+    assert o.stats[1] >= 2 * ne       # every env finished at least two episodes
+
+
+def test_v0_real_mt_trace(oracle_mod, golden_dir):
+    """BASELINE config-1-style run: spawns came from the reference's own MT19937 stream."""
+    z = np.load(os.path.join(golden_dir, "v0_traces.npz"))
+    o = oracle_mod.OracleVec(oracle_mod.V0, 1, autoreset=True)
+    o.reset(spawn=[[z["mt_spawn0"][0], z["mt_spawn0"][1], -1, -1]])
+    goal_bits = np.float32(100.0).view(np.uint32)
+    for t in range(len(z["mt_actions"])):
+        sp = z["mt_spawn"][t]
+        spawn = [[sp[0], sp[1], -1, -1]] if z["mt_done"][t] else [[1, 1, -1, -1]]
+        _, rew, done = o.step([z["mt_actions"][t]], spawn=spawn, want_obs=False)
+        assert rew.view(np.uint32)[0] == np.float32(f64(z["mt_reward_bits"][t])).view(np.uint32)
+        assert done[0] == z["mt_done"][t]
+        if not done[0]:
+            assert tuple(o.export()[0][0][:2]) == tuple(z["mt_pos"][t])
+        elif rew.view(np.uint32)[0] == goal_bits:
+            pass
+    assert z["mt_done"].sum() >= 5
+
+
+def test_v3_transition_table(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v3_table.npz"))
+    tab = np.concatenate([z["table"], z["edge"]])
+    assert len(z["table"]) == 6 * 73 * 5
+    o = oracle_mod.OracleVec(oracle_mod.V3, 1, autoreset=False)
+    for (bx, by, gx, gy, a, sb, nx, ny, rb, d, sa) in tab:
+        o.force(0, int(bx), int(by), int(gx), int(gy), step_count=int(sb))
+        dd, _ = o.step_one(0, int(a))
+        pos, sc, _, rw = o.export()
+        assert tuple(pos[0]) == (nx, ny, gx, gy)
+        assert rw.view(np.int64)[0] == rb
+        assert dd == d and sc[0] == sa
+
+
+def test_v3_renders(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v3_table.npz"))
+    o = oracle_mod.OracleVec(oracle_mod.V3, 1, autoreset=False)
+    for (bx, by, gx, gy), bits in zip(z["render_keys"], z["renders"]):
+        o.force(0, int(bx), int(by), int(gx), int(gy))
+        assert np.array_equal(o.render_one(0), unpack(bits, (3, 72, 72)))
+    bx, by, gx, gy, sc = z["reset_info"]
+    obs = o.reset(spawn=[[bx, by, gx, gy]])
+    assert np.array_equal(obs[0], unpack(z["reset_obs"], (3, 72, 72)))
+    assert tuple(z["test_info"]) == (7, 8, 8, 8)       # reset(mode="test") cells
+    o.force(0, 7, 8, 8, 8)
+    assert np.array_equal(o.render_one(0), unpack(z["test_obs"], (3, 72, 72)))
+
+
+def test_philox_known_answers(oracle_mod):
+    # Random123 known-answer vectors for philox4x32-10
+    assert [hex(v) for v in oracle_mod.philox([0] * 4, [0] * 2)] == \
+        ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(v) for v in oracle_mod.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)] == \
+        ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(v) for v in oracle_mod.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                                              [0xa4093822, 0x299f31d0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_rng_spawn_distribution(oracle_mod):
+    rows = oracle_mod.layout(oracle_mod.V0)
+    counts = {}
+    for i in range(7100):
+        sx, sy, gx, gy = oracle_mod.rng_spawn(oracle_mod.V0, 99, i, 0)
+        assert rows[sx][sy] in "BS"
+        counts[(sx, sy)] = counts.get((sx, sy), 0) + 1
+    assert len(counts) == 71 and min(counts.values()) > 50 and max(counts.values()) < 160
+    rows3 = oracle_mod.layout(oracle_mod.V3)
+    for i in range(500):
+        sx, sy, gx, gy = oracle_mod.rng_spawn(oracle_mod.V3, 5, i, 2)
+        assert rows3[sx][sy] != "W" and rows3[gx][gy] != "W" and (sx, sy) != (gx, gy)
+    acts = [oracle_mod.rng_action(1, 2, t) for t in range(4000)]
+    assert sorted(set(acts)) == [0, 1, 2, 3] and min(np.bincount(acts)) > 850
