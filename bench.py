@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of the fused LMaze step at 1M envs per B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: the fused kernel (action
+decode, wall lookup, move, reward, done, auto-reset, full f32 observation render,
+statistics) over every env of the rank's shard.  Workload = BASELINE.json
+configs[2] ("lmaze_env_v0 1M envs, fused step+auto-reset+obs render on 1xB200"),
+N = 2^20 envs PER GPU (weak scaling, one process per GPU, no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with the action
+stream already resident in HBM; `e2e` = the same metric through the host-buffer
+C-ABI call lmz_step_host (pinned host actions -> H2D -> fused step -> D2H
+reward/done), observations staying in HBM where the policy consumes them (DLPack).
+`--impl reference` times the CPU oracle port (the reference's algorithm in C,
+oracle/) on all host threads; the reference itself is pure Python and cannot
+travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V0_OBS_BYTES = 4 * 84 * 84 * 4
+# algorithmic bytes per env-step of the fused v0 step (SURVEY.md section 8d / DESIGN.md):
+# obs write + u8 action read + packed state read + write + f32 reward write + u8 done write
+V0_STEP_BYTES = V0_OBS_BYTES + 1 + 4 + 4 + 4 + 1
+V3_OBS_BYTES = 3 * 72 * 72 * 4
+V3_STEP_BYTES = V3_OBS_BYTES + 1 + 4 + 4 + 4 + 1
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--variant", default="v0", choices=["v0", "v3"])
+    ap.add_argument("--render-mode", default="tma", choices=["tma", "st128"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rollout / obs-to-host side measurements")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(variant, render_mode):
+    """dram bytes per launch from the committed `ncu --set full` capture, if any."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return rec.get("%s_%s" % (variant, render_mode))
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)
+def cpu_oracle_throughput(variant, n_envs, threads, budget_s, min_steps=2):
+    """Steps/s of the C oracle port (full step + auto-reset + f32 render) on `threads` host threads."""
+    import numpy as np
+    from oracle import oracle as O
+    ov = O.V0 if variant == "v0" else O.V3
+    vec = O.OracleVec(ov, n_envs, seed=1, autoreset=True, threads=threads)
+    obs = np.empty((n_envs,) + O.OBS_SHAPE[ov], dtype=np.float32)
+    vec.reset(want_obs=False)
+    rng = np.random.RandomState(1)
+    acts = rng.randint(0, 4, size=(8, n_envs)).astype(np.int64)
+    vec.step(acts[0], obs_out=obs)          # warm (touch pages)
+    t0 = time.perf_counter()
+    k = 0
+    while k < min_steps or time.perf_counter() - t0 < budget_s:
+        vec.step(acts[k % 8], obs_out=obs)
+        k += 1
+    dt = time.perf_counter() - t0
+    return n_envs * k / dt, k, dt
+
+
+def python_loop_throughput(n_steps=40):
+    """The reference's implementation STYLE (interpreted per-pixel loop) on this host, 1 core."""
+    from oracle import oracle as O
+    from oracle.pyloop import PyLoopV0
+    import random
+    env = PyLoopV0(O.layout(O.V0), (1, 1))
+    rng = random.Random(1)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        _, _, d, _ = env.step(rng.randrange(4))
+        if d:
+            env.reset((1, 1))
+    return n_steps / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU arm.  Rank 0 only; other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    threads = os.cpu_count() or 1
+    sample_envs = 32768
+    ov = O.V0 if args.variant == "v0" else O.V3
+    import numpy as np
+    vec = O.OracleVec(ov, sample_envs, seed=1, autoreset=True, threads=threads)
+    obs = np.empty((sample_envs,) + O.OBS_SHAPE[ov], dtype=np.float32)
+    vec.reset(want_obs=False)
+    acts = np.random.RandomState(1).randint(0, 4, size=(8, sample_envs)).astype(np.int64)
+    for i in range(args.warmup):
+        vec.step(acts[i % 8], obs_out=obs)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        vec.step(acts[i % 8], obs_out=obs)
+    dt = time.perf_counter() - t0
+    value = sample_envs * args.steps / dt
+    sample = ("%d-env slice of the %d-env workload per step (full step + auto-reset + f32 obs render), "
+              "C oracle port of the reference algorithm, %d pthreads" % (sample_envs, args.envs, threads))
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, note="CPU arm: bounded sample per step"),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, note=None):
+    cfg = {
+        "workload": "lmaze_env_%s %d envs/GPU, fused step+auto-reset+obs render (BASELINE configs[2], HBM roofline run)"
+                    % (args.variant, args.envs),
+        "variant": args.variant, "envs_per_gpu": args.envs, "obs": "f32 (4,84,84) full render" if args.variant == "v0"
+        else "f32 (3,72,72) full render", "actions": "u8 ring [4,N] resident in HBM", "render_mode": args.render_mode,
+        "autoreset": True, "l2": "no flush needed: each step streams %.1f GB of obs, >> 126 MB L2"
+                                 % (args.envs * (V0_OBS_BYTES if args.variant == "v0" else V3_OBS_BYTES) / 1e9),
+    }
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import gym_lmaze_b200 as lmz          # raises if the CUDA library is missing: no fallback
+    N = args.envs
+    step_bytes = V0_STEP_BYTES if args.variant == "v0" else V3_STEP_BYTES
+    env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, env_id0=rank * N, autoreset=True,
+                           render_mode=args.render_mode)
+    R = 4
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ring = torch.randint(0, 4, (R, N), generator=gen, device=dev, dtype=torch.uint8)
+    env.reset()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident inputs: K launches of the fused kernel, CUDA events on the launch stream
+    for i in range(args.warmup):
+        env.step(ring[i % R])
+    launches0 = env.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        env.step(ring[i % R])
+        evs[i + 1].record()
+    barrier()
+    total_ms = reduce_max(evs[0].elapsed_time(evs[-1]))
+    gpu_launches = env.launch_count - launches0
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * N * args.steps / (total_ms * 1e-3)
+    kernel_ms = total_ms / args.steps            # one kernel launch per step: step time == kernel time
+    achieved = N * step_bytes / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory)
+    a_host = torch.randint(0, 4, (R, N), dtype=torch.uint8).pin_memory()
+    r_host = torch.empty(N, dtype=torch.float32).pin_memory()
+    d_host = torch.empty(N, dtype=torch.uint8).pin_memory()
+    for i in range(max(3, args.warmup)):
+        env.step_host(a_host[i % R], r_host, d_host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        env.step_host(a_host[i % R], r_host, d_host)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = reduce_max(max(e0.elapsed_time(e1), wall_ms))
+    e2e_value = world * N * args.steps / (e2e_ms * 1e-3)
+    checksum = float(r_host.sum())               # the host really consumes the result
+
+    extras = {}
+    if not args.no_extras and rank == 0 and world == 1:
+        extras = side_measurements(env, args, torch, dev)
+
+    stats = env.stats_allreduce() if world > 1 else env.stats()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    line = {
+        "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N, "d2h_bytes_per_step": 5 * N,
+                "ms_per_step": e2e_ms / args.steps, "api": "LmazeVecCuda.step_host -> lmz_step_host (C ABI)",
+                "obs": "device-resident (consumed on the GPU via DLPack); see extras.e2e_obs_to_host for the "
+                       "full obs D2H variant", "reward_checksum": checksum},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": recorded_traffic(args.variant, args.render_mode), "peak_source": peak_src,
+                     "kernel": "lmz_env_kernel<%s,%s>" % (args.variant.upper(), args.render_mode),
+                     "bytes_per_env_step": step_bytes, "bytes_per_launch": N * step_bytes,
+                     "kernel_ms_avg": kernel_ms, "kernel_ms_min": per_step[0],
+                     "kernel_ms_median": per_step[len(per_step) // 2]},
+        "episode_stats": stats,
+    }
+    if extras:
+        line["extras"] = extras
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as O
+        O.build()
+        P = os.cpu_count() or 1
+        v_all, k_all, dt_all = cpu_oracle_throughput(args.variant, 16384, P, args.cpu_budget)
+        v_one, k_one, dt_one = cpu_oracle_throughput(args.variant, 2048, 1, min(4.0, args.cpu_budget))
+        line["cpu_baseline"] = {
+            "value": v_all, "unit": "env-steps/s", "cores": P, "kind": "port",
+            "sample": "%d steps of a 16384-env slice of the workload (%.1f s), C oracle port, %d pthreads"
+                      % (k_all, dt_all, P),
+            "single_core": {"value": v_one, "sample": "%d steps x 2048 envs (%.1f s)" % (k_one, dt_one)},
+            "python_loop": {"value": python_loop_throughput(), "cores": 1,
+                            "sample": "40 steps of the interpreted per-pixel loop restatement (oracle/pyloop.py), "
+                                      "the reference's implementation style; survey-time probe of the real "
+                                      "reference: ~40 env-steps/s/core"},
+        }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def side_measurements(env, args, torch, dev):
+    """Other operating points, each named with its own mode (never mixed into `value`)."""
+    out = {}
+    N = env.num_envs
+    # (1) BASELINE configs[4]-style: T=64 fused rollout, device-side Philox actions, no per-step obs
+    T = 64
+    rew = torch.empty((T, N), dtype=torch.float32, device=dev)
+    don = torch.empty((T, N), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        env.rollout(T, rewards=rew, dones=don)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        env.rollout(T, rewards=rew, dones=don)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    out["rollout_T64"] = {"value": N * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_rollout": ms, "envs": N,
+                          "mode": "lmz_rollout_kernel, no per-step obs, device Philox actions, reward f32 + done u8 "
+                                  "[T,N] written", "bytes_per_env_step": 5.25,
+                          "achieved_gbs": N * T * 5.25 / (ms * 1e-3) / 1e9}
+    del rew, don
+    # (2) e2e including the full observation D2H, on a bounded slice (PCIe-bound by construction)
+    try:
+        import gym_lmaze_b200 as lmz
+        n2 = 16384
+        env2 = lmz.LmazeVecCuda(n2, args.variant, device=dev, seed=1, render_mode=args.render_mode)
+        env2.reset()
+        a = torch.randint(0, 4, (n2,), dtype=torch.uint8).pin_memory()
+        r = torch.empty(n2, dtype=torch.float32).pin_memory()
+        d = torch.empty(n2, dtype=torch.uint8).pin_memory()
+        o = torch.empty((n2,) + env2.obs_shape, dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            env2.step_host(a, r, d, o)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            env2.step_host(a, r, d, o)
+        dt = (time.perf_counter() - t0) / reps
+        out["e2e_obs_to_host"] = {"value": n2 / dt, "unit": "env-steps/s", "envs": n2,
+                                  "d2h_bytes_per_step": n2 * (o[0].numel() * 4 + 5),
+                                  "d2h_gbs": n2 * o[0].numel() * 4 / dt / 1e9,
+                                  "mode": "lmz_step_host with obs_host: every obs byte copied to pinned host memory"}
+        env2.close()
+    except Exception as exc:  # pragma: no cover
+        out["e2e_obs_to_host"] = {"error": repr(exc)}
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

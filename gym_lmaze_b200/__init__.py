@@ -1,0 +1,54 @@
+"""gym_lmaze_b200 -- B200-native batched LMaze step/reset (drop-in for the hot path of gkm2708/gym-lmaze).
+
+Keeps the reference's registration ids (reference gym_lmaze/__init__.py:3-38) for the
+variants that are built and adds vectorised ids.  `make(id, num_envs=...)` works without
+gym; when gym or gymnasium is importable the ids are registered there as well.
+"""
+from .envs import LmazeVecCuda, shard_range, allreduce_stats, INVALID_ACTION  # noqa: F401
+
+__version__ = "0.1.0"
+
+# id -> (variant, default kwargs).  'lmaze-vK' are the reference's ids; 'lmaze-vec-vK' the batched ones.
+_REGISTRY = {}
+
+
+def register(id, variant, **defaults):
+    _REGISTRY[id] = (variant, defaults)
+
+
+def make(id, **kwargs):
+    if id not in _REGISTRY:
+        raise KeyError("unknown env id %r; built ids: %s" % (id, ", ".join(sorted(_REGISTRY))))
+    variant, defaults = _REGISTRY[id]
+    kw = dict(defaults)
+    kw.update(kwargs)
+    return LmazeVecCuda(variant=variant, **kw)
+
+
+def registered_ids():
+    return sorted(_REGISTRY)
+
+
+register("lmaze-v0", "v0", num_envs=1)
+register("lmaze-v3", "v3", num_envs=1)
+register("lmaze-vec-v0", "v0", num_envs=4096)
+register("lmaze-vec-v3", "v3", num_envs=4096)
+
+
+def _register_with_gym():
+    for modname in ("gymnasium", "gym"):
+        try:
+            mod = __import__(modname + ".envs.registration", fromlist=["register"])
+            if not hasattr(__import__(modname), "__version__"):
+                continue
+            for env_id, (variant, defaults) in _REGISTRY.items():
+                try:
+                    mod.register(id=env_id, entry_point="gym_lmaze_b200:LmazeVecCuda",
+                                 kwargs=dict(defaults, variant=variant))
+                except Exception:
+                    pass
+        except Exception:
+            continue
+
+
+_register_with_gym()

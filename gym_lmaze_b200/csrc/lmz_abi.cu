@@ -1,0 +1,592 @@
+// lmz_abi.cu -- C-ABI shim of the batched LMaze path (include/lmaze_b200.h).
+//
+// Host side only does bookkeeping: handle lifecycle, argument / DLPack
+// validation, template-blob construction and kernel launches on the caller's
+// stream.  No torch types, no exceptions across the boundary, no hidden syncs on
+// the step path, and NO CPU implementation of the env -- if there is no CUDA
+// device lmz_create fails.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/lmaze_b200.h"
+#include "lmz_kernels.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ error plumbing
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define LMZ_CUDA(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return fail(LMZ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------ mazes
+// Cell letters as in the reference: W wall, B blank, S start, X goal.
+// v0: lmaze_env.py:37-48.  v3: lmaze_env_v3.py:26-43.  tests/test_layouts.py checks
+// both against the golden extraction from the reference.
+const char V0_CELLS[] =
+    "WWWWWWWWWWWW" "WSBBBBBBBBBW" "WBWWBWWWWWBW" "WBBBWBBBBBBW" "WBBWBBBWWWBW" "WBWBWXWBBBBW"
+    "WBBBWBBWWBBW" "WBWBWBBBBWBW" "WBWBBBWBBBBW" "WBBWWWBBWWBW" "WBBBBBBBBBBW" "WWWWWWWWWWWW";
+const char V3_CELLS[] =
+    "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW"
+    "WWWWSBBBWBBBBBWWWW" "WWWWBWWWWBWWBBWWWW" "WWWWBWBBBBBWBBWWWW" "WWWWBWBBBBBWBBWWWW"
+    "WWWWBBBBXBBWWWWWWW" "WWWWBWBBBBBWBBWWWW" "WWWWBWBBBBBWBBWWWW" "WWWWBWBBBBBWBBWWWW"
+    "WWWWBWWWWWBWBBWWWW" "WWWWBBBBWBBBBBWWWW" "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW"
+    "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW";
+
+const char *cells_of(int variant) {
+  if (variant == LMZ_V0) return V0_CELLS;
+  if (variant == LMZ_V3) return V3_CELLS;
+  return nullptr;
+}
+
+int cls_of(char c) {
+  switch (c) {
+    case 'W': return lmz::CLS_W;
+    case 'B': return lmz::CLS_B;
+    case 'X': return lmz::CLS_X;
+    default: return lmz::CLS_S;
+  }
+}
+
+// Host construction of the template blob (layout documented in lmz_variants.h).
+template <class V>
+void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand, int &s_cell, int &x_cell) {
+  blob.assign(V::BLOB_BYTES, 0);
+  auto plane = [&](uint32_t off, auto pred) {   // upsampled ExE mask of `pred(cell)`
+    float *f = reinterpret_cast<float *>(blob.data() + off);
+    for (int i = 0; i < V::G; ++i)
+      for (int j = 0; j < V::G; ++j)
+        if (pred(cells[i * V::G + j]))
+          for (int ii = 0; ii < V::E; ++ii)
+            for (int jj = 0; jj < V::E; ++jj) f[(i * V::E + ii) * V::S + j * V::E + jj] = 1.0f;
+  };
+  if (V::ID == 0) {
+    plane(V::STATIC_OFF + 0 * V::PLANE_BYTES, [](char c) { return c == 'W'; });   // lmaze_env.py:92-94
+    plane(V::STATIC_OFF + 1 * V::PLANE_BYTES, [](char c) { return c == 'X'; });   // :96-98
+    plane(V::STATIC_OFF + 2 * V::PLANE_BYTES, [](char c) { return c == 'B'; });   // :105-107
+  } else {
+    plane(V::STATIC_OFF, [](char c) { return c == 'B' || c == 'S' || c == 'X'; });  // lmaze_env_v3.py:166
+  }
+  for (int y = 0; y < V::G; ++y) {   // band table: E rows with ones in columns [E*y, E*y+E)
+    float *f = reinterpret_cast<float *>(blob.data() + V::BAND_OFF + y * V::BAND_BYTES);
+    for (int ii = 0; ii < V::E; ++ii)
+      for (int jj = 0; jj < V::E; ++jj) f[ii * V::S + y * V::E + jj] = 1.0f;
+  }
+  uint16_t *cand = reinterpret_cast<uint16_t *>(blob.data() + V::CAND_OFF);
+  n_cand = 0; s_cell = 0; x_cell = 0;
+  for (int i = 0; i < V::G * V::G; ++i) {
+    const char c = cells[i];
+    blob[V::CLS_OFF + i] = (unsigned char)cls_of(c);
+    if (c == 'S' && s_cell == 0) s_cell = i;
+    if (c == 'X' && x_cell == 0) x_cell = i;
+    // spawn candidates: v0 not in {W,X} (lmaze_env.py:73); v3 not W (lmaze_env_v3.py:148,157)
+    const bool ok = (V::ID == 0) ? (c != 'W' && c != 'X') : (c != 'W');
+    if (ok && n_cand < V::MAX_CAND) cand[n_cand++] = (uint16_t)i;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+struct lmz_env {
+  lmz_config cfg;
+  int G, C, S;
+  size_t obs_bytes_per_env;
+  int num_sms;
+  // device memory owned by the handle
+  uint32_t *state, *goal_count, *episode;
+  unsigned char *blob;
+  unsigned long long *stats;     // NUM_STATS counters + 1 error counter
+  void *act_stage;               // lmz_step_host staging, lazily allocated (N * 8 bytes)
+  // bound outputs (caller-owned)
+  float *obs, *reward;
+  uint8_t *done;
+  bool bound;
+  int n_cand, s_cell, x_cell;
+  uint64_t rollout_t;            // rollout steps taken so far (keys the action RNG)
+  int64_t launches;
+};
+
+namespace {
+
+struct DeviceGuard {   // run on the handle's device, restore the caller's on exit
+  int prev;
+  bool changed;
+  explicit DeviceGuard(int dev) : prev(-1), changed(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
+lmz::KParams base_params(lmz_env *h) {
+  lmz::KParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = h->cfg.num_envs;
+  p.state = h->state; p.goal_count = h->goal_count; p.episode = h->episode;
+  p.obs = h->obs; p.reward = h->reward; p.done = h->done;
+  p.blob = h->blob; p.stats = h->stats;
+  p.errors = reinterpret_cast<unsigned int *>(h->stats + lmz::NUM_STATS);
+  p.seed = h->cfg.seed; p.env_id0 = (uint64_t)h->cfg.env_id0;
+  p.autoreset = h->cfg.autoreset; p.random_ball = h->cfg.random_ball; p.random_goal = h->cfg.random_goal;
+  p.n_cand = h->n_cand; p.s_cell = h->s_cell;
+  return p;
+}
+
+constexpr int TMA_THREADS = 128;     // 4 warps: the TMA engine does the moving
+constexpr int ST_THREADS = 1024;     // 32 warps of vector stores per SM
+
+template <class V, int RENDER, int THREADS>
+int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  auto kern = lmz::lmz_env_kernel<V, RENDER, THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V::BLOB_BYTES));
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, V::BLOB_BYTES));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "env kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  const int64_t tiles = (p.n + 31) / 32;
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;      // persistent: a whole number of CTAs per SM
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, V::BLOB_BYTES, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+template <class V>
+int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.render_mode == LMZ_RENDER_ST128 && p.obs != nullptr)
+    return launch_env_t<V, lmz::RENDER_ST128, ST_THREADS>(h, p, s);
+  return launch_env_t<V, lmz::RENDER_TMA, TMA_THREADS>(h, p, s);
+}
+
+int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.variant == LMZ_V0) return launch_env_v<lmz::V0>(h, p, s);
+  return launch_env_v<lmz::V3>(h, p, s);
+}
+
+template <class V>
+int launch_rollout_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  constexpr int THREADS = 256;
+  int64_t blocks = (p.n + THREADS - 1) / THREADS;
+  const int64_t cap = (int64_t)h->num_sms * 8;            // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  lmz::lmz_rollout_kernel<V, THREADS><<<(unsigned)blocks, THREADS, 0, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+int check_handle(lmz_env *h) {
+  if (!h) return fail(LMZ_ERR_INVALID, "env handle is NULL");
+  return LMZ_OK;
+}
+
+int check_bound(lmz_env *h) {
+  if (!h->bound) return fail(LMZ_ERR_STATE, "output buffers not bound: call lmz_bind first");
+  return LMZ_OK;
+}
+
+// ---- DLPack validation -----------------------------------------------------
+struct Want {
+  const char *name;
+  uint8_t code;      // DLDataTypeCode, or 255 = any integer action type
+  uint8_t bits;
+  int ndim;
+  int64_t shape[4];
+  bool host_ok;
+  int align;        // required alignment of the data pointer in bytes
+};
+
+int check_dl(const lmz_env *h, const DLManagedTensor *mt, const Want &w, void **data, int *action_dtype) {
+  if (!mt) return fail(LMZ_ERR_INVALID, "%s: DLManagedTensor is NULL", w.name);
+  const DLTensor &t = mt->dl_tensor;
+  if (t.device.device_type == kDLCUDA || t.device.device_type == kDLCUDAManaged) {
+    if (t.device.device_id != h->cfg.device)
+      return fail(LMZ_ERR_INVALID, "%s: tensor is on cuda:%d, env is on cuda:%d", w.name, t.device.device_id,
+                  h->cfg.device);
+  } else if (!(w.host_ok && (t.device.device_type == kDLCUDAHost || t.device.device_type == kDLCPU))) {
+    return fail(LMZ_ERR_INVALID, "%s: tensor must live on the CUDA device (device_type %d)", w.name,
+                t.device.device_type);
+  }
+  if (t.dtype.lanes != 1) return fail(LMZ_ERR_INVALID, "%s: vector dtypes not supported", w.name);
+  if (w.code == 255) {
+    int ad = -1;
+    if ((t.dtype.code == kDLUInt || t.dtype.code == kDLBool) && t.dtype.bits == 8) ad = LMZ_ACT_U8;
+    else if (t.dtype.code == kDLInt && t.dtype.bits == 32) ad = LMZ_ACT_I32;
+    else if (t.dtype.code == kDLInt && t.dtype.bits == 64) ad = LMZ_ACT_I64;
+    if (ad < 0)
+      return fail(LMZ_ERR_INVALID, "%s: dtype must be uint8, int32 or int64 (got code %d bits %d)", w.name,
+                  t.dtype.code, t.dtype.bits);
+    if (action_dtype) *action_dtype = ad;
+  } else {
+    const bool u8_like = (w.code == kDLUInt && w.bits == 8) &&
+                         ((t.dtype.code == kDLUInt || t.dtype.code == kDLBool) && t.dtype.bits == 8);
+    if (!u8_like && (t.dtype.code != w.code || t.dtype.bits != w.bits))
+      return fail(LMZ_ERR_INVALID, "%s: wrong dtype (got code %d bits %d, want code %d bits %d)", w.name,
+                  t.dtype.code, t.dtype.bits, w.code, w.bits);
+  }
+  if (t.ndim != w.ndim) return fail(LMZ_ERR_INVALID, "%s: ndim %d, want %d", w.name, t.ndim, w.ndim);
+  int64_t expect_stride = 1;
+  for (int d = w.ndim - 1; d >= 0; --d) {
+    if (t.shape[d] != w.shape[d])
+      return fail(LMZ_ERR_INVALID, "%s: shape[%d] = %lld, want %lld", w.name, d, (long long)t.shape[d],
+                  (long long)w.shape[d]);
+    if (t.strides && t.shape[d] > 1 && t.strides[d] != expect_stride)
+      return fail(LMZ_ERR_INVALID, "%s: tensor must be contiguous (stride[%d] = %lld, want %lld)", w.name, d,
+                  (long long)t.strides[d], (long long)expect_stride);
+    expect_stride *= t.shape[d];
+  }
+  unsigned char *ptr = static_cast<unsigned char *>(t.data) + t.byte_offset;
+  if ((reinterpret_cast<uintptr_t>(ptr) % (uintptr_t)w.align) != 0)
+    return fail(LMZ_ERR_INVALID, "%s: data pointer must be %d-byte aligned", w.name, w.align);
+  *data = ptr;
+  return LMZ_OK;
+}
+
+}  // namespace
+
+// ================================================================== exports
+extern "C" {
+
+int lmz_abi_version(void) { return LMZ_ABI_VERSION; }
+
+const char *lmz_last_error(void) { return g_err; }
+
+void lmz_default_config(lmz_config *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = (int32_t)sizeof(lmz_config);
+  cfg->variant = LMZ_V0;
+  cfg->num_envs = 1;
+  cfg->autoreset = 1;
+  cfg->random_ball = 1;     // lmaze_env.py:25
+  cfg->random_goal = 1;     // lmaze_env_v3.py:104
+  cfg->render_mode = LMZ_RENDER_TMA;
+}
+
+int lmz_obs_shape(int32_t variant, int64_t shape[3]) {
+  if (!shape) return fail(LMZ_ERR_INVALID, "shape is NULL");
+  if (variant == LMZ_V0) { shape[0] = lmz::V0::C; shape[1] = shape[2] = lmz::V0::S; return LMZ_OK; }
+  if (variant == LMZ_V3) { shape[0] = lmz::V3::C; shape[1] = shape[2] = lmz::V3::S; return LMZ_OK; }
+  return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+}
+
+int lmz_grid_size(int32_t variant) {
+  if (variant == LMZ_V0) return lmz::V0::G;
+  if (variant == LMZ_V3) return lmz::V3::G;
+  return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+}
+
+int lmz_layout(int32_t variant, char *cells) {
+  const char *c = cells_of(variant);
+  if (!c) return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+  if (!cells) return fail(LMZ_ERR_INVALID, "cells is NULL");
+  const int G = lmz_grid_size(variant);
+  memcpy(cells, c, (size_t)G * G);
+  return LMZ_OK;
+}
+
+int lmz_create(const lmz_config *cfg, lmz_env **out) {
+  if (!cfg || !out) return fail(LMZ_ERR_INVALID, "cfg/out is NULL");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(lmz_config))
+    return fail(LMZ_ERR_INVALID, "lmz_config.struct_size %d != %d: header/library mismatch", cfg->struct_size,
+                (int)sizeof(lmz_config));
+  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3)
+    return fail(LMZ_ERR_UNSUPPORTED, "variant %d is not built (supported: 0 = lmaze-v0, 3 = lmaze-v3)", cfg->variant);
+  if (cfg->num_envs < 1) return fail(LMZ_ERR_INVALID, "num_envs must be >= 1 (got %lld)", (long long)cfg->num_envs);
+  if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
+  if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128)
+    return fail(LMZ_ERR_INVALID, "unknown render_mode %d", cfg->render_mode);
+  for (int i = 0; i < 7; ++i)
+    if (cfg->reserved[i] != 0) return fail(LMZ_ERR_INVALID, "lmz_config.reserved must be zero");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(LMZ_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(LMZ_ERR_INVALID, "device %d out of range", cfg->device);
+  DeviceGuard guard(cfg->device);
+  cudaDeviceProp prop;
+  LMZ_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10)
+    return fail(LMZ_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                prop.major, prop.minor);
+
+  lmz_env *h = new (std::nothrow) lmz_env();
+  if (!h) return fail(LMZ_ERR_INVALID, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
+  std::vector<unsigned char> blob;
+  if (cfg->variant == LMZ_V0) {
+    h->G = lmz::V0::G; h->C = lmz::V0::C; h->S = lmz::V0::S; h->obs_bytes_per_env = lmz::V0::OBS_BYTES;
+    build_blob<lmz::V0>(V0_CELLS, blob, h->n_cand, h->s_cell, h->x_cell);
+  } else {
+    h->G = lmz::V3::G; h->C = lmz::V3::C; h->S = lmz::V3::S; h->obs_bytes_per_env = lmz::V3::OBS_BYTES;
+    build_blob<lmz::V3>(V3_CELLS, blob, h->n_cand, h->s_cell, h->x_cell);
+  }
+  const size_t n = (size_t)cfg->num_envs;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&h->state, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->goal_count, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->episode, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->blob, blob.size());
+  if (e == cudaSuccess) e = cudaMalloc(&h->stats, (lmz::NUM_STATS + 1) * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->goal_count, 0, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->episode, 0, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->stats, 0, (lmz::NUM_STATS + 1) * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpy(h->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    // Before the first reset every env sits on the 'S' cell with the goal on 'X'
+    // (lmaze_env_v3.py:119-123 starts at 0,0; any in-range cell keeps the kernels' +-1 lookups in the table).
+    lmz::EnvRegs r;
+    r.x = h->s_cell / h->G; r.y = h->s_cell % h->G; r.gx = h->x_cell / h->G; r.gy = h->x_cell % h->G;
+    r.step = 0; r.rcode = lmz::RC_NEG_ZERO;
+    const uint32_t packed = (cfg->variant == LMZ_V0) ? lmz::V0::pack(r) : lmz::V3::pack(r);
+    std::vector<uint32_t> init(n < (1u << 20) ? n : (1u << 20), packed);
+    for (size_t off = 0; off < n && e == cudaSuccess; off += init.size()) {
+      const size_t cnt = (n - off < init.size()) ? n - off : init.size();
+      e = cudaMemcpy(h->state + off, init.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    }
+  }
+  if (e != cudaSuccess) {
+    fail(LMZ_ERR_CUDA, "device allocation/initialisation failed: %s", cudaGetErrorString(e));
+    lmz_destroy(h);
+    return LMZ_ERR_CUDA;
+  }
+  *out = h;
+  return LMZ_OK;
+}
+
+int lmz_destroy(lmz_env *h) {
+  if (!h) return LMZ_OK;
+  DeviceGuard guard(h->cfg.device);
+  cudaFree(h->state); cudaFree(h->goal_count); cudaFree(h->episode); cudaFree(h->blob); cudaFree(h->stats);
+  cudaFree(h->act_stage);
+  delete h;
+  return LMZ_OK;
+}
+
+int lmz_bind(lmz_env *h, float *obs, float *reward, uint8_t *done) {
+  if (int rc = check_handle(h)) return rc;
+  if (!reward || !done) return fail(LMZ_ERR_INVALID, "reward/done must not be NULL");
+  if ((reinterpret_cast<uintptr_t>(obs) & 15u) != 0) return fail(LMZ_ERR_INVALID, "obs must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(reward) & 3u) != 0) return fail(LMZ_ERR_INVALID, "reward must be 4-byte aligned");
+  h->obs = obs; h->reward = reward; h->done = done; h->bound = true;
+  return LMZ_OK;
+}
+
+int lmz_bind_dl(lmz_env *h, DLManagedTensor *obs, DLManagedTensor *reward, DLManagedTensor *done) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *po = nullptr, *pr = nullptr, *pd = nullptr;
+  if (obs) {
+    Want w{"obs", kDLFloat, 32, 4, {n, h->C, h->S, h->S}, false, 16};
+    if (int rc = check_dl(h, obs, w, &po, nullptr)) return rc;
+  }
+  Want wr{"reward", kDLFloat, 32, 1, {n, 0, 0, 0}, false, 4};
+  if (int rc = check_dl(h, reward, wr, &pr, nullptr)) return rc;
+  Want wd{"done", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+  if (int rc = check_dl(h, done, wd, &pd, nullptr)) return rc;
+  return lmz_bind(h, static_cast<float *>(po), static_cast<float *>(pr), static_cast<uint8_t *>(pd));
+}
+
+int lmz_reset(lmz_env *h, const uint8_t *mask, const int32_t *spawn, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_bound(h)) return rc;
+  if ((reinterpret_cast<uintptr_t>(spawn) & 15u) != 0) return fail(LMZ_ERR_INVALID, "spawn must be 16-byte aligned");
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_RESET; p.mask = mask; p.spawn = reinterpret_cast<const int4 *>(spawn);
+  return launch_env(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int lmz_reset_dl(lmz_env *h, DLManagedTensor *mask, DLManagedTensor *spawn, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pm = nullptr, *ps = nullptr;
+  if (mask) {
+    Want w{"mask", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+    if (int rc = check_dl(h, mask, w, &pm, nullptr)) return rc;
+  }
+  if (spawn) {
+    Want w{"spawn", kDLInt, 32, 2, {n, 4, 0, 0}, false, 16};
+    if (int rc = check_dl(h, spawn, w, &ps, nullptr)) return rc;
+  }
+  return lmz_reset(h, static_cast<const uint8_t *>(pm), static_cast<const int32_t *>(ps), stream);
+}
+
+int lmz_step(lmz_env *h, const void *actions, int32_t action_dtype, const int32_t *spawn, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_bound(h)) return rc;
+  if (!actions) return fail(LMZ_ERR_INVALID, "actions is NULL");
+  if (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64)
+    return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
+  if ((reinterpret_cast<uintptr_t>(spawn) & 15u) != 0) return fail(LMZ_ERR_INVALID, "spawn must be 16-byte aligned");
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_STEP; p.actions = actions; p.action_dtype = action_dtype;
+  p.spawn = reinterpret_cast<const int4 *>(spawn);
+  return launch_env(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int lmz_step_dl(lmz_env *h, DLManagedTensor *actions, DLManagedTensor *spawn, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pa = nullptr, *ps = nullptr;
+  int ad = 0;
+  Want wa{"actions", 255, 0, 1, {n, 0, 0, 0}, false, 1};
+  if (int rc = check_dl(h, actions, wa, &pa, &ad)) return rc;
+  if (spawn) {
+    Want w{"spawn", kDLInt, 32, 2, {n, 4, 0, 0}, false, 16};
+    if (int rc = check_dl(h, spawn, w, &ps, nullptr)) return rc;
+  }
+  return lmz_step(h, pa, ad, static_cast<const int32_t *>(ps), stream);
+}
+
+int lmz_step_host(lmz_env *h, const void *actions_host, int32_t action_dtype, float *reward_host,
+                  uint8_t *done_host, float *obs_host, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_bound(h)) return rc;
+  if (!actions_host || !reward_host || !done_host) return fail(LMZ_ERR_INVALID, "host buffers must not be NULL");
+  if (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64)
+    return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
+  if (obs_host && !h->obs) return fail(LMZ_ERR_STATE, "obs_host given but no device obs buffer is bound");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)h->cfg.num_envs;
+  if (!h->act_stage) LMZ_CUDA(cudaMalloc(&h->act_stage, n * 8));
+  const size_t esz = action_dtype == LMZ_ACT_U8 ? 1 : action_dtype == LMZ_ACT_I32 ? 4 : 8;
+  LMZ_CUDA(cudaMemcpyAsync(h->act_stage, actions_host, n * esz, cudaMemcpyHostToDevice, s));
+  if (int rc = lmz_step(h, h->act_stage, action_dtype, nullptr, stream)) return rc;
+  LMZ_CUDA(cudaMemcpyAsync(reward_host, h->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaMemcpyAsync(done_host, h->done, n, cudaMemcpyDeviceToHost, s));
+  if (obs_host) LMZ_CUDA(cudaMemcpyAsync(obs_host, h->obs, n * h->obs_bytes_per_env, cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaStreamSynchronize(s));
+  return LMZ_OK;
+}
+
+int lmz_render(lmz_env *h, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_bound(h)) return rc;
+  if (!h->obs) return fail(LMZ_ERR_STATE, "no obs buffer bound");
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_RENDER;
+  return launch_env(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int lmz_rollout(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype, float *rewards, uint8_t *dones,
+                void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
+  if (!rewards || !dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
+  if (actions && (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64))
+    return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_STEP; p.actions = actions; p.action_dtype = action_dtype;
+  p.reward = rewards; p.done = dones; p.obs = nullptr; p.T = T; p.t0 = h->rollout_t;
+  int rc = (h->cfg.variant == LMZ_V0) ? launch_rollout_v<lmz::V0>(h, p, static_cast<cudaStream_t>(stream))
+                                      : launch_rollout_v<lmz::V3>(h, p, static_cast<cudaStream_t>(stream));
+  if (rc == LMZ_OK) h->rollout_t += (uint64_t)T;
+  return rc;
+}
+
+int lmz_rollout_dl(lmz_env *h, int32_t T, DLManagedTensor *actions, DLManagedTensor *rewards, DLManagedTensor *dones,
+                   void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pa = nullptr, *pr = nullptr, *pd = nullptr;
+  int ad = 0;
+  if (actions) {
+    Want wa{"actions", 255, 0, 2, {T, n, 0, 0}, false, 1};
+    if (int rc = check_dl(h, actions, wa, &pa, &ad)) return rc;
+  }
+  Want wr{"rewards", kDLFloat, 32, 2, {T, n, 0, 0}, false, 4};
+  if (int rc = check_dl(h, rewards, wr, &pr, nullptr)) return rc;
+  Want wd{"dones", kDLUInt, 8, 2, {T, n, 0, 0}, false, 1};
+  if (int rc = check_dl(h, dones, wd, &pd, nullptr)) return rc;
+  return lmz_rollout(h, T, pa, ad, static_cast<float *>(pr), static_cast<uint8_t *>(pd), stream);
+}
+
+static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!io) return fail(LMZ_ERR_INVALID, "state buffer is NULL");
+  DeviceGuard guard(h->cfg.device);
+  const int64_t n = h->cfg.num_envs;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->cfg.variant == LMZ_V0)
+    lmz::lmz_state_kernel<lmz::V0><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
+  else
+    lmz::lmz_state_kernel<lmz::V3><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+int lmz_get_state(lmz_env *h, int32_t *out, void *stream) { return state_xfer(h, out, 0, stream); }
+int lmz_set_state(lmz_env *h, const int32_t *in, void *stream) {
+  return state_xfer(h, const_cast<int32_t *>(in), 1, stream);
+}
+
+static int state_xfer_dl(lmz_env *h, DLManagedTensor *t, int set, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  void *pt = nullptr;
+  Want w{"state", kDLInt, 32, 2, {h->cfg.num_envs, LMZ_ST_COLS, 0, 0}, false, 4};
+  if (int rc = check_dl(h, t, w, &pt, nullptr)) return rc;
+  return state_xfer(h, static_cast<int32_t *>(pt), set, stream);
+}
+int lmz_get_state_dl(lmz_env *h, DLManagedTensor *out, void *stream) { return state_xfer_dl(h, out, 0, stream); }
+int lmz_set_state_dl(lmz_env *h, DLManagedTensor *in, void *stream) { return state_xfer_dl(h, in, 1, stream); }
+
+int lmz_stats(lmz_env *h, int64_t *out_host, int64_t *errors_host, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out_host) return fail(LMZ_ERR_INVALID, "out_host is NULL");
+  DeviceGuard guard(h->cfg.device);
+  unsigned long long tmp[lmz::NUM_STATS + 1];
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LMZ_CUDA(cudaMemcpyAsync(tmp, h->stats, sizeof(tmp), cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < lmz::NUM_STATS; ++i) out_host[i] = (int64_t)tmp[i];
+  if (errors_host) *errors_host = (int64_t)(tmp[lmz::NUM_STATS] & 0xffffffffull);
+  return LMZ_OK;
+}
+
+int lmz_stats_reset(lmz_env *h, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  DeviceGuard guard(h->cfg.device);
+  LMZ_CUDA(cudaMemsetAsync(h->stats, 0, (lmz::NUM_STATS + 1) * sizeof(unsigned long long),
+                           static_cast<cudaStream_t>(stream)));
+  return LMZ_OK;
+}
+
+int64_t lmz_launch_count(const lmz_env *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

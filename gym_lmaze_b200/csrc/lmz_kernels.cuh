@@ -1,0 +1,464 @@
+// lmz_kernels.cuh -- sm_100a kernels of the batched LMaze step/reset path.
+//
+//   lmz_env_kernel      fused reset / step / render: one thread per env does the
+//                       transition (lmaze_env.py:146-196,246-249; lmaze_env_v3.py:
+//                       220-265,398), warp ballots feed the episode statistics, and
+//                       the observation (lmaze_env.py:208-234) is emitted either as
+//                       bulk async shared->global copies (TMA engine) or as 128-bit
+//                       vector stores, both sourced from a template blob that one
+//                       cp.async.bulk load stages into shared memory per CTA.
+//   lmz_rollout_kernel  T fused steps, state in registers, no per-step obs,
+//                       optional device-side Philox actions.
+//   lmz_state_kernel    pack / unpack of the per-env state for get/set_state.
+//
+// Nothing here is GEMM-shaped: the path is a pure HBM streaming write (112,896 B
+// per env-step for v0), so tensor cores / TMEM are deliberately unused.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lmz_variants.h"
+
+namespace lmz {
+
+enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
+enum : int { ACT_U8 = 0, ACT_I32 = 1, ACT_I64 = 2 };
+enum : int { RENDER_TMA = 0, RENDER_ST128 = 1 };
+enum : int {
+  STAT_STEPS = 0, STAT_EPISODES, STAT_GOALS, STAT_TIMEOUTS, STAT_WALL_BUMPS, STAT_MOVES, STAT_STALE,
+  STAT_EPLEN_SUM, NUM_STATS
+};
+
+struct KParams {
+  int64_t n;                    // envs in this handle
+  int mode;                     // MODE_*
+  const void *actions;          // [n] (step) or [T][n] (rollout); may be null in rollout
+  int action_dtype;
+  const int4 *spawn;            // optional injected spawn: sx, sy, gx, gy
+  const uint8_t *mask;          // reset only, optional
+  uint32_t *state;              // packed per-env state
+  uint32_t *goal_count;         // goalCount per env (v0; lmaze_env.py:24,195)
+  uint32_t *episode;            // resets so far (RNG counter)
+  float *obs;                   // [n][C][S][S] or null
+  float *reward;                // [n] or [T][n]
+  uint8_t *done;                // [n] or [T][n]
+  const uint8_t *blob;          // template blob in global memory
+  unsigned long long *stats;    // [NUM_STATS]
+  unsigned int *errors;         // rejected injected spawns
+  uint64_t seed, env_id0;
+  uint64_t t0;                  // rollout: global index of the first step
+  int T;                        // rollout length
+  int autoreset, random_ball, random_goal;
+  int n_cand;                   // entries in the spawn-candidate table
+  int s_cell;                   // linear index of the 'S' cell
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk async copy (TMA engine), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// shared -> global bulk async copy (TMA engine), tracked by the thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// streaming 128-bit store: the obs is written once and not re-read by this kernel
+__device__ __forceinline__ void st_stream_v4(void *p, const uint4 &v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// ------------------------------------------------------------------ RNG (spec in DESIGN.md; CPU twin in oracle/)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+constexpr uint32_t TAG_SPAWN = 0x53u, TAG_ACTION = 0x41u;
+
+struct WordStream {   // words 4a..4a+3 come from Philox block `a` of (seed, env, episode)
+  uint32_t c0, c1, c2, k0, k1, attempt, buf[4];
+  int have;
+  __device__ __forceinline__ void init(uint64_t seed, uint64_t gid, uint32_t episode) {
+    c0 = (uint32_t)gid; c1 = (uint32_t)(gid >> 32); c2 = episode;
+    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); attempt = 0; have = 0;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    if (have == 0) {
+      philox4x32_10(c0, c1, c2, (attempt << 8) | TAG_SPAWN, k0, k1, buf);
+      attempt += 1; have = 4;
+    }
+    const int i = 4 - have;
+    have -= 1;
+    return i == 0 ? buf[0] : i == 1 ? buf[1] : i == 2 ? buf[2] : buf[3];
+  }
+  // exactly uniform in [0, n): multiply-shift, rejecting the short low range
+  __device__ __forceinline__ uint32_t uniform(uint32_t n) {
+    const uint32_t thresh = (uint32_t)(0x100000000ull % n);
+    for (;;) {
+      const uint64_t m = (uint64_t)next() * (uint64_t)n;
+      if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ transition
+__device__ __forceinline__ long long load_action(const void *base, int dtype, int64_t idx) {
+  if (dtype == ACT_U8) return (long long)((const uint8_t *)base)[idx];
+  if (dtype == ACT_I32) return (long long)((const int32_t *)base)[idx];
+  return ((const long long *)base)[idx];
+}
+
+__device__ __forceinline__ uint32_t reward_bits(int rc) {
+  // float32 images of the reference's four possible rewards (lmaze_env.py:21-23,109)
+  return rc == RC_NEG_ZERO ? 0x80000000u : rc == RC_WALL ? 0xBF800000u : rc == RC_MOVE ? 0xBC23D70Au : 0x42C80000u;
+}
+
+struct StepOut {
+  int cls;      // branch taken: CLS_W wall, CLS_B move, CLS_X goal, CLS_S none
+  bool done;
+};
+
+// One reference step() on registers.  `cls` is the G*G cell-class table in shared memory.
+template <class V>
+__device__ __forceinline__ StepOut transition(EnvRegs &r, long long a, const uint8_t *cls, uint32_t &goal_hits) {
+  StepOut o;
+  r.step = r.step < V::STEP_SAT ? r.step + 1 : V::STEP_SAT;                 // lmaze_env.py:151
+  int ox = 0, oy = 0;                                                       // lmaze_env.py:153-170
+  if (a == 0) ox = -1; else if (a == 1) ox = 1; else if (a == 2) oy = -1; else if (a == 3) oy = 1;
+  const int t = cls[(r.x + ox) * V::G + (r.y + oy)];
+  if (V::ID == 0) {
+    if (t == CLS_W) { r.rcode = RC_WALL; }                                   // :172-174
+    else if (t == CLS_B) { r.x += ox; r.y += oy; r.rcode = RC_MOVE; }        // :176-184
+    else if (t == CLS_X) { r.x += ox; r.y += oy; r.rcode = RC_GOAL; goal_hits += 1; }  // :186-195
+    /* CLS_S: no branch -- position and reward keep their previous values */
+    o.cls = t;
+    o.done = (r.rcode == RC_GOAL) || (r.step == (uint32_t)V::STEP_LIMIT);    // :246-249 (equality)
+  } else {
+    if (t == CLS_W) { r.rcode = RC_WALL; o.cls = CLS_W; }                    // lmaze_env_v3.py:251-252
+    else {                                                                   // :255-265
+      r.x += ox; r.y += oy; r.rcode = RC_MOVE; o.cls = CLS_B;
+      if (r.x + ox == r.gx && r.y + oy == r.gy) { r.rcode = RC_GOAL; o.cls = CLS_X; }   // look-ahead
+    }
+    o.done = (r.rcode == RC_GOAL) || (r.step > (uint32_t)V::STEP_LIMIT);     // :398 (strictly greater)
+  }
+  return o;
+}
+
+// reset(): new spawn (injected or device RNG), stepCount 0, reward -0.0
+// (lmaze_env.py:70-80,109-110; lmaze_env_v3.py:143-164).
+template <class V>
+__device__ __forceinline__ void respawn(EnvRegs &r, const KParams &p, int64_t e, uint32_t &episode,
+                                        const uint8_t *cls, const uint16_t *cand) {
+  int sx, sy, gx = r.gx, gy = r.gy;
+  const int s_x = p.s_cell / V::G, s_y = p.s_cell % V::G;
+  if (p.spawn) {
+    const int4 s = p.spawn[e];
+    sx = s.x; sy = s.y;
+    bool ok = true;
+    if (V::ID == 3 && p.random_goal && s.z >= 0) {
+      const bool gok = s.z >= 1 && s.z <= V::G - 2 && s.w >= 1 && s.w <= V::G - 2 && cls[s.z * V::G + s.w] != CLS_W;
+      if (gok) { gx = s.z; gy = s.w; } else ok = false;
+    }
+    if (p.random_ball) {
+      bool bok = sx >= 1 && sx <= V::G - 2 && sy >= 1 && sy <= V::G - 2;
+      if (bok) {
+        const int c = cls[sx * V::G + sy];
+        bok = (V::ID == 0) ? (c != CLS_W && c != CLS_X) : (c != CLS_W && !(sx == gx && sy == gy));
+      }
+      if (!bok) { ok = false; sx = s_x; sy = s_y; }
+    }
+    if (!ok) atomicAdd(p.errors, 1u);
+  } else {
+    WordStream ws;
+    ws.init(p.seed, p.env_id0 + (uint64_t)e, episode);
+    if (V::ID == 0) {
+      const int k = cand[ws.uniform((uint32_t)p.n_cand)];
+      sx = k / V::G; sy = k % V::G;
+    } else {
+      const uint32_t gi = ws.uniform((uint32_t)p.n_cand);
+      uint32_t bi = ws.uniform((uint32_t)p.n_cand - 1u);
+      if (bi >= gi) bi += 1;
+      if (p.random_goal) { gx = cand[gi] / V::G; gy = cand[gi] % V::G; }
+      // if the goal is pinned the ball must still avoid it (lmaze_env_v3.py:157)
+      sx = cand[bi] / V::G; sy = cand[bi] % V::G;
+      if (!p.random_goal && sx == gx && sy == gy) { sx = cand[gi] / V::G; sy = cand[gi] % V::G; }
+    }
+  }
+  if (!p.random_ball) { sx = s_x; sy = s_y; }                               // lmaze_env.py:82-89
+  r.x = sx; r.y = sy; r.gx = gx; r.gy = gy;
+  r.step = 0; r.rcode = RC_NEG_ZERO;
+  episode += 1;
+}
+
+// ------------------------------------------------------------------ fused reset / step / render
+template <class V, int RENDER, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) lmz_env_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int WARPS = THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // Stage the template blob (static channels, zero rows, band table, cell classes,
+  // spawn candidates) with ONE bulk async load; the TMA engine signals the mbarrier.
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, V::BLOB_BYTES);
+    bulk_g2s(smem, p.blob, V::BLOB_BYTES, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const uint8_t *cls = smem + V::CLS_OFF;
+  const uint16_t *cand = reinterpret_cast<const uint16_t *>(smem + V::CAND_OFF);
+  const uint32_t blob_s = smem_addr(smem);
+
+  uint32_t c_steps = 0, c_ep = 0, c_goal = 0, c_wall = 0, c_move = 0, c_stale = 0;
+  unsigned long long c_len = 0;
+
+  // Warp w of CTA b owns tiles w*grid+b, +grid*WARPS, ...: small batches still spread over all SMs.
+  const int64_t tiles = (p.n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * WARPS;
+  for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < tiles; tile += wstride) {
+    const int64_t e = tile * 32 + lane;
+    const bool valid = e < p.n;
+    uint32_t st = 0;
+    bool render = false, done = false;
+    int cls_taken = -1;
+    if (valid) {
+      st = p.state[e];
+      EnvRegs r = V::unpack(st);
+      bool reset_now = false;
+      if (p.mode == MODE_STEP) {
+        const long long a = load_action(p.actions, p.action_dtype, e);
+        uint32_t hits = 0;
+        const StepOut o = transition<V>(r, a, cls, hits);
+        if (V::ID == 0 && hits) p.goal_count[e] += hits;
+        done = o.done; cls_taken = o.cls;
+        p.reward[e] = __uint_as_float(reward_bits(r.rcode));
+        p.done[e] = done ? 1 : 0;
+        if (done) c_len += r.step;
+        reset_now = done && p.autoreset;
+        render = true;
+      } else if (p.mode == MODE_RESET) {
+        reset_now = (p.mask == nullptr) || (p.mask[e] != 0);
+        render = reset_now;
+      } else {
+        render = true;
+      }
+      if (reset_now) {
+        uint32_t ep = p.episode[e];
+        respawn<V>(r, p, e, ep, cls, cand);
+        p.episode[e] = ep;
+      }
+      st = V::pack(r);
+      if (p.mode != MODE_RENDER) p.state[e] = st;
+    }
+    // ---- episode statistics: one ballot per counter, popc'd into per-warp registers
+    if (p.mode == MODE_STEP) {
+      c_steps += __popc(__ballot_sync(0xffffffffu, valid));
+      c_ep += __popc(__ballot_sync(0xffffffffu, done));
+      c_goal += __popc(__ballot_sync(0xffffffffu, done && cls_taken == CLS_X));
+      c_wall += __popc(__ballot_sync(0xffffffffu, cls_taken == CLS_W));
+      c_move += __popc(__ballot_sync(0xffffffffu, cls_taken == CLS_B || cls_taken == CLS_X));
+      c_stale += __popc(__ballot_sync(0xffffffffu, cls_taken == CLS_S));
+    }
+    // ---- observation render (lmaze_env.py:208-234): the env's image is NSEG blob segments
+    unsigned rmask = __ballot_sync(0xffffffffu, render && p.obs != nullptr);
+    while (rmask) {
+      const int l = __ffs(rmask) - 1;
+      rmask &= rmask - 1;
+      const uint32_t s = __shfl_sync(0xffffffffu, st, l);
+      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + l) * V::OBS_BYTES;
+      Seg sg[V::NSEG];
+      V::segments(V::unpack(s), sg);
+      if (RENDER == RENDER_TMA) {
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < V::NSEG; ++k)
+            if (sg[k].len) bulk_s2g(dst + sg[k].dst, blob_s + sg[k].src, sg[k].len);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < V::NSEG; ++k) {
+          const uint32_t n16 = sg[k].len >> 4;
+          const uint32_t src = blob_s + sg[k].src;
+          unsigned char *d = dst + sg[k].dst;
+          uint32_t i = lane;
+          for (; i + 96 < n16; i += 128) {          // 4 independent 16-byte moves per lane in flight
+            const uint4 v0 = lds_v4(src + (i << 4)), v1 = lds_v4(src + ((i + 32) << 4));
+            const uint4 v2 = lds_v4(src + ((i + 64) << 4)), v3 = lds_v4(src + ((i + 96) << 4));
+            st_stream_v4(d + ((size_t)i << 4), v0);
+            st_stream_v4(d + ((size_t)(i + 32) << 4), v1);
+            st_stream_v4(d + ((size_t)(i + 64) << 4), v2);
+            st_stream_v4(d + ((size_t)(i + 96) << 4), v3);
+          }
+          for (; i < n16; i += 32) st_stream_v4(d + ((size_t)i << 4), lds_v4(src + (i << 4)));
+        }
+      }
+    }
+  }
+  if (RENDER == RENDER_TMA) {
+    // the blob must outlive every copy that reads it; also waits for the global writes
+    bulk_commit();
+    bulk_wait_all();
+  }
+  if (p.mode == MODE_STEP && lane == 0 && c_steps) {
+    // c_goal etc. hold the same value in every lane (ballot results); eplen needs a warp sum
+    atomicAdd(&p.stats[STAT_STEPS], (unsigned long long)c_steps);
+    if (c_ep) {
+      atomicAdd(&p.stats[STAT_EPISODES], (unsigned long long)c_ep);
+      atomicAdd(&p.stats[STAT_TIMEOUTS], (unsigned long long)(c_ep - c_goal));
+    }
+    if (c_goal) atomicAdd(&p.stats[STAT_GOALS], (unsigned long long)c_goal);
+    if (c_wall) atomicAdd(&p.stats[STAT_WALL_BUMPS], (unsigned long long)c_wall);
+    if (c_move) atomicAdd(&p.stats[STAT_MOVES], (unsigned long long)c_move);
+    if (c_stale) atomicAdd(&p.stats[STAT_STALE], (unsigned long long)c_stale);
+  }
+  if (p.mode == MODE_STEP) {
+    // episode-length sum: per-lane partials -> warp reduction -> one atomic per warp
+    unsigned long long v = c_len;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0 && v) atomicAdd(&p.stats[STAT_EPLEN_SUM], v);
+  }
+}
+
+// ------------------------------------------------------------------ T-step rollout, no per-step obs
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_rollout_kernel(const KParams p) {
+  __shared__ uint8_t cls[V::G * V::G];
+  __shared__ uint16_t cand[V::MAX_CAND];
+  __shared__ unsigned long long blk_stats[NUM_STATS];
+  for (int i = threadIdx.x; i < V::G * V::G; i += THREADS) cls[i] = p.blob[V::CLS_OFF + i];
+  for (int i = threadIdx.x; i < V::MAX_CAND; i += THREADS)
+    cand[i] = reinterpret_cast<const uint16_t *>(p.blob + V::CAND_OFF)[i];
+  if (threadIdx.x < NUM_STATS) blk_stats[threadIdx.x] = 0;
+  __syncthreads();
+
+  uint32_t c_ep = 0, c_goal = 0, c_wall = 0, c_move = 0, c_stale = 0, c_steps = 0;
+  unsigned long long c_len = 0;
+  const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+
+  for (int64_t e = (int64_t)blockIdx.x * THREADS + threadIdx.x; e < p.n; e += (int64_t)gridDim.x * THREADS) {
+    EnvRegs r = V::unpack(p.state[e]);
+    uint32_t ep = p.episode[e];
+    uint32_t hits = 0;
+    const uint64_t gid = p.env_id0 + (uint64_t)e;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int t = 0; t < p.T; ++t) {
+      long long a;
+      if (p.actions) {
+        a = load_action(p.actions, p.action_dtype, (int64_t)t * p.n + e);
+      } else {
+        const uint64_t tg = p.t0 + (uint64_t)t;
+        const uint32_t slot = (uint32_t)(tg & 63);
+        if (slot == 0 || t == 0) {      // one Philox block = 64 two-bit actions
+          const uint64_t blk = tg >> 6;
+          philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk,
+                        ((uint32_t)(blk >> 32) << 8) | TAG_ACTION, k0, k1, w);
+        }
+        const uint32_t word = (slot >> 4) == 0 ? w[0] : (slot >> 4) == 1 ? w[1] : (slot >> 4) == 2 ? w[2] : w[3];
+        a = (word >> (2 * (slot & 15))) & 3u;
+      }
+      const StepOut o = transition<V>(r, a, cls, hits);
+      const int64_t oi = (int64_t)t * p.n + e;
+      __stcs(p.reward + oi, __uint_as_float(reward_bits(r.rcode)));
+      __stcs(p.done + oi, (uint8_t)(o.done ? 1 : 0));
+      c_steps += 1;
+      c_wall += (o.cls == CLS_W); c_move += (o.cls == CLS_B || o.cls == CLS_X); c_stale += (o.cls == CLS_S);
+      if (o.done) {
+        c_ep += 1; c_len += r.step; c_goal += (o.cls == CLS_X);
+        if (p.autoreset) respawn<V>(r, p, e, ep, cls, cand);
+      }
+    }
+    p.state[e] = V::pack(r);
+    p.episode[e] = ep;
+    if (V::ID == 0 && hits) p.goal_count[e] += hits;
+  }
+  // statistics: warp reduce -> shared atomics -> one global atomic per counter per CTA
+  unsigned long long v[NUM_STATS] = {c_steps, c_ep, c_goal, (unsigned long long)(c_ep - c_goal), c_wall, c_move,
+                                     c_stale, c_len};
+#pragma unroll
+  for (int k = 0; k < NUM_STATS; ++k) {
+    unsigned long long x = v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(&blk_stats[k], x);
+  }
+  __syncthreads();
+  if (threadIdx.x < NUM_STATS && blk_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], blk_stats[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ state exchange (get/set_state)
+// cols: x, y, goal_x, goal_y, step_count, reward_code, goal_count, episode
+template <class V>
+__global__ void lmz_state_kernel(int64_t n, uint32_t *state, uint32_t *goal_count, uint32_t *episode, int32_t *io,
+                                 int set) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int32_t *row = io + e * 8;
+  if (set) {
+    EnvRegs r;
+    auto clampi = [](int v) { return v < 1 ? 1 : (v > V::G - 2 ? V::G - 2 : v); };   // keep +-1 lookups in the table
+    r.x = clampi(row[0]); r.y = clampi(row[1]); r.gx = clampi(row[2]); r.gy = clampi(row[3]);
+    r.step = (uint32_t)row[4] < V::STEP_SAT ? (uint32_t)row[4] : V::STEP_SAT;
+    r.rcode = row[5] & 3;
+    state[e] = V::pack(r);
+    goal_count[e] = (uint32_t)row[6];
+    episode[e] = (uint32_t)row[7];
+  } else {
+    const EnvRegs r = V::unpack(state[e]);
+    row[0] = r.x; row[1] = r.y; row[2] = r.gx; row[3] = r.gy; row[4] = (int32_t)r.step; row[5] = r.rcode;
+    row[6] = (int32_t)goal_count[e]; row[7] = (int32_t)episode[e];
+  }
+}
+
+}  // namespace lmz

@@ -1,0 +1,270 @@
+"""LmazeVecCuda -- the reference's gym Env surface over N mazes on one B200.
+
+Host-side mirror of the reference classes for the hot path:
+  variant "v0" <-> LmazeEnv     (reference gym_lmaze/envs/lmaze_env.py:11-256)
+  variant "v3" <-> LmazeEnv_v3  (reference gym_lmaze/envs/lmaze_env_v3.py:17-402)
+
+Same method names and argument meaning -- `reset()` returns the observation,
+`step(action)` returns `(obs, reward, done, info)` (old-gym 4-tuple,
+lmaze_env.py:237), `action_space` / `observation_space` are the reference's
+(`Discrete(4)`, `Box(0, 1, (4, 84, 84))`, lmaze_env.py:16,20) -- but every value is
+a batch: obs `float32 [N, C, H, W]`, reward `float32 [N]`, done `bool [N]` CUDA
+tensors.  This module only owns tensors and forwards to the C ABI
+(include/lmaze_b200.h) through ctypes with tensors exchanged as DLPack capsules;
+all env arithmetic happens in the CUDA kernels.  There is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from .. import _abi
+from ..spaces import make_spaces
+
+_VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
+             "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3}
+_RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128}
+# lmaze_env_v3.py:236-247 -- the strings v3's step() accepts; anything else is its unmatched branch
+_V3_WORDS = {"left": 0, "0": 0, "right": 1, "1": 1, "up": 2, "2": 2, "down": 3, "3": 3}
+INVALID_ACTION = 255
+_ACTION_DTYPES = (torch.uint8, torch.int32, torch.int64)
+
+
+def shard_range(total_envs, rank, world_size):
+    """Contiguous global-id range [lo, hi) owned by `rank`."""
+    total_envs, rank, world_size = int(total_envs), int(rank), int(world_size)
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    lo = total_envs * rank // world_size
+    hi = total_envs * (rank + 1) // world_size
+    return lo, hi
+
+
+class LmazeVecCuda(object):
+    metadata = {"render.modes": ["human"]}          # lmaze_env.py:12
+
+    def __init__(self, num_envs=1, variant="v0", device=None, seed=0, autoreset=True, render_mode="tma",
+                 env_id0=0, random_ball=True, random_goal=True, with_obs=True):
+        if variant not in _VARIANTS:
+            raise ValueError("unknown variant %r (built: v0, v3)" % (variant,))
+        if render_mode not in _RENDER:
+            raise ValueError("render_mode must be 'tma' or 'st128'")
+        self._lib = _abi.load()          # raises if the CUDA extension is missing: no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("LmazeVecCuda needs a CUDA device; gym_lmaze_b200 has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.variant = _VARIANTS[variant]
+        self.num_envs = int(num_envs)
+        self.autoreset = bool(autoreset)
+        self.env_id0 = int(env_id0)
+        self.seed = int(seed)
+
+        shape = (ctypes.c_int64 * 3)()
+        _abi.check(self._lib.lmz_obs_shape(self.variant, ctypes.byref(shape)))
+        self.obs_shape = tuple(shape)
+        self.grid_size = self._lib.lmz_grid_size(self.variant)
+        self.single_action_space, self.single_observation_space = make_spaces(4, self.obs_shape)
+        self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
+        self.VISUALIZE = False           # lmaze_env.py:26; cv2 display is out of scope
+
+        cfg = _abi.LmzConfig()
+        self._lib.lmz_default_config(ctypes.byref(cfg))
+        cfg.variant, cfg.num_envs, cfg.env_id0 = self.variant, self.num_envs, self.env_id0
+        cfg.seed, cfg.device = self.seed & 0xFFFFFFFFFFFFFFFF, self.device.index
+        cfg.autoreset, cfg.random_ball, cfg.random_goal = int(autoreset), int(random_ball), int(random_goal)
+        cfg.render_mode = _RENDER[render_mode]
+        handle = ctypes.c_void_p()
+        _abi.check(self._lib.lmz_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+
+        # caller-owned (PyTorch) output tensors, bound once; the kernels write them in place
+        n = self.num_envs
+        self.obs = torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=self.device) if with_obs else None
+        self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._done_u8 = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.done = self._done_u8.view(torch.bool)
+        self._bind()
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _bind(self):
+        po, ko = _abi.dl(self.obs)
+        pr, kr = _abi.dl(self.reward)
+        pd, kd = _abi.dl(self._done_u8)
+        _abi.check(self._lib.lmz_bind_dl(self._h, po, pr, pd))
+        self._bound_keepalive = (ko, kr, kd)
+
+    def _as_actions(self, actions):
+        """Anything the reference's `int(msg)` (lmaze_env.py:148) accepts, batched."""
+        if isinstance(actions, (list, tuple)) and actions and isinstance(actions[0], str):
+            actions = [_V3_WORDS.get(a, INVALID_ACTION) for a in actions]
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(actions)
+        if actions.is_floating_point():
+            actions = actions.to(torch.int64)            # int() truncates toward zero
+        elif actions.dtype == torch.bool:
+            actions = actions.to(torch.uint8)
+        elif actions.dtype not in _ACTION_DTYPES:
+            actions = actions.to(torch.int64)
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        return actions.contiguous()
+
+    def _as_spawn(self, spawn):
+        if spawn is None:
+            return None
+        spawn = torch.as_tensor(spawn)
+        if spawn.dim() == 2 and spawn.shape[1] == 2:      # v0 convenience: (x, y) only
+            spawn = torch.cat([spawn, torch.full_like(spawn, -1)], dim=1)
+        return spawn.to(device=self.device, dtype=torch.int32).contiguous()
+
+    # ------------------------------------------------------------------ gym surface
+    def reset(self, spawn=None, mask=None):
+        """Start new episodes (all envs, or those where `mask` is true) and return obs.
+
+        spawn: optional int [N, 4] (ball_x, ball_y, goal_x, goal_y) -- the cells the
+        reference's rejection sampling (lmaze_env.py:70-78) would have drawn; default is
+        the device RNG.
+        """
+        spawn = self._as_spawn(spawn)
+        if mask is not None:
+            mask = torch.as_tensor(mask).to(device=self.device).to(torch.uint8).contiguous()
+        pm, km = _abi.dl(mask)
+        ps, ks = _abi.dl(spawn)
+        _abi.check(self._lib.lmz_reset_dl(self._h, pm, ps, self._stream()))
+        return self.obs
+
+    def step(self, actions, spawn=None):
+        """One fused kernel: transition + reward + done (+ auto-reset) + obs render.
+
+        Returns (obs, reward, done, info); `info["action"]` echoes the actions, the
+        batched form of the reference returning `msg` as its 4th element
+        (lmaze_env.py:237).  With autoreset the obs rows of finished envs already
+        show the next episode's first observation.
+        """
+        actions = self._as_actions(actions)
+        spawn = self._as_spawn(spawn)
+        pa, ka = _abi.dl(actions)
+        ps, ks = _abi.dl(spawn)
+        _abi.check(self._lib.lmz_step_dl(self._h, pa, ps, self._stream()))
+        return self.obs, self.reward, self.done, {"action": actions}
+
+    def step_host(self, actions_host, reward_host, done_host, obs_host=None):
+        """End-to-end step with HOST buffers (pinned CPU tensors): H2D actions, fused
+        step, D2H reward/done (and obs if given), stream synchronised on return."""
+        for t in (actions_host, reward_host, done_host):
+            if t.device.type != "cpu" or not t.is_contiguous():
+                raise ValueError("step_host takes contiguous CPU tensors")
+        if actions_host.dtype not in _ACTION_DTYPES:
+            raise ValueError("actions_host dtype must be uint8/int32/int64")
+        if actions_host.numel() != self.num_envs or reward_host.numel() != self.num_envs \
+                or done_host.numel() != self.num_envs:
+            raise ValueError("host buffers must have num_envs elements")
+        if reward_host.dtype != torch.float32 or done_host.dtype not in (torch.uint8, torch.bool):
+            raise ValueError("reward_host must be float32 and done_host uint8/bool")
+        if obs_host is not None and (obs_host.dtype != torch.float32 or not obs_host.is_contiguous()
+                                     or obs_host.numel() != self.obs.numel()):
+            raise ValueError("obs_host must be a contiguous float32 tensor shaped like obs")
+        ad = _ACTION_DTYPES.index(actions_host.dtype)
+        _abi.check(self._lib.lmz_step_host(
+            self._h, actions_host.data_ptr(), ad, reward_host.data_ptr(), done_host.data_ptr(),
+            None if obs_host is None else obs_host.data_ptr(), self._stream()))
+        return reward_host, done_host
+
+    def rollout(self, T, actions=None, rewards=None, dones=None):
+        """T fused steps, no per-step obs.  actions None => device-side random actions.
+        Returns (rewards f32 [T, N], dones bool [T, N])."""
+        T = int(T)
+        if actions is not None:
+            actions = self._as_actions(actions)
+        if rewards is None:
+            rewards = torch.empty((T, self.num_envs), dtype=torch.float32, device=self.device)
+        if dones is None:
+            dones = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self.device)
+        dones_u8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones
+        pa, ka = _abi.dl(actions)
+        pr, kr = _abi.dl(rewards)
+        pd, kd = _abi.dl(dones_u8)
+        _abi.check(self._lib.lmz_rollout_dl(self._h, T, pa, pr, pd, self._stream()))
+        return rewards, dones_u8.view(torch.bool)
+
+    def render_obs(self):
+        """Re-render the current state into `obs` without stepping."""
+        _abi.check(self._lib.lmz_render(self._h, self._stream()))
+        return self.obs
+
+    def render(self, mode="human", close=False):
+        # the reference's render() only flips the cv2 display flag (lmaze_env.py:55-59)
+        self.VISUALIZE = (mode == "human")
+
+    def rendering(self, msg):                          # lmaze_env.py:251-252
+        self.VISUALIZE = msg
+
+    def writing(self, msg):                            # lmaze_env.py:255-256
+        self.SAVEFRAME = msg
+
+    # ------------------------------------------------------------------ state / stats
+    def get_state(self):
+        """int32 [N, 8]: x, y, goal_x, goal_y, step_count, reward_code, goal_count, episode."""
+        out = torch.empty((self.num_envs, _abi.ST_COLS), dtype=torch.int32, device=self.device)
+        p, k = _abi.dl(out)
+        _abi.check(self._lib.lmz_get_state_dl(self._h, p, self._stream()))
+        return out
+
+    def set_state(self, state):
+        state = torch.as_tensor(state).to(device=self.device, dtype=torch.int32).contiguous()
+        p, k = _abi.dl(state)
+        _abi.check(self._lib.lmz_set_state_dl(self._h, p, self._stream()))
+
+    def stats(self, check_errors=True):
+        out = (ctypes.c_int64 * _abi.NUM_STATS)()
+        err = ctypes.c_int64()
+        _abi.check(self._lib.lmz_stats(self._h, ctypes.byref(out), ctypes.byref(err), self._stream()))
+        if check_errors and err.value:
+            raise ValueError("%d injected spawn cells were rejected (wall/goal/out of range)" % err.value)
+        return dict(zip(_abi.STAT_NAMES, (int(v) for v in out)))
+
+    def stats_reset(self):
+        _abi.check(self._lib.lmz_stats_reset(self._h, self._stream()))
+
+    def stats_allreduce(self, group=None):
+        """Sum of the integer episode counters over all ranks (never on the step path)."""
+        import torch.distributed as dist
+        local = self.stats()
+        return allreduce_stats(local, self.device, group) if dist.is_available() and dist.is_initialized() else local
+
+    @property
+    def launch_count(self):
+        return int(self._lib.lmz_launch_count(self._h))
+
+    def layout(self):
+        buf = ctypes.create_string_buffer(self.grid_size * self.grid_size)
+        _abi.check(self._lib.lmz_layout(self.variant, buf))
+        s = buf.raw.decode("ascii")
+        return [s[i * self.grid_size:(i + 1) * self.grid_size] for i in range(self.grid_size)]
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.lmz_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def allreduce_stats(local, device, group=None):
+    """All-reduce a stats dict as one int64[8] message (NCCL on GPU, gloo on CPU)."""
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = device if backend == "nccl" else torch.device("cpu")
+    t = torch.tensor([local[k] for k in _abi.STAT_NAMES], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return dict(zip(_abi.STAT_NAMES, (int(v) for v in t.tolist())))

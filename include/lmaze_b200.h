@@ -1,0 +1,175 @@
+/*
+ * lmaze_b200.h -- C ABI of the B200-native batched LMaze step/reset path.
+ *
+ * The reference (gkm2708/gym-lmaze) has no FFI layer: its hot path sits behind
+ * gym's Python Env protocol -- `reset() -> obs`, `step(a) -> (obs, reward, done,
+ * info)` on one maze (reference gym_lmaze/envs/lmaze_env.py:64,146,237;
+ * lmaze_env_v3.py:134,220,398-402).  This header is the boundary a maintainer
+ * would bind instead (ctypes stub in INTEGRATION.md): the same operations over N
+ * independent mazes whose state and outputs live in GPU memory.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative lmz_status; the message
+ *     for the calling thread's last failure is lmz_last_error()
+ *   - no exceptions, aborts or hidden synchronisation: work is enqueued on the
+ *     caller's CUDA stream (`stream` is a cudaStream_t passed as void*; NULL =
+ *     the legacy default stream); asynchronous CUDA faults surface on a later call
+ *   - the caller owns every buffer; pointers are DEVICE pointers unless the
+ *     name says `_host`; the handle owns only its small per-env state arrays
+ *   - the `_dl` forms take borrowed `DLManagedTensor*` (include/lmz_dlpack.h),
+ *     validate device / dtype / shape / contiguity / alignment and forward to the
+ *     plain-pointer forms.  They never call the tensor's deleter.
+ *   - one handle <-> one device; calls on one handle must be serialised by the caller
+ *
+ * There is no CPU implementation behind this ABI.
+ */
+#ifndef LMAZE_B200_H
+#define LMAZE_B200_H
+
+#include <stdint.h>
+#include "lmz_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMZ_ABI_VERSION 1
+
+typedef struct lmz_env lmz_env;   /* opaque handle */
+
+typedef enum {
+  LMZ_OK = 0,
+  LMZ_ERR_INVALID = -1,    /* bad argument (NULL, range, shape, dtype, alignment) */
+  LMZ_ERR_CUDA = -2,       /* a CUDA runtime call failed; message has the cudaError */
+  LMZ_ERR_STATE = -3,      /* call not legal in the handle's state (e.g. step before bind) */
+  LMZ_ERR_UNSUPPORTED = -4
+} lmz_status;
+
+/* Maze variants (reference class each one replaces). */
+typedef enum {
+  LMZ_V0 = 0,   /* LmazeEnv     'lmaze-v0', 12x12, obs f32 (4,84,84)  -- lmaze_env.py:11-256    */
+  LMZ_V3 = 3    /* LmazeEnv_v3  'lmaze-v3', 18x18, obs f32 (3,72,72)  -- lmaze_env_v3.py:17-402 */
+} lmz_variant;
+
+/* How the fused kernel writes the observation tensor. */
+typedef enum {
+  LMZ_RENDER_TMA = 0,     /* bulk async shared->global copies (cp.async.bulk) of template segments */
+  LMZ_RENDER_ST128 = 1    /* 128-bit vector stores (st.global.v4) fed from the shared-memory template */
+} lmz_render_mode;
+
+/* Element type of an action buffer. */
+typedef enum { LMZ_ACT_U8 = 0, LMZ_ACT_I32 = 1, LMZ_ACT_I64 = 2 } lmz_action_dtype;
+
+typedef struct lmz_config {
+  int32_t  struct_size;   /* = sizeof(lmz_config); guards against header/library skew */
+  int32_t  variant;       /* lmz_variant */
+  int64_t  num_envs;      /* N: mazes owned by this handle (this rank's shard) */
+  int64_t  env_id0;       /* global id of env 0; the device RNG is keyed by global id so
+                             trajectories do not depend on how envs are sharded over GPUs */
+  uint64_t seed;
+  int32_t  device;        /* CUDA device ordinal */
+  int32_t  autoreset;     /* 1: an env that finishes is re-spawned inside the same step and the
+                             returned obs is the new episode's first obs (terminal reward/done kept);
+                             0: reference behaviour, stepping past done is legal (lmaze_env.py:246-249) */
+  int32_t  random_ball;   /* RANDOM_BALL  (lmaze_env.py:25, lmaze_env_v3.py:103); 0 => spawn on 'S' */
+  int32_t  random_goal;   /* RANDOM_GOAL  (lmaze_env_v3.py:104); ignored by v0 */
+  int32_t  render_mode;   /* lmz_render_mode */
+  int32_t  reserved[7];   /* must be zero */
+} lmz_config;
+
+/* Episode statistics kept on the device as integer counters (lmz_stats). */
+enum {
+  LMZ_STAT_STEPS = 0,     /* env-steps executed */
+  LMZ_STAT_EPISODES,      /* done flags raised */
+  LMZ_STAT_GOALS,         /* reward == 100.0 */
+  LMZ_STAT_TIMEOUTS,      /* done without a goal */
+  LMZ_STAT_WALL_BUMPS,    /* 'W' branch  (lmaze_env.py:172-174) */
+  LMZ_STAT_MOVES,         /* 'B'/'X' branches (lmaze_env.py:176-195) */
+  LMZ_STAT_STALE,         /* 'S' target: no branch, reward kept (v0 quirk) */
+  LMZ_STAT_EPLEN_SUM,     /* sum of stepCount over finished episodes */
+  LMZ_NUM_STATS
+};
+
+/* Columns of the unpacked per-env state exchanged by lmz_get_state / lmz_set_state. */
+enum {
+  LMZ_ST_X = 0, LMZ_ST_Y, LMZ_ST_GOAL_X, LMZ_ST_GOAL_Y, LMZ_ST_STEP_COUNT,
+  LMZ_ST_REWARD_CODE,     /* 0: -0.0  1: -1.0  2: -0.01  3: 100.0  (last reward, lmaze_env.py:109,174-194) */
+  LMZ_ST_GOAL_COUNT,      /* goalCount, survives reset (lmaze_env.py:24,195) */
+  LMZ_ST_EPISODE,         /* resets performed so far (device RNG counter) */
+  LMZ_ST_COLS
+};
+
+/* ---- library ---- */
+int         lmz_abi_version(void);
+const char *lmz_last_error(void);
+void        lmz_default_config(lmz_config *cfg);                    /* fills struct_size + defaults */
+/* Static facts about a variant: obs shape (C,H,W) -- observation_space of
+ * lmaze_env.py:20 / lmaze_env_v3.py:91 -- and grid side. */
+int         lmz_obs_shape(int32_t variant, int64_t shape[3]);
+int         lmz_grid_size(int32_t variant);
+/* Copies the maze rows (G*G cell letters, row-major, no terminator) -- lmaze_env.py:37-48. */
+int         lmz_layout(int32_t variant, char *cells);
+
+/* ---- handle lifecycle: replaces LmazeEnv.__init__ (lmaze_env.py:14-53) minus its first reset ---- */
+int lmz_create(const lmz_config *cfg, lmz_env **out);
+int lmz_destroy(lmz_env *env);
+
+/* Bind the output buffers every later call writes: obs f32 [N,C,H,W] (may be NULL:
+ * transition only, nothing rendered), reward f32 [N], done u8 [N].  16-byte aligned. */
+int lmz_bind(lmz_env *env, float *obs, float *reward, uint8_t *done);
+int lmz_bind_dl(lmz_env *env, DLManagedTensor *obs, DLManagedTensor *reward, DLManagedTensor *done);
+
+/* reset(): replaces LmazeEnv.reset (lmaze_env.py:64-141) / LmazeEnv_v3.reset
+ * (lmaze_env_v3.py:134-206) for every env whose mask byte is non-zero (mask NULL =
+ * all).  spawn NULL => device RNG; else int32 [N][4] = ball_x, ball_y, goal_x,
+ * goal_y (the cells the reference's rejection loop would have accepted; goal
+ * ignored by v0).  Re-renders obs for the envs it resets. */
+int lmz_reset(lmz_env *env, const uint8_t *mask, const int32_t *spawn, void *stream);
+int lmz_reset_dl(lmz_env *env, DLManagedTensor *mask, DLManagedTensor *spawn, void *stream);
+
+/* step(): replaces LmazeEnv.step (lmaze_env.py:146-237) / LmazeEnv_v3.step
+ * (lmaze_env_v3.py:220-402): one fused kernel -- action decode, wall lookup,
+ * move, reward, done, optional auto-reset, obs render, statistics.  actions is
+ * [N] of `action_dtype`; codes 0..3 move, any other value takes the reference's
+ * unmatched branch (offset 0,0).  spawn as for lmz_reset, consumed only by envs
+ * that auto-reset in this step. */
+int lmz_step(lmz_env *env, const void *actions, int32_t action_dtype, const int32_t *spawn, void *stream);
+int lmz_step_dl(lmz_env *env, DLManagedTensor *actions, DLManagedTensor *spawn, void *stream);
+
+/* Host-buffer form of step() (the end-to-end call): copies actions H2D, runs the
+ * fused step, copies reward/done (and obs when obs_host != NULL) D2H and waits
+ * for the stream.  Host buffers should be pinned for the copies to be asynchronous. */
+int lmz_step_host(lmz_env *env, const void *actions_host, int32_t action_dtype,
+                  float *reward_host, uint8_t *done_host, float *obs_host, void *stream);
+
+/* Render the current state into the bound obs without stepping (the
+ * upsample loop of lmaze_env.py:208-234 on its own). */
+int lmz_render(lmz_env *env, void *stream);
+
+/* T fused steps with state in registers and no per-step observation:
+ * rewards f32 [T][N], dones u8 [T][N].  actions NULL => device-side random
+ * actions (Philox keyed by seed, global env id, step index); else [T][N]. */
+int lmz_rollout(lmz_env *env, int32_t T, const void *actions, int32_t action_dtype,
+                float *rewards, uint8_t *dones, void *stream);
+int lmz_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedTensor *rewards,
+                   DLManagedTensor *dones, void *stream);
+
+/* Unpacked per-env state, int32 [N][LMZ_ST_COLS] on the device (checkpoint /
+ * resume, and how parity tests start both sides from the same state). */
+int lmz_get_state(lmz_env *env, int32_t *out, void *stream);
+int lmz_set_state(lmz_env *env, const int32_t *in, void *stream);
+int lmz_get_state_dl(lmz_env *env, DLManagedTensor *out, void *stream);
+int lmz_set_state_dl(lmz_env *env, DLManagedTensor *in, void *stream);
+
+/* Copies the device counters to out_host[LMZ_NUM_STATS] (synchronises `stream`).
+ * *errors_host (may be NULL) receives the number of rejected injected spawns. */
+int lmz_stats(lmz_env *env, int64_t *out_host, int64_t *errors_host, void *stream);
+int lmz_stats_reset(lmz_env *env, void *stream);
+
+/* Launch bookkeeping for benchmarks: kernels launched by this handle so far. */
+int64_t lmz_launch_count(const lmz_env *env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,110 @@
+"""CPU tier: the C-ABI library loads without a GPU, exports every symbol the header
+declares, validates arguments, and refuses to run without a CUDA device (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from gym_lmaze_b200 import build, _abi
+    build.build()
+    return _abi
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "lmaze_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lmz_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(abi):
+    L = abi.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), "header declares %s but the library does not export it" % s
+    assert sorted(abi.EXPORTS) == syms            # the binding covers the whole header
+    assert L.lmz_abi_version() == 1
+
+
+def test_library_is_self_contained(abi):
+    """No torch / python / oracle linkage: only libc-level dependencies."""
+    import subprocess
+    out = subprocess.run(["ldd", abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "torch" not in out and "python" not in out and "oracle" not in out and "libcudart" not in out
+
+
+def test_static_queries_and_layouts(abi, golden_dir):
+    L = abi.load()
+    shape = (ctypes.c_int64 * 3)()
+    assert L.lmz_obs_shape(abi.LMZ_V0, ctypes.byref(shape)) == 0 and tuple(shape) == (4, 84, 84)
+    assert L.lmz_obs_shape(abi.LMZ_V3, ctypes.byref(shape)) == 0 and tuple(shape) == (3, 72, 72)
+    assert L.lmz_obs_shape(5, ctypes.byref(shape)) < 0 and b"unknown variant" in L.lmz_last_error()
+    z = np.load(os.path.join(golden_dir, "layouts.npz"))
+    for name, variant, G in (("v0", abi.LMZ_V0, 12), ("v3", abi.LMZ_V3, 18)):
+        assert L.lmz_grid_size(variant) == G
+        buf = ctypes.create_string_buffer(G * G)
+        assert L.lmz_layout(variant, buf) == 0
+        cells = buf.raw.decode()
+        assert [cells[i * G:(i + 1) * G] for i in range(G)] == [str(r) for r in z[name]]
+
+
+def test_config_validation_and_no_cpu_fallback(abi):
+    import torch
+    L = abi.load()
+    cfg = abi.LmzConfig()
+    L.lmz_default_config(ctypes.byref(cfg))
+    assert cfg.struct_size == ctypes.sizeof(abi.LmzConfig) and cfg.autoreset == 1 and cfg.random_ball == 1
+    h = ctypes.c_void_p()
+    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.struct_size = 8
+    assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -1 and b"struct_size" in L.lmz_last_error()
+    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.variant = 2
+    assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -4
+    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.num_envs = 0
+    assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    assert L.lmz_step(None, None, 0, None, None) == -1 and b"NULL" in L.lmz_last_error()
+    if not torch.cuda.is_available():
+        # the product path must fail loudly without a device -- never fall back to a CPU env
+        assert L.lmz_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
+        assert b"no CPU path" in L.lmz_last_error()
+        import gym_lmaze_b200 as g
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            g.make("lmaze-v0")
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gym_lmaze_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no dependency on torch or Python", "") or f == "lmz_kernels.cuh" \
+                    and "CPU twin in oracle/" in txt, f
+
+
+def test_registry_and_spaces():
+    import gym_lmaze_b200 as g
+    from gym_lmaze_b200.spaces import make_spaces
+    assert {"lmaze-v0", "lmaze-v3", "lmaze-vec-v0", "lmaze-vec-v3"} <= set(g.registered_ids())
+    assert "lmaze-v7" not in g.registered_ids()      # the reference registers a class that does not exist
+    a, o = make_spaces(4, (4, 84, 84))
+    assert a.n == 4 and tuple(o.shape) == (4, 84, 84) and o.dtype == np.float32
+    assert float(np.min(o.low)) == 0.0 and float(np.max(o.high)) == 1.0
+
+
+def test_shard_range_partitions_exactly():
+    from gym_lmaze_b200 import shard_range
+    for total in (1, 7, 4096, 1_000_000, 16_000_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 3)
