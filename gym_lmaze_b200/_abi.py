@@ -38,7 +38,8 @@ class LmzConfig(ctypes.Structure):
         ("random_ball", ctypes.c_int32),
         ("random_goal", ctypes.c_int32),
         ("render_mode", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 7),
+        ("tune", ctypes.c_int32 * 4),
+        ("reserved", ctypes.c_int32 * 3),
     ]
 
 

@@ -148,6 +148,9 @@ lmz::KParams base_params(lmz_env *h) {
   p.seed = h->cfg.seed; p.env_id0 = (uint64_t)h->cfg.env_id0;
   p.autoreset = h->cfg.autoreset; p.random_ball = h->cfg.random_ball; p.random_goal = h->cfg.random_goal;
   p.n_cand = h->n_cand; p.s_cell = h->s_cell;
+  p.l2_policy = h->cfg.tune[1] ? h->cfg.tune[1] : lmz::DEFAULT_L2_POLICY;
+  p.tile_order = h->cfg.tune[2] ? h->cfg.tune[2] : lmz::DEFAULT_TILE_ORDER;
+  p.bulk_split = (uint32_t)h->cfg.tune[3];
   return p;
 }
 
@@ -179,7 +182,13 @@ template <class V>
 int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (h->cfg.render_mode == LMZ_RENDER_ST128 && p.obs != nullptr)
     return launch_env_t<V, lmz::RENDER_ST128, ST_THREADS>(h, p, s);
-  return launch_env_t<V, lmz::RENDER_TMA, TMA_THREADS>(h, p, s);
+  switch (h->cfg.tune[0]) {
+    case 32: return launch_env_t<V, lmz::RENDER_TMA, 32>(h, p, s);
+    case 64: return launch_env_t<V, lmz::RENDER_TMA, 64>(h, p, s);
+    case 256: return launch_env_t<V, lmz::RENDER_TMA, 256>(h, p, s);
+    case 512: return launch_env_t<V, lmz::RENDER_TMA, 512>(h, p, s);
+    default: return launch_env_t<V, lmz::RENDER_TMA, TMA_THREADS>(h, p, s);
+  }
 }
 
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
@@ -322,8 +331,16 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
   if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128)
     return fail(LMZ_ERR_INVALID, "unknown render_mode %d", cfg->render_mode);
-  for (int i = 0; i < 7; ++i)
+  for (int i = 0; i < 3; ++i)
     if (cfg->reserved[i] != 0) return fail(LMZ_ERR_INVALID, "lmz_config.reserved must be zero");
+  {
+    const int t = cfg->tune[0];
+    if (t != 0 && t != 32 && t != 64 && t != 128 && t != 256 && t != 512)
+      return fail(LMZ_ERR_INVALID, "tune[0] (threads per CTA) must be 0, 32, 64, 128, 256 or 512");
+    if (cfg->tune[1] < 0 || cfg->tune[1] > 4) return fail(LMZ_ERR_INVALID, "tune[1] (L2 policy) must be 0..4");
+    if (cfg->tune[2] < 0 || cfg->tune[2] > 3) return fail(LMZ_ERR_INVALID, "tune[2] (tile order) must be 0..3");
+    if (cfg->tune[3] < 0 || (cfg->tune[3] & 15)) return fail(LMZ_ERR_INVALID, "tune[3] (bulk split) must be a multiple of 16");
+  }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)

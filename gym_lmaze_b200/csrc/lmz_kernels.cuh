@@ -51,7 +51,15 @@ struct KParams {
   int autoreset, random_ball, random_goal;
   int n_cand;                   // entries in the spawn-candidate table
   int s_cell;                   // linear index of the 'S' cell
+  int l2_policy;                // L2_* policy of the obs stores (TMA path)
+  int tile_order;               // ORDER_*
+  uint32_t bulk_split;          // 0, or the largest single bulk copy in bytes
 };
+
+enum : int { L2_EVICT_FIRST = 1, L2_EVICT_NORMAL = 2, L2_EVICT_LAST = 3, L2_NONE = 4 };
+enum : int { ORDER_WARP_MAJOR = 1, ORDER_CTA_CONTIG = 2, ORDER_CHUNK = 3 };
+constexpr int DEFAULT_L2_POLICY = L2_NONE;
+constexpr int DEFAULT_TILE_ORDER = ORDER_WARP_MAJOR;
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
@@ -92,6 +100,18 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem),
                "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t make_l2_policy(int kind) {
+  uint64_t pol = 0;
+  if (kind == L2_EVICT_FIRST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == L2_EVICT_LAST) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -263,10 +283,19 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_kernel(const KParams p) {
   uint32_t c_steps = 0, c_ep = 0, c_goal = 0, c_wall = 0, c_move = 0, c_stale = 0;
   unsigned long long c_len = 0;
 
-  // Warp w of CTA b owns tiles w*grid+b, +grid*WARPS, ...: small batches still spread over all SMs.
+  // Tile (= 32 consecutive envs) -> warp mapping.  Default: warp w of CTA b owns tiles
+  // w*grid+b, +grid*WARPS, ... so small batches still spread over all SMs.
   const int64_t tiles = (p.n + 31) >> 5;
-  const int64_t wstride = (int64_t)gridDim.x * WARPS;
-  for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < tiles; tile += wstride) {
+  int64_t tile, tstride, tend = tiles;
+  if (p.tile_order == ORDER_CTA_CONTIG) {
+    tile = (int64_t)blockIdx.x * WARPS + warp; tstride = (int64_t)gridDim.x * WARPS;
+  } else if (p.tile_order == ORDER_CHUNK) {
+    tile = tiles * blockIdx.x / gridDim.x + warp; tend = tiles * (blockIdx.x + 1) / gridDim.x; tstride = WARPS;
+  } else {
+    tile = (int64_t)warp * gridDim.x + blockIdx.x; tstride = (int64_t)gridDim.x * WARPS;
+  }
+  const uint64_t l2pol = (RENDER == RENDER_TMA && p.l2_policy != L2_NONE) ? make_l2_policy(p.l2_policy) : 0;
+  for (; tile < tend; tile += tstride) {
     const int64_t e = tile * 32 + lane;
     const bool valid = e < p.n;
     uint32_t st = 0;
@@ -322,8 +351,15 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_kernel(const KParams p) {
       if (RENDER == RENDER_TMA) {
         if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < V::NSEG; ++k)
-            if (sg[k].len) bulk_s2g(dst + sg[k].dst, blob_s + sg[k].src, sg[k].len);
+          for (int k = 0; k < V::NSEG; ++k) {
+            uint32_t off = 0, left = sg[k].len;
+            while (left) {
+              const uint32_t len = (p.bulk_split && left > p.bulk_split) ? p.bulk_split : left;
+              if (p.l2_policy != L2_NONE) bulk_s2g_hint(dst + sg[k].dst + off, blob_s + sg[k].src + off, len, l2pol);
+              else bulk_s2g(dst + sg[k].dst + off, blob_s + sg[k].src + off, len);
+              off += len; left -= len;
+            }
+          }
         }
       } else {
 #pragma unroll

@@ -43,7 +43,7 @@ class LmazeVecCuda(object):
     metadata = {"render.modes": ["human"]}          # lmaze_env.py:12
 
     def __init__(self, num_envs=1, variant="v0", device=None, seed=0, autoreset=True, render_mode="tma",
-                 env_id0=0, random_ball=True, random_goal=True, with_obs=True):
+                 env_id0=0, random_ball=True, random_goal=True, with_obs=True, tune=None):
         if variant not in _VARIANTS:
             raise ValueError("unknown variant %r (built: v0, v3)" % (variant,))
         if render_mode not in _RENDER:
@@ -76,6 +76,8 @@ class LmazeVecCuda(object):
         cfg.seed, cfg.device = self.seed & 0xFFFFFFFFFFFFFFFF, self.device.index
         cfg.autoreset, cfg.random_ball, cfg.random_goal = int(autoreset), int(random_ball), int(random_goal)
         cfg.render_mode = _RENDER[render_mode]
+        for i, v in enumerate(tune or ()):
+            cfg.tune[i] = int(v)
         handle = ctypes.c_void_p()
         _abi.check(self._lib.lmz_create(ctypes.byref(cfg), ctypes.byref(handle)))
         self._h = handle

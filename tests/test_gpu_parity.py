@@ -206,7 +206,7 @@ def test_config2_4096_envs_per_step_parity(lmz, oracle_mod, variant, render_mode
                 assert np.array_equal(st[:, 6], gc)
     s = env.stats()
     assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist()
-    assert s["episodes"] >= 2 * N * (T // 128) or T < 128
+    assert s["episodes"] >= N * (T // 101)          # every env timed out (or scored) at least T//101 times
     env.close()
 
 

@@ -178,3 +178,33 @@ def test_rng_spawn_distribution(oracle_mod):
         assert rows3[sx][sy] != "W" and rows3[gx][gy] != "W" and (sx, sy) != (gx, gy)
     acts = [oracle_mod.rng_action(1, 2, t) for t in range(4000)]
     assert sorted(set(acts)) == [0, 1, 2, 3] and min(np.bincount(acts)) > 850
+
+
+def test_pyloop_matches_c_oracle(oracle_mod):
+    """The interpreted restatement bench.py times for context agrees with the C oracle."""
+    from oracle.pyloop import PyLoopV0
+    env = PyLoopV0(oracle_mod.layout(oracle_mod.V0), (3, 5))
+    o = oracle_mod.OracleVec(oracle_mod.V0, 1, autoreset=False)
+    o.reset(spawn=[[3, 5, -1, -1]])
+    for a in (1, 1, 0, 7, 3, 2):
+        obs, r, d, _ = env.step(a)
+        o_ref, r_ref, d_ref = o.step([a])
+        assert np.array_equal(obs, o_ref[0]) and np.float32(r).view(np.uint32) == r_ref.view(np.uint32)[0]
+        assert bool(d) == bool(d_ref[0])
+
+
+def test_live_reference_random_walk(oracle_mod):
+    """Where the reference checkout is present (build container), step it live beside the oracle."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference checkout not present (GPU box): golden fixtures cover this")
+    env, scripted, _ = ref_loader.make_reference_env("v0", first_draws=(4, 4))
+    o = oracle_mod.OracleVec(oracle_mod.V0, 1, autoreset=False)
+    o.reset(spawn=[[4, 4, -1, -1]])
+    rng = np.random.RandomState(5)
+    for t in range(25):
+        a = int(rng.randint(0, 5))
+        obs, r, d, info = env.step(a)
+        o_ref, r_ref, d_ref = o.step([a])
+        assert np.array_equal(obs, o_ref[0]) and np.float32(r).view(np.uint32) == r_ref.view(np.uint32)[0]
+        assert bool(d) == bool(d_ref[0]) and info == a
