@@ -306,7 +306,9 @@ def run_ours(args):
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.variant, args.render_mode), "peak_source": peak_src,
-                     "kernel": "lmz_env_kernel<%s,%s>" % (args.variant.upper(), args.render_mode),
+                     "kernel": "lmz_env_%s_kernel<%s>" % ("tma" if args.render_mode == "tma" else "st", args.variant.upper()),
+                     "note": "write-only stream; peak is the measured read+write COPY rate, so frac may exceed 1 "
+                             "(compare extras.pure_write_fill_gbs)",
                      "bytes_per_env_step": step_bytes, "bytes_per_launch": N * step_bytes,
                      "kernel_ms_avg": kernel_ms, "kernel_ms_min": per_step[0],
                      "kernel_ms_median": per_step[len(per_step) // 2]},
@@ -339,6 +341,21 @@ def side_measurements(env, args, torch, dev):
     """Other operating points, each named with its own mode (never mixed into `value`)."""
     out = {}
     N = env.num_envs
+    # (0) what a trivial streaming-write kernel gets on this GPU right now (8 GB torch fill_)
+    scratch = torch.empty(2 << 30, dtype=torch.float32, device=dev)
+    scratch.fill_(1.0)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        scratch.fill_(1.0)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    out["pure_write_fill_gbs"] = {"value": 5 * scratch.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9,
+                                  "what": "torch.fill_ over 8 GiB, same process: the write-only ceiling; "
+                                          "MEASURED_PEAKS hbm_gbs is a read+write copy, so a pure-write kernel "
+                                          "can exceed it"}
+    del scratch
     # (1) BASELINE configs[4]-style: T=64 fused rollout, device-side Philox actions, no per-step obs
     T = 64
     rew = torch.empty((T, N), dtype=torch.float32, device=dev)

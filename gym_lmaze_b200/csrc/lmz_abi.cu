@@ -113,7 +113,7 @@ struct lmz_env {
   // device memory owned by the handle
   uint32_t *state, *goal_count, *episode;
   unsigned char *blob;
-  unsigned long long *stats;     // NUM_STATS counters + 1 error counter
+  unsigned long long *stats;     // NUM_STATS counters + 1 error counter + 2 work-distribution words
   void *act_stage;               // lmz_step_host staging, lazily allocated (N * 8 bytes)
   // bound outputs (caller-owned)
   float *obs, *reward;
@@ -149,17 +149,17 @@ lmz::KParams base_params(lmz_env *h) {
   p.autoreset = h->cfg.autoreset; p.random_ball = h->cfg.random_ball; p.random_goal = h->cfg.random_goal;
   p.n_cand = h->n_cand; p.s_cell = h->s_cell;
   p.l2_policy = h->cfg.tune[1] ? h->cfg.tune[1] : lmz::DEFAULT_L2_POLICY;
-  p.tile_order = h->cfg.tune[2] ? h->cfg.tune[2] : lmz::DEFAULT_TILE_ORDER;
+  p.work = h->stats + lmz::NUM_STATS + 1;
   p.bulk_split = (uint32_t)h->cfg.tune[3];
   return p;
 }
 
-constexpr int TMA_THREADS = 128;     // 4 warps: the TMA engine does the moving
+constexpr int TMA_THREADS = 32;      // one warp per SM issues the bulk copies: the TMA engine does the moving
 constexpr int ST_THREADS = 1024;     // 32 warps of vector stores per SM
 
 template <class V, int RENDER, int THREADS>
 int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  auto kern = lmz::lmz_env_kernel<V, RENDER, THREADS>;
+  auto kern = (RENDER == lmz::RENDER_TMA) ? lmz::lmz_env_tma_kernel<V, THREADS> : lmz::lmz_env_st_kernel<V, THREADS>;
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
   if (configured_dev != h->cfg.device) {
@@ -168,9 +168,10 @@ int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "env kernel does not fit on an SM");
     configured_dev = h->cfg.device;
   }
-  const int64_t tiles = (p.n + 31) / 32;
-  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;      // persistent: a whole number of CTAs per SM
-  if (grid > tiles) grid = tiles;
+  // persistent grid: a whole number of CTAs per SM, never more work units than envs
+  const int64_t units = (RENDER == lmz::RENDER_TMA) ? (p.n + 31) / 32 : p.n;
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  if (grid > units) grid = units;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, THREADS, V::BLOB_BYTES, s>>>(p);
   LMZ_CUDA(cudaGetLastError());
@@ -180,13 +181,15 @@ int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 
 template <class V>
 int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (h->cfg.render_mode == LMZ_RENDER_ST128 && p.obs != nullptr)
+  if (h->cfg.render_mode == LMZ_RENDER_ST128 && p.obs != nullptr) {
+    if (h->cfg.tune[0] == 512) return launch_env_t<V, lmz::RENDER_ST128, 512>(h, p, s);
+    if (h->cfg.tune[0] == 256) return launch_env_t<V, lmz::RENDER_ST128, 256>(h, p, s);
     return launch_env_t<V, lmz::RENDER_ST128, ST_THREADS>(h, p, s);
+  }
   switch (h->cfg.tune[0]) {
-    case 32: return launch_env_t<V, lmz::RENDER_TMA, 32>(h, p, s);
     case 64: return launch_env_t<V, lmz::RENDER_TMA, 64>(h, p, s);
+    case 128: return launch_env_t<V, lmz::RENDER_TMA, 128>(h, p, s);
     case 256: return launch_env_t<V, lmz::RENDER_TMA, 256>(h, p, s);
-    case 512: return launch_env_t<V, lmz::RENDER_TMA, 512>(h, p, s);
     default: return launch_env_t<V, lmz::RENDER_TMA, TMA_THREADS>(h, p, s);
   }
 }
@@ -338,7 +341,7 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     if (t != 0 && t != 32 && t != 64 && t != 128 && t != 256 && t != 512)
       return fail(LMZ_ERR_INVALID, "tune[0] (threads per CTA) must be 0, 32, 64, 128, 256 or 512");
     if (cfg->tune[1] < 0 || cfg->tune[1] > 4) return fail(LMZ_ERR_INVALID, "tune[1] (L2 policy) must be 0..4");
-    if (cfg->tune[2] < 0 || cfg->tune[2] > 3) return fail(LMZ_ERR_INVALID, "tune[2] (tile order) must be 0..3");
+    if (cfg->tune[2] != 0) return fail(LMZ_ERR_INVALID, "tune[2] is reserved and must be 0");
     if (cfg->tune[3] < 0 || (cfg->tune[3] & 15)) return fail(LMZ_ERR_INVALID, "tune[3] (bulk split) must be a multiple of 16");
   }
   int ndev = 0;
@@ -373,10 +376,10 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->goal_count, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->episode, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->blob, blob.size());
-  if (e == cudaSuccess) e = cudaMalloc(&h->stats, (lmz::NUM_STATS + 1) * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->stats, (lmz::NUM_STATS + 3) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->goal_count, 0, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(h->episode, 0, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(h->stats, 0, (lmz::NUM_STATS + 1) * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->stats, 0, (lmz::NUM_STATS + 3) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemcpy(h->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     // Before the first reset every env sits on the 'S' cell with the goal on 'X'

@@ -1,7 +1,7 @@
 // lmz_kernels.cuh -- sm_100a kernels of the batched LMaze step/reset path.
 //
-//   lmz_env_kernel      fused reset / step / render: one thread per env does the
-//                       transition (lmaze_env.py:146-196,246-249; lmaze_env_v3.py:
+//   lmz_env_tma_kernel  fused reset / step / render: one thread per env does the
+//   lmz_env_st_kernel   transition (lmaze_env.py:146-196,246-249; lmaze_env_v3.py:
 //                       220-265,398), warp ballots feed the episode statistics, and
 //                       the observation (lmaze_env.py:208-234) is emitted either as
 //                       bulk async shared->global copies (TMA engine) or as 128-bit
@@ -52,14 +52,12 @@ struct KParams {
   int n_cand;                   // entries in the spawn-candidate table
   int s_cell;                   // linear index of the 'S' cell
   int l2_policy;                // L2_* policy of the obs stores (TMA path)
-  int tile_order;               // ORDER_*
+  unsigned long long *work;     // [2]: next tile to hand out, grabbers finished (self re-arming)
   uint32_t bulk_split;          // 0, or the largest single bulk copy in bytes
 };
 
 enum : int { L2_EVICT_FIRST = 1, L2_EVICT_NORMAL = 2, L2_EVICT_LAST = 3, L2_NONE = 4 };
-enum : int { ORDER_WARP_MAJOR = 1, ORDER_CTA_CONTIG = 2, ORDER_CHUNK = 3 };
-constexpr int DEFAULT_L2_POLICY = L2_NONE;
-constexpr int DEFAULT_TILE_ORDER = ORDER_WARP_MAJOR;
+constexpr int DEFAULT_L2_POLICY = L2_EVICT_FIRST;   // the obs is streamed out once (sweep: +0.3 % over no hint)
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
@@ -260,150 +258,251 @@ __device__ __forceinline__ void respawn(EnvRegs &r, const KParams &p, int64_t e,
 }
 
 // ------------------------------------------------------------------ fused reset / step / render
-template <class V, int RENDER, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) lmz_env_kernel(const KParams p) {
+// Everything one env does in a fused call except writing its observation.
+struct LaneOut {
+  uint32_t st;        // packed state after the call
+  bool render;        // obs row must be (re)written
+  bool done;
+  int cls;            // branch taken by the transition (-1: no step)
+  uint32_t eplen;     // stepCount of an episode that finished in this call
+};
+
+template <class V>
+__device__ __forceinline__ LaneOut env_lane(const KParams &p, int64_t e, const uint8_t *cls, const uint16_t *cand) {
+  LaneOut o;
+  o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
+  EnvRegs r = V::unpack(p.state[e]);
+  bool reset_now = false;
+  if (p.mode == MODE_STEP) {
+    const long long a = load_action(p.actions, p.action_dtype, e);
+    uint32_t hits = 0;
+    const StepOut so = transition<V>(r, a, cls, hits);
+    if (V::ID == 0 && hits) p.goal_count[e] += hits;
+    o.done = so.done; o.cls = so.cls;
+    p.reward[e] = __uint_as_float(reward_bits(r.rcode));
+    p.done[e] = so.done ? 1 : 0;
+    if (so.done) o.eplen = r.step;
+    reset_now = so.done && p.autoreset;
+    o.render = true;
+  } else if (p.mode == MODE_RESET) {
+    reset_now = (p.mask == nullptr) || (p.mask[e] != 0);
+    o.render = reset_now;
+  } else {
+    o.render = true;
+  }
+  if (reset_now) {
+    uint32_t ep = p.episode[e];
+    respawn<V>(r, p, e, ep, cls, cand);
+    p.episode[e] = ep;
+  }
+  o.st = V::pack(r);
+  if (p.mode != MODE_RENDER) p.state[e] = o.st;
+  return o;
+}
+
+// Episode statistics of one warp: a ballot + popc per counter (the counts are warp-uniform
+// registers), a shuffle reduction for the episode-length sum, one atomicAdd per counter at the end.
+struct WarpStats {
+  uint32_t steps = 0, ep = 0, goal = 0, wall = 0, move = 0, stale = 0;
+  unsigned long long len = 0;
+  __device__ __forceinline__ void add(bool valid, const LaneOut &o) {
+    steps += __popc(__ballot_sync(0xffffffffu, valid && o.cls >= 0));
+    ep += __popc(__ballot_sync(0xffffffffu, valid && o.done));
+    goal += __popc(__ballot_sync(0xffffffffu, valid && o.done && o.cls == CLS_X));
+    wall += __popc(__ballot_sync(0xffffffffu, valid && o.cls == CLS_W));
+    move += __popc(__ballot_sync(0xffffffffu, valid && (o.cls == CLS_B || o.cls == CLS_X)));
+    stale += __popc(__ballot_sync(0xffffffffu, valid && o.cls == CLS_S));
+    if (valid) len += o.eplen;
+  }
+  __device__ __forceinline__ void flush(unsigned long long *stats, int lane) {
+    unsigned long long v = len;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane != 0 || steps == 0) return;
+    atomicAdd(&stats[STAT_STEPS], (unsigned long long)steps);
+    if (ep) {
+      atomicAdd(&stats[STAT_EPISODES], (unsigned long long)ep);
+      if (ep - goal) atomicAdd(&stats[STAT_TIMEOUTS], (unsigned long long)(ep - goal));
+      atomicAdd(&stats[STAT_EPLEN_SUM], v);
+    }
+    if (goal) atomicAdd(&stats[STAT_GOALS], (unsigned long long)goal);
+    if (wall) atomicAdd(&stats[STAT_WALL_BUMPS], (unsigned long long)wall);
+    if (move) atomicAdd(&stats[STAT_MOVES], (unsigned long long)move);
+    if (stale) atomicAdd(&stats[STAT_STALE], (unsigned long long)stale);
+  }
+};
+
+// Stage the template blob (static channels, zero rows, band table, cell classes, spawn
+// candidates) with ONE bulk async load; the TMA engine signals the mbarrier.
+template <class V>
+__device__ __forceinline__ void stage_blob(unsigned char *smem, uint64_t *bar, const uint8_t *blob) {
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, V::BLOB_BYTES);
+    bulk_g2s(smem, blob, V::BLOB_BYTES, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// Dynamic work distribution.  A B200's SMs do NOT get equal shares of a saturated write path
+// (tools/wbench.cu: with a static env->SM split the first SM finishes ~5 ms of 16 ms before the
+// last and the chip averages 6.4 TB/s; with tiles handed out by an atomic counter the spread is
+// 0.02 ms and the same copies reach 7.5 TB/s).  So tiles of 32 consecutive envs are grabbed from
+// work[0]; work[1] counts finished grabbers and the last one re-arms both for the next launch
+// (self-contained, so the launch is also safe to replay from a CUDA graph).
+__device__ __forceinline__ int64_t grab_tile(unsigned long long *work) {
+  return (int64_t)atomicAdd(&work[0], 1ull);
+}
+__device__ __forceinline__ void finish_grabber(unsigned long long *work, unsigned long long grabbers) {
+  __threadfence();
+  if (atomicAdd(&work[1], 1ull) == grabbers - 1) { work[0] = 0; work[1] = 0; }
+}
+
+template <class V>
+__device__ __forceinline__ LaneOut tile_lane(const KParams &p, int64_t tile, int lane, int64_t tiles,
+                                             const uint8_t *cls, const uint16_t *cand, bool &valid) {
+  LaneOut o;
+  o.st = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
+  const int64_t e = tile * 32 + lane;
+  valid = tile < tiles && e < p.n;
+  if (valid) o = env_lane<V>(p, e, cls, cand);
+  return o;
+}
+
+// ---- render path 1: the TMA engine writes the observation ------------------------------------
+// Warp-granular: each lane owns one env of the warp's 32-env tile.  The loop is software
+// pipelined: the NEXT tile is grabbed and its transitions (loads, table lookups, stores) run
+// while the TMA engine is still draining the copies issued for the previous tile; then lane 0
+// issues, env by env, one cp.async.bulk shared->global copy per blob segment.
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) lmz_env_tma_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   constexpr int WARPS = THREADS / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // Stage the template blob (static channels, zero rows, band table, cell classes,
-  // spawn candidates) with ONE bulk async load; the TMA engine signals the mbarrier.
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, V::BLOB_BYTES);
-    bulk_g2s(smem, p.blob, V::BLOB_BYTES, &bar);
-  }
-  mbar_wait(&bar, 0);
+  const int lane = threadIdx.x & 31;
+  stage_blob<V>(smem, &bar, p.blob);
   const uint8_t *cls = smem + V::CLS_OFF;
   const uint16_t *cand = reinterpret_cast<const uint16_t *>(smem + V::CAND_OFF);
   const uint32_t blob_s = smem_addr(smem);
-
-  uint32_t c_steps = 0, c_ep = 0, c_goal = 0, c_wall = 0, c_move = 0, c_stale = 0;
-  unsigned long long c_len = 0;
-
-  // Tile (= 32 consecutive envs) -> warp mapping.  Default: warp w of CTA b owns tiles
-  // w*grid+b, +grid*WARPS, ... so small batches still spread over all SMs.
+  const uint64_t l2pol = (p.l2_policy != L2_NONE) ? make_l2_policy(p.l2_policy) : 0;
   const int64_t tiles = (p.n + 31) >> 5;
-  int64_t tile, tstride, tend = tiles;
-  if (p.tile_order == ORDER_CTA_CONTIG) {
-    tile = (int64_t)blockIdx.x * WARPS + warp; tstride = (int64_t)gridDim.x * WARPS;
-  } else if (p.tile_order == ORDER_CHUNK) {
-    tile = tiles * blockIdx.x / gridDim.x + warp; tend = tiles * (blockIdx.x + 1) / gridDim.x; tstride = WARPS;
-  } else {
-    tile = (int64_t)warp * gridDim.x + blockIdx.x; tstride = (int64_t)gridDim.x * WARPS;
-  }
-  const uint64_t l2pol = (RENDER == RENDER_TMA && p.l2_policy != L2_NONE) ? make_l2_policy(p.l2_policy) : 0;
-  for (; tile < tend; tile += tstride) {
-    const int64_t e = tile * 32 + lane;
-    const bool valid = e < p.n;
-    uint32_t st = 0;
-    bool render = false, done = false;
-    int cls_taken = -1;
-    if (valid) {
-      st = p.state[e];
-      EnvRegs r = V::unpack(st);
-      bool reset_now = false;
-      if (p.mode == MODE_STEP) {
-        const long long a = load_action(p.actions, p.action_dtype, e);
-        uint32_t hits = 0;
-        const StepOut o = transition<V>(r, a, cls, hits);
-        if (V::ID == 0 && hits) p.goal_count[e] += hits;
-        done = o.done; cls_taken = o.cls;
-        p.reward[e] = __uint_as_float(reward_bits(r.rcode));
-        p.done[e] = done ? 1 : 0;
-        if (done) c_len += r.step;
-        reset_now = done && p.autoreset;
-        render = true;
-      } else if (p.mode == MODE_RESET) {
-        reset_now = (p.mask == nullptr) || (p.mask[e] != 0);
-        render = reset_now;
-      } else {
-        render = true;
-      }
-      if (reset_now) {
-        uint32_t ep = p.episode[e];
-        respawn<V>(r, p, e, ep, cls, cand);
-        p.episode[e] = ep;
-      }
-      st = V::pack(r);
-      if (p.mode != MODE_RENDER) p.state[e] = st;
-    }
-    // ---- episode statistics: one ballot per counter, popc'd into per-warp registers
-    if (p.mode == MODE_STEP) {
-      c_steps += __popc(__ballot_sync(0xffffffffu, valid));
-      c_ep += __popc(__ballot_sync(0xffffffffu, done));
-      c_goal += __popc(__ballot_sync(0xffffffffu, done && cls_taken == CLS_X));
-      c_wall += __popc(__ballot_sync(0xffffffffu, cls_taken == CLS_W));
-      c_move += __popc(__ballot_sync(0xffffffffu, cls_taken == CLS_B || cls_taken == CLS_X));
-      c_stale += __popc(__ballot_sync(0xffffffffu, cls_taken == CLS_S));
-    }
+  WarpStats ws;
+
+  auto next_tile = [&]() {
+    int64_t t = 0;
+    if (lane == 0) t = grab_tile(p.work);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  int64_t tile = next_tile();
+  bool valid;
+  LaneOut o = tile_lane<V>(p, tile, lane, tiles, cls, cand, valid);
+  if (p.mode == MODE_STEP) ws.add(valid, o);
+  while (tile < tiles) {
+    const int64_t ntile = next_tile();
+    bool nvalid;
+    const LaneOut no = tile_lane<V>(p, ntile, lane, tiles, cls, cand, nvalid);
+    if (p.mode == MODE_STEP) ws.add(nvalid, no);
     // ---- observation render (lmaze_env.py:208-234): the env's image is NSEG blob segments
-    unsigned rmask = __ballot_sync(0xffffffffu, render && p.obs != nullptr);
+    unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render && p.obs != nullptr);
     while (rmask) {
       const int l = __ffs(rmask) - 1;
       rmask &= rmask - 1;
-      const uint32_t s = __shfl_sync(0xffffffffu, st, l);
-      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + l) * V::OBS_BYTES;
-      Seg sg[V::NSEG];
-      V::segments(V::unpack(s), sg);
-      if (RENDER == RENDER_TMA) {
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < V::NSEG; ++k) {
-            uint32_t off = 0, left = sg[k].len;
-            while (left) {
-              const uint32_t len = (p.bulk_split && left > p.bulk_split) ? p.bulk_split : left;
-              if (p.l2_policy != L2_NONE) bulk_s2g_hint(dst + sg[k].dst + off, blob_s + sg[k].src + off, len, l2pol);
-              else bulk_s2g(dst + sg[k].dst + off, blob_s + sg[k].src + off, len);
-              off += len; left -= len;
-            }
-          }
-        }
-      } else {
+      const uint32_t s = __shfl_sync(0xffffffffu, o.st, l);
+      if (lane == 0) {
+        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + l) * V::OBS_BYTES;
+        Seg sg[V::NSEG];
+        V::segments(V::unpack(s), sg);
 #pragma unroll
         for (int k = 0; k < V::NSEG; ++k) {
-          const uint32_t n16 = sg[k].len >> 4;
-          const uint32_t src = blob_s + sg[k].src;
-          unsigned char *d = dst + sg[k].dst;
-          uint32_t i = lane;
-          for (; i + 96 < n16; i += 128) {          // 4 independent 16-byte moves per lane in flight
-            const uint4 v0 = lds_v4(src + (i << 4)), v1 = lds_v4(src + ((i + 32) << 4));
-            const uint4 v2 = lds_v4(src + ((i + 64) << 4)), v3 = lds_v4(src + ((i + 96) << 4));
-            st_stream_v4(d + ((size_t)i << 4), v0);
-            st_stream_v4(d + ((size_t)(i + 32) << 4), v1);
-            st_stream_v4(d + ((size_t)(i + 64) << 4), v2);
-            st_stream_v4(d + ((size_t)(i + 96) << 4), v3);
+          uint32_t off = 0, left = sg[k].len;
+          while (left) {
+            const uint32_t len = (p.bulk_split && left > p.bulk_split) ? p.bulk_split : left;
+            if (p.l2_policy != L2_NONE) bulk_s2g_hint(dst + sg[k].dst + off, blob_s + sg[k].src + off, len, l2pol);
+            else bulk_s2g(dst + sg[k].dst + off, blob_s + sg[k].src + off, len);
+            off += len; left -= len;
           }
-          for (; i < n16; i += 32) st_stream_v4(d + ((size_t)i << 4), lds_v4(src + (i << 4)));
         }
       }
     }
+    tile = ntile; o = no; valid = nvalid;
   }
-  if (RENDER == RENDER_TMA) {
-    // the blob must outlive every copy that reads it; also waits for the global writes
-    bulk_commit();
-    bulk_wait_all();
-  }
-  if (p.mode == MODE_STEP && lane == 0 && c_steps) {
-    // c_goal etc. hold the same value in every lane (ballot results); eplen needs a warp sum
-    atomicAdd(&p.stats[STAT_STEPS], (unsigned long long)c_steps);
-    if (c_ep) {
-      atomicAdd(&p.stats[STAT_EPISODES], (unsigned long long)c_ep);
-      atomicAdd(&p.stats[STAT_TIMEOUTS], (unsigned long long)(c_ep - c_goal));
-    }
-    if (c_goal) atomicAdd(&p.stats[STAT_GOALS], (unsigned long long)c_goal);
-    if (c_wall) atomicAdd(&p.stats[STAT_WALL_BUMPS], (unsigned long long)c_wall);
-    if (c_move) atomicAdd(&p.stats[STAT_MOVES], (unsigned long long)c_move);
-    if (c_stale) atomicAdd(&p.stats[STAT_STALE], (unsigned long long)c_stale);
-  }
-  if (p.mode == MODE_STEP) {
-    // episode-length sum: per-lane partials -> warp reduction -> one atomic per warp
-    unsigned long long v = c_len;
+  // the blob must outlive every copy that reads it; wait_group 0 also covers the global writes
+  bulk_commit();
+  bulk_wait_all();
+  if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+  if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
+}
+
+// ---- render path 2: 128-bit vector stores -----------------------------------------------------
+// CTA-cooperative.  Warp 0 grabs a 32-env tile and runs its transitions (one env per lane),
+// parking the packed states in shared memory; then ALL threads copy the tile's observations env
+// by env with LDS.128 -> st.global.cs.v4 (consecutive threads, consecutive 16-byte words) while
+// warp 0 is already working on the next tile (double-buffered, one __syncthreads per tile).
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) lmz_env_st_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_st[2][32];
+  __shared__ long long s_tile[2];
+  constexpr uint32_t NO_RENDER = 0xffffffffu;           // not a packable state (x would be 31)
+  constexpr uint32_t OBS16 = V::OBS_BYTES / 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_blob<V>(smem, &bar, p.blob);
+  const uint8_t *cls = smem + V::CLS_OFF;
+  const uint16_t *cand = reinterpret_cast<const uint16_t *>(smem + V::CAND_OFF);
+  const uint32_t blob_s = smem_addr(smem);
+  const int64_t tiles = (p.n + 31) >> 5;
+  WarpStats ws;
+
+  auto produce = [&](int buf) {                          // warp 0 only
+    int64_t t = 0;
+    if (lane == 0) t = grab_tile(p.work);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    bool valid;
+    const LaneOut o = tile_lane<V>(p, t, lane, tiles, cls, cand, valid);
+    if (p.mode == MODE_STEP) ws.add(valid, o);
+    s_st[buf][lane] = (valid && o.render && p.obs != nullptr) ? o.st : NO_RENDER;
+    if (lane == 0) s_tile[buf] = t;
+  };
+  if (warp == 0) produce(0);
+  for (int buf = 0;; buf ^= 1) {
+    __syncthreads();                                     // s_st[buf] ready; s_st[buf^1] free again
+    const int64_t tile = s_tile[buf];
+    if (tile >= tiles) break;
+    if (warp == 0) produce(buf ^ 1);
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t s = s_st[buf][k];
+      if (s == NO_RENDER) continue;
+      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + k) * V::OBS_BYTES;
+      Seg sg[V::NSEG];
+      V::segments(V::unpack(s), sg);
+      // 16-byte word f of the obs comes from blob byte 16*f + delta[q], q = the segment holding f
+      uint32_t bnd[V::NSEG];
+      int32_t delta[V::NSEG];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (lane == 0 && v) atomicAdd(&p.stats[STAT_EPLEN_SUM], v);
+      for (int q = 0; q < V::NSEG; ++q) { bnd[q] = sg[q].dst >> 4; delta[q] = (int32_t)sg[q].src - (int32_t)sg[q].dst; }
+      auto src_of = [&](uint32_t f) {
+        int32_t d = delta[0];
+#pragma unroll
+        for (int q = 1; q < V::NSEG; ++q) d = (f >= bnd[q]) ? delta[q] : d;
+        return blob_s + (uint32_t)((int32_t)(f << 4) + d);
+      };
+      uint32_t f = tid;
+      for (; f + 3 * THREADS < OBS16; f += 4 * THREADS) {     // 4 independent 16-byte moves in flight
+        const uint4 v0 = lds_v4(src_of(f)), v1 = lds_v4(src_of(f + THREADS));
+        const uint4 v2 = lds_v4(src_of(f + 2 * THREADS)), v3 = lds_v4(src_of(f + 3 * THREADS));
+        st_stream_v4(dst + ((size_t)f << 4), v0);
+        st_stream_v4(dst + ((size_t)(f + THREADS) << 4), v1);
+        st_stream_v4(dst + ((size_t)(f + 2 * THREADS) << 4), v2);
+        st_stream_v4(dst + ((size_t)(f + 3 * THREADS) << 4), v3);
+      }
+      for (; f < OBS16; f += THREADS) st_stream_v4(dst + ((size_t)f << 4), lds_v4(src_of(f)));
+    }
+  }
+  if (warp == 0) {
+    if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+    if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
   }
 }
 

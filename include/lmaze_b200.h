@@ -75,9 +75,9 @@ typedef struct lmz_config {
   int32_t  random_goal;   /* RANDOM_GOAL  (lmaze_env_v3.py:104); ignored by v0 */
   int32_t  render_mode;   /* lmz_render_mode */
   int32_t  tune[4];       /* launch tuning for the TMA render path, 0 = library default:
-                             [0] threads per CTA (32/64/128/256/512)
+                             [0] threads per CTA (TMA path: 32/64/128/256 issuing warps x32; ST128 path: 256/512/1024)
                              [1] L2 policy of the obs stores: 1 evict_first, 2 evict_normal, 3 evict_last, 4 none
-                             [2] tile order: 1 warp-major across the grid, 2 CTA-contiguous, 3 one contiguous chunk per CTA
+                             [2] reserved (0): tiles of 32 envs are handed to SMs dynamically
                              [3] split bulk copies into pieces of at most this many bytes (multiple of 16) */
   int32_t  reserved[3];   /* must be zero */
 } lmz_config;

@@ -73,20 +73,16 @@ def main():
         del env
         return ms
 
-    combos = [("st128", (0, 0, 0, 0))]
+    combos = [("st128", (0, 0, 0, 0)), ("st128", (512, 0, 0, 0)), ("st128", (256, 0, 0, 0))]
     if args.quick:
-        combos += [("tma", (0, 0, 0, 0)), ("tma", (32, 0, 0, 0)), ("tma", (128, 1, 0, 0))]
+        combos += [("tma", (0, 0, 0, 0)), ("tma", (64, 0, 0, 0))]
     else:
         for thr in (32, 64, 128, 256):
             combos.append(("tma", (thr, 0, 0, 0)))
-        for pol in (1, 2, 3):
-            combos.append(("tma", (128, pol, 0, 0)))
-        for order in (2, 3):
-            for thr in (32, 128):
-                combos.append(("tma", (thr, 0, order, 0)))
-        for split in (4096, 16384, 32768):
-            combos.append(("tma", (128, 0, 0, split)))
-        combos += [("tma", (32, 1, 3, 0)), ("tma", (64, 1, 0, 0)), ("tma", (512, 0, 0, 0))]
+        for pol in (1, 2):
+            combos.append(("tma", (32, pol, 0, 0)))
+        for split in (4704, 37632):
+            combos.append(("tma", (32, 0, 0, split)))
     for mode, tune in combos:
         ms = run(mode, tune)
         gbs = N * step_bytes / ms / 1e6
