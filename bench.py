@@ -46,6 +46,10 @@ def parse_args():
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--variant", default="v0", choices=["v0", "v3"])
     ap.add_argument("--render-mode", default="tma", choices=["tma", "st128"])
+    ap.add_argument("--obs-mode", default="full", choices=["full", "compact"])
+    ap.add_argument("--window", type=int, default=0,
+                    help="obs rows kept in HBM (render window); 0 = all envs.  A step then = fused step over "
+                         "every env + a render pass per remaining window, so every env's obs is still produced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the rollout / obs-to-host side measurements")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing")
@@ -192,14 +196,24 @@ def run_reference(args):
 
 
 def workload_config(args, note=None):
+    G, E, C = (12, 7, 4) if args.variant == "v0" else (18, 4, 3)
+    if args.obs_mode == "compact":
+        obs, per_env = "u8 (%d,%d,%d) compact (un-expanded layers; reference image = x%d replication)" % (C, G, G, E), C * G * G
+    else:
+        obs, per_env = "f32 (%d,%d,%d) full render" % (C, G * E, G * E), C * G * E * G * E * 4
+    W = args.window if 0 < args.window < args.envs else args.envs
+    which = ("BASELINE configs[2], HBM roofline run" if args.variant == "v0" and args.obs_mode == "full"
+             else "BASELINE configs[3]-style: largest maze variant" if args.variant == "v3" else "compact-observation mode")
     cfg = {
-        "workload": "lmaze_env_%s %d envs/GPU, fused step+auto-reset+obs render (BASELINE configs[2], HBM roofline run)"
-                    % (args.variant, args.envs),
-        "variant": args.variant, "envs_per_gpu": args.envs, "obs": "f32 (4,84,84) full render" if args.variant == "v0"
-        else "f32 (3,72,72) full render", "actions": "u8 ring [4,N] resident in HBM", "render_mode": args.render_mode,
-        "autoreset": True, "l2": "no flush needed: each step streams %.1f GB of obs, >> 126 MB L2"
-                                 % (args.envs * (V0_OBS_BYTES if args.variant == "v0" else V3_OBS_BYTES) / 1e9),
+        "workload": "lmaze_env_%s %d envs/GPU, fused step+auto-reset+obs render (%s)" % (args.variant, args.envs, which),
+        "variant": args.variant, "envs_per_gpu": args.envs, "obs": obs, "actions": "u8 ring [4,N] resident in HBM",
+        "render_mode": args.render_mode, "obs_mode": args.obs_mode, "autoreset": True,
+        "obs_window_envs": W,
+        "l2": "no flush needed: each step streams %.2f GB of obs, >> 126 MB L2" % (args.envs * per_env / 1e9),
     }
+    if W < args.envs:
+        cfg["window"] = ("obs tensor holds %d of %d envs; a step = 1 fused step launch + %d render-window launches, "
+                         "every env's obs is written once per step" % (W, args.envs, -(-args.envs // W) - 1))
     if note:
         cfg["note"] = note
     return cfg
@@ -220,9 +234,22 @@ def run_ours(args):
 
     import gym_lmaze_b200 as lmz          # raises if the CUDA library is missing: no fallback
     N = args.envs
-    step_bytes = V0_STEP_BYTES if args.variant == "v0" else V3_STEP_BYTES
+    W = args.window if 0 < args.window < N else N
     env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, env_id0=rank * N, autoreset=True,
-                           render_mode=args.render_mode)
+                           render_mode=args.render_mode, obs_mode=args.obs_mode, obs_window=W)
+    windows = list(range(0, N, W))
+    if windows[-1] + W > N:
+        windows[-1] = N - W
+    obs_bytes = env.obs[0].numel() * env.obs.element_size()
+    step_bytes = obs_bytes + 14
+
+    def full_step(actions):
+        """one step = transition of every env + every env's observation written once"""
+        if len(windows) > 1:
+            env.set_window(windows[0])
+        env.step(actions)
+        for lo in windows[1:]:
+            env.render_window(lo)
     R = 4
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ring = torch.randint(0, 4, (R, N), generator=gen, device=dev, dtype=torch.uint8)
@@ -243,7 +270,7 @@ def run_ours(args):
 
     # ---- device-resident inputs: K launches of the fused kernel, CUDA events on the launch stream
     for i in range(args.warmup):
-        env.step(ring[i % R])
+        full_step(ring[i % R])
     launches0 = env.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -252,29 +279,40 @@ def run_ours(args):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
     for i in range(args.steps):
-        env.step(ring[i % R])
+        full_step(ring[i % R])
         evs[i + 1].record()
     barrier()
     total_ms = reduce_max(evs[0].elapsed_time(evs[-1]))
     gpu_launches = env.launch_count - launches0
-    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) / max(1, len(windows)) for i in range(args.steps))
     clocks = sampler.stop() if rank == 0 else None
     value = world * N * args.steps / (total_ms * 1e-3)
-    kernel_ms = total_ms / args.steps            # one kernel launch per step: step time == kernel time
-    achieved = N * step_bytes / (kernel_ms * 1e-3) / 1e9
+    step_ms = total_ms / args.steps
+    launches_per_step = max(1, gpu_launches // args.steps)
+    kernel_ms = step_ms / launches_per_step      # default config: ONE launch per step, step time == kernel time
+    achieved = N * step_bytes / (step_ms * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory)
     a_host = torch.randint(0, 4, (R, N), dtype=torch.uint8).pin_memory()
     r_host = torch.empty(N, dtype=torch.float32).pin_memory()
     d_host = torch.empty(N, dtype=torch.uint8).pin_memory()
-    for i in range(max(3, args.warmup)):
+    def full_step_host(i):
+        if len(windows) > 1:
+            env.set_window(windows[0])
         env.step_host(a_host[i % R], r_host, d_host)
+        for lo in windows[1:]:
+            env.render_window(lo)
+        if len(windows) > 1:
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(3, args.warmup)):
+        full_step_host(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
-        env.step_host(a_host[i % R], r_host, d_host)
+        full_step_host(i)
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -295,7 +333,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks,
@@ -305,11 +343,15 @@ def run_ours(args):
                        "full obs D2H variant", "reward_checksum": checksum},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(args.variant, args.render_mode), "peak_source": peak_src,
-                     "kernel": "lmz_env_%s_kernel<%s>" % ("tma" if args.render_mode == "tma" else "st", args.variant.upper()),
+                     "traffic": recorded_traffic(args.variant, args.render_mode)
+                     if (args.obs_mode == "full" and W == N and N == 1 << 20) else None, "peak_source": peak_src,
+                     "kernel": "lmz_env_%s_kernel<%s>" % ("compact" if args.obs_mode == "compact" else
+                                                          "tma" if args.render_mode == "tma" else "st",
+                                                          args.variant.upper()),
+                     "launches_per_step": launches_per_step,
                      "note": "write-only stream; peak is the measured read+write COPY rate, so frac may exceed 1 "
                              "(compare extras.pure_write_fill_gbs)",
-                     "bytes_per_env_step": step_bytes, "bytes_per_launch": N * step_bytes,
+                     "bytes_per_env_step": step_bytes, "bytes_per_launch": N * step_bytes // launches_per_step,
                      "kernel_ms_avg": kernel_ms, "kernel_ms_min": per_step[0],
                      "kernel_ms_median": per_step[len(per_step) // 2]},
         "episode_stats": stats,
@@ -405,6 +447,18 @@ def side_measurements(env, args, torch, dev):
 
 def main():
     args = parse_args()
+    # Only the JSON line may reach stdout (NCCL / torchrun banners go to stderr).
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    import builtins
+    _print = builtins.print
+
+    def json_print(*a, **k):
+        k.setdefault("file", out)
+        _print(*a, **k)
+        out.flush()
+    globals()["print"] = json_print
     if args.impl == "reference":
         run_reference(args)
     else:

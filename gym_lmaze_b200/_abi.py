@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_PKG, "liblmaze_b200.so")
 
 LMZ_V0, LMZ_V3 = 0, 3
 RENDER_TMA, RENDER_ST128 = 0, 1
+OBS_FULL, OBS_COMPACT = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 NUM_STATS = 8
 ST_COLS = 8
@@ -19,7 +20,8 @@ STATE_COLS = ("x", "y", "goal_x", "goal_y", "step_count", "reward_code", "goal_c
 
 # every symbol include/lmaze_b200.h declares (tests/test_abi_symbols.py checks the header against this)
 EXPORTS = (
-    "lmz_abi_version", "lmz_last_error", "lmz_default_config", "lmz_obs_shape", "lmz_grid_size", "lmz_layout",
+    "lmz_abi_version", "lmz_last_error", "lmz_default_config", "lmz_obs_shape", "lmz_grid_size", "lmz_obs_desc",
+    "lmz_layout", "lmz_set_window", "lmz_set_window_dl",
     "lmz_create", "lmz_destroy", "lmz_bind", "lmz_bind_dl", "lmz_reset", "lmz_reset_dl", "lmz_step",
     "lmz_step_dl", "lmz_step_host", "lmz_render", "lmz_rollout", "lmz_rollout_dl", "lmz_get_state",
     "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
@@ -39,7 +41,8 @@ class LmzConfig(ctypes.Structure):
         ("random_goal", ctypes.c_int32),
         ("render_mode", ctypes.c_int32),
         ("tune", ctypes.c_int32 * 4),
-        ("reserved", ctypes.c_int32 * 3),
+        ("obs_mode", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 2),
     ]
 
 
@@ -69,6 +72,9 @@ def load():
     L.lmz_default_config.restype = None
     L.lmz_obs_shape.argtypes = [i32, ctypes.POINTER(i64 * 3)]
     L.lmz_grid_size.argtypes = [i32]
+    L.lmz_obs_desc.argtypes = [i32, i32, ctypes.POINTER(i64 * 3), ctypes.POINTER(i32)]
+    L.lmz_set_window.argtypes = [vp, vp, i64, i64]
+    L.lmz_set_window_dl.argtypes = [vp, vp, i64]
     L.lmz_layout.argtypes = [i32, ctypes.c_char_p]
     L.lmz_create.argtypes = [ctypes.POINTER(LmzConfig), ctypes.POINTER(vp)]
     L.lmz_destroy.argtypes = [vp]

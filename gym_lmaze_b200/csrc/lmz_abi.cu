@@ -90,9 +90,16 @@ void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand
       for (int jj = 0; jj < V::E; ++jj) f[ii * V::S + y * V::E + jj] = 1.0f;
   }
   uint16_t *cand = reinterpret_cast<uint16_t *>(blob.data() + V::CAND_OFF);
+  unsigned char *compact = blob.data() + V::COMPACT_OFF;   // u8 [C][G][G]: the un-expanded static layers
   n_cand = 0; s_cell = 0; x_cell = 0;
   for (int i = 0; i < V::G * V::G; ++i) {
     const char c = cells[i];
+    if (V::ID == 0) {
+      compact[1 * V::G * V::G + i] = (c == 'W'); compact[2 * V::G * V::G + i] = (c == 'X');
+      compact[3 * V::G * V::G + i] = (c == 'B');
+    } else {
+      compact[i] = (c == 'B' || c == 'S' || c == 'X');
+    }
     blob[V::CLS_OFF + i] = (unsigned char)cls_of(c);
     if (c == 'S' && s_cell == 0) s_cell = i;
     if (c == 'X' && x_cell == 0) x_cell = i;
@@ -116,9 +123,12 @@ struct lmz_env {
   unsigned long long *stats;     // NUM_STATS counters + 1 error counter + 2 work-distribution words
   void *act_stage;               // lmz_step_host staging, lazily allocated (N * 8 bytes)
   // bound outputs (caller-owned)
-  float *obs, *reward;
+  void *obs;                     // f32 [win_n][C][S][S] or u8 [win_n][C][G][G]
+  float *reward;
   uint8_t *done;
   bool bound;
+  int64_t win_lo, win_n;         // obs rows hold envs [win_lo, win_lo + win_n)
+  size_t compact_bytes_per_env;
   int n_cand, s_cell, x_cell;
   uint64_t rollout_t;            // rollout steps taken so far (keys the action RNG)
   int64_t launches;
@@ -143,6 +153,8 @@ lmz::KParams base_params(lmz_env *h) {
   p.n = h->cfg.num_envs;
   p.state = h->state; p.goal_count = h->goal_count; p.episode = h->episode;
   p.obs = h->obs; p.reward = h->reward; p.done = h->done;
+  p.win_lo = h->win_lo; p.win_n = h->win_n;
+  p.tile_begin = 0; p.tile_end = (p.n + 31) / 32;
   p.blob = h->blob; p.stats = h->stats;
   p.errors = reinterpret_cast<unsigned int *>(h->stats + lmz::NUM_STATS);
   p.seed = h->cfg.seed; p.env_id0 = (uint64_t)h->cfg.env_id0;
@@ -168,8 +180,8 @@ int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "env kernel does not fit on an SM");
     configured_dev = h->cfg.device;
   }
-  // persistent grid: a whole number of CTAs per SM, never more work units than envs
-  const int64_t units = (RENDER == lmz::RENDER_TMA) ? (p.n + 31) / 32 : p.n;
+  // persistent grid: a whole number of CTAs per SM, never more CTAs than tiles
+  const int64_t units = p.tile_end - p.tile_begin;
   int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
   if (grid > units) grid = units;
   if (grid < 1) grid = 1;
@@ -179,9 +191,23 @@ int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return LMZ_OK;
 }
 
+// transition-only (no obs bound) and compact-obs launches: small hardware-scheduled CTAs
+template <class V>
+int launch_compact(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  constexpr int THREADS = 128;
+  const int64_t units = p.tile_end - p.tile_begin;
+  const int64_t grid = (units + THREADS / 32 - 1) / (THREADS / 32);
+  if (grid < 1) return LMZ_OK;
+  lmz::lmz_env_compact_kernel<V, THREADS><<<(unsigned)grid, THREADS, 0, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
 template <class V>
 int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (h->cfg.render_mode == LMZ_RENDER_ST128 && p.obs != nullptr) {
+  if (p.obs == nullptr || h->cfg.obs_mode == LMZ_OBS_COMPACT) return launch_compact<V>(h, p, s);
+  if (h->cfg.render_mode == LMZ_RENDER_ST128) {
     if (h->cfg.tune[0] == 512) return launch_env_t<V, lmz::RENDER_ST128, 512>(h, p, s);
     if (h->cfg.tune[0] == 256) return launch_env_t<V, lmz::RENDER_ST128, 256>(h, p, s);
     return launch_env_t<V, lmz::RENDER_ST128, ST_THREADS>(h, p, s);
@@ -307,6 +333,20 @@ int lmz_obs_shape(int32_t variant, int64_t shape[3]) {
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
+int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *elem_bytes) {
+  if (!shape) return fail(LMZ_ERR_INVALID, "shape is NULL");
+  if (int rc = lmz_obs_shape(variant, shape)) return rc;
+  if (obs_mode == LMZ_OBS_COMPACT) {
+    shape[1] = shape[2] = lmz_grid_size(variant);
+    if (elem_bytes) *elem_bytes = 1;
+  } else if (obs_mode == LMZ_OBS_FULL) {
+    if (elem_bytes) *elem_bytes = 4;
+  } else {
+    return fail(LMZ_ERR_INVALID, "unknown obs_mode %d", obs_mode);
+  }
+  return LMZ_OK;
+}
+
 int lmz_grid_size(int32_t variant) {
   if (variant == LMZ_V0) return lmz::V0::G;
   if (variant == LMZ_V3) return lmz::V3::G;
@@ -334,8 +374,10 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
   if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128)
     return fail(LMZ_ERR_INVALID, "unknown render_mode %d", cfg->render_mode);
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 2; ++i)
     if (cfg->reserved[i] != 0) return fail(LMZ_ERR_INVALID, "lmz_config.reserved must be zero");
+  if (cfg->obs_mode != LMZ_OBS_FULL && cfg->obs_mode != LMZ_OBS_COMPACT)
+    return fail(LMZ_ERR_INVALID, "unknown obs_mode %d", cfg->obs_mode);
   {
     const int t = cfg->tune[0];
     if (t != 0 && t != 32 && t != 64 && t != 128 && t != 256 && t != 512)
@@ -362,12 +404,15 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
+  h->win_lo = 0; h->win_n = cfg->num_envs;
   std::vector<unsigned char> blob;
   if (cfg->variant == LMZ_V0) {
     h->G = lmz::V0::G; h->C = lmz::V0::C; h->S = lmz::V0::S; h->obs_bytes_per_env = lmz::V0::OBS_BYTES;
+    h->compact_bytes_per_env = lmz::V0::COMPACT_BYTES;
     build_blob<lmz::V0>(V0_CELLS, blob, h->n_cand, h->s_cell, h->x_cell);
   } else {
     h->G = lmz::V3::G; h->C = lmz::V3::C; h->S = lmz::V3::S; h->obs_bytes_per_env = lmz::V3::OBS_BYTES;
+    h->compact_bytes_per_env = lmz::V3::COMPACT_BYTES;
     build_blob<lmz::V3>(V3_CELLS, blob, h->n_cand, h->s_cell, h->x_cell);
   }
   const size_t n = (size_t)cfg->num_envs;
@@ -412,28 +457,58 @@ int lmz_destroy(lmz_env *h) {
   return LMZ_OK;
 }
 
-int lmz_bind(lmz_env *h, float *obs, float *reward, uint8_t *done) {
+int lmz_bind(lmz_env *h, void *obs, float *reward, uint8_t *done) {
   if (int rc = check_handle(h)) return rc;
   if (!reward || !done) return fail(LMZ_ERR_INVALID, "reward/done must not be NULL");
   if ((reinterpret_cast<uintptr_t>(obs) & 15u) != 0) return fail(LMZ_ERR_INVALID, "obs must be 16-byte aligned");
   if ((reinterpret_cast<uintptr_t>(reward) & 3u) != 0) return fail(LMZ_ERR_INVALID, "reward must be 4-byte aligned");
   h->obs = obs; h->reward = reward; h->done = done; h->bound = true;
+  h->win_lo = 0; h->win_n = h->cfg.num_envs;
   return LMZ_OK;
+}
+
+static int check_obs_dl(lmz_env *h, DLManagedTensor *obs, int64_t rows, void **po) {
+  if (h->cfg.obs_mode == LMZ_OBS_COMPACT) {
+    Want w{"obs", kDLUInt, 8, 4, {rows, h->C, h->G, h->G}, false, 16};
+    return check_dl(h, obs, w, po, nullptr);
+  }
+  Want w{"obs", kDLFloat, 32, 4, {rows, h->C, h->S, h->S}, false, 16};
+  return check_dl(h, obs, w, po, nullptr);
 }
 
 int lmz_bind_dl(lmz_env *h, DLManagedTensor *obs, DLManagedTensor *reward, DLManagedTensor *done) {
   if (int rc = check_handle(h)) return rc;
   const int64_t n = h->cfg.num_envs;
   void *po = nullptr, *pr = nullptr, *pd = nullptr;
-  if (obs) {
-    Want w{"obs", kDLFloat, 32, 4, {n, h->C, h->S, h->S}, false, 16};
-    if (int rc = check_dl(h, obs, w, &po, nullptr)) return rc;
-  }
+  if (obs)
+    if (int rc = check_obs_dl(h, obs, n, &po)) return rc;
   Want wr{"reward", kDLFloat, 32, 1, {n, 0, 0, 0}, false, 4};
   if (int rc = check_dl(h, reward, wr, &pr, nullptr)) return rc;
   Want wd{"done", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
   if (int rc = check_dl(h, done, wd, &pd, nullptr)) return rc;
-  return lmz_bind(h, static_cast<float *>(po), static_cast<float *>(pr), static_cast<uint8_t *>(pd));
+  return lmz_bind(h, po, static_cast<float *>(pr), static_cast<uint8_t *>(pd));
+}
+
+int lmz_set_window(lmz_env *h, void *obs, int64_t env_lo, int64_t env_count) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_bound(h)) return rc;
+  if (!obs) return fail(LMZ_ERR_INVALID, "obs is NULL");
+  if ((reinterpret_cast<uintptr_t>(obs) & 15u) != 0) return fail(LMZ_ERR_INVALID, "obs must be 16-byte aligned");
+  if (env_lo < 0 || env_count < 1 || env_lo + env_count > h->cfg.num_envs)
+    return fail(LMZ_ERR_INVALID, "window [%lld, %lld) outside [0, %lld)", (long long)env_lo,
+                (long long)(env_lo + env_count), (long long)h->cfg.num_envs);
+  h->obs = obs; h->win_lo = env_lo; h->win_n = env_count;
+  return LMZ_OK;
+}
+
+int lmz_set_window_dl(lmz_env *h, DLManagedTensor *obs, int64_t env_lo) {
+  if (int rc = check_handle(h)) return rc;
+  if (!obs) return fail(LMZ_ERR_INVALID, "obs: DLManagedTensor is NULL");
+  if (obs->dl_tensor.ndim < 1) return fail(LMZ_ERR_INVALID, "obs: ndim %d, want 4", obs->dl_tensor.ndim);
+  const int64_t rows = obs->dl_tensor.shape[0];
+  void *po = nullptr;
+  if (int rc = check_obs_dl(h, obs, rows, &po)) return rc;
+  return lmz_set_window(h, po, env_lo, rows);
 }
 
 int lmz_reset(lmz_env *h, const uint8_t *mask, const int32_t *spawn, void *stream) {
@@ -490,7 +565,7 @@ int lmz_step_dl(lmz_env *h, DLManagedTensor *actions, DLManagedTensor *spawn, vo
 }
 
 int lmz_step_host(lmz_env *h, const void *actions_host, int32_t action_dtype, float *reward_host,
-                  uint8_t *done_host, float *obs_host, void *stream) {
+                  uint8_t *done_host, void *obs_host, void *stream) {
   if (int rc = check_handle(h)) return rc;
   if (int rc = check_bound(h)) return rc;
   if (!actions_host || !reward_host || !done_host) return fail(LMZ_ERR_INVALID, "host buffers must not be NULL");
@@ -506,7 +581,10 @@ int lmz_step_host(lmz_env *h, const void *actions_host, int32_t action_dtype, fl
   if (int rc = lmz_step(h, h->act_stage, action_dtype, nullptr, stream)) return rc;
   LMZ_CUDA(cudaMemcpyAsync(reward_host, h->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
   LMZ_CUDA(cudaMemcpyAsync(done_host, h->done, n, cudaMemcpyDeviceToHost, s));
-  if (obs_host) LMZ_CUDA(cudaMemcpyAsync(obs_host, h->obs, n * h->obs_bytes_per_env, cudaMemcpyDeviceToHost, s));
+  if (obs_host) {
+    const size_t per_env = h->cfg.obs_mode == LMZ_OBS_COMPACT ? h->compact_bytes_per_env : h->obs_bytes_per_env;
+    LMZ_CUDA(cudaMemcpyAsync(obs_host, h->obs, (size_t)h->win_n * per_env, cudaMemcpyDeviceToHost, s));
+  }
   LMZ_CUDA(cudaStreamSynchronize(s));
   return LMZ_OK;
 }
@@ -518,6 +596,8 @@ int lmz_render(lmz_env *h, void *stream) {
   DeviceGuard guard(h->cfg.device);
   lmz::KParams p = base_params(h);
   p.mode = lmz::MODE_RENDER;
+  p.tile_begin = h->win_lo / 32;                     // only the tiles that intersect the window
+  p.tile_end = (h->win_lo + h->win_n + 31) / 32;
   return launch_env(h, p, static_cast<cudaStream_t>(stream));
 }
 

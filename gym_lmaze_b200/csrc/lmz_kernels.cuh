@@ -24,6 +24,7 @@ namespace lmz {
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
 enum : int { ACT_U8 = 0, ACT_I32 = 1, ACT_I64 = 2 };
 enum : int { RENDER_TMA = 0, RENDER_ST128 = 1 };
+enum : int { OBS_FULL = 0, OBS_COMPACT = 1 };
 enum : int {
   STAT_STEPS = 0, STAT_EPISODES, STAT_GOALS, STAT_TIMEOUTS, STAT_WALL_BUMPS, STAT_MOVES, STAT_STALE,
   STAT_EPLEN_SUM, NUM_STATS
@@ -39,7 +40,9 @@ struct KParams {
   uint32_t *state;              // packed per-env state
   uint32_t *goal_count;         // goalCount per env (v0; lmaze_env.py:24,195)
   uint32_t *episode;            // resets so far (RNG counter)
-  float *obs;                   // [n][C][S][S] or null
+  void *obs;                    // f32 [win_n][C][S][S], or u8 [win_n][C][G][G] (compact), or null
+  int64_t win_lo, win_n;        // obs rows hold envs [win_lo, win_lo + win_n)
+  int64_t tile_begin, tile_end; // tiles (32 envs) this launch visits
   float *reward;                // [n] or [T][n]
   uint8_t *done;                // [n] or [T][n]
   const uint8_t *blob;          // template blob in global memory
@@ -366,7 +369,10 @@ __device__ __forceinline__ LaneOut tile_lane(const KParams &p, int64_t tile, int
   o.st = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
   const int64_t e = tile * 32 + lane;
   valid = tile < tiles && e < p.n;
-  if (valid) o = env_lane<V>(p, e, cls, cand);
+  if (valid) {
+    o = env_lane<V>(p, e, cls, cand);
+    o.render = o.render && p.obs != nullptr && e >= p.win_lo && e < p.win_lo + p.win_n;   // render window
+  }
   return o;
 }
 
@@ -386,12 +392,12 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_tma_kernel(const KParams p
   const uint16_t *cand = reinterpret_cast<const uint16_t *>(smem + V::CAND_OFF);
   const uint32_t blob_s = smem_addr(smem);
   const uint64_t l2pol = (p.l2_policy != L2_NONE) ? make_l2_policy(p.l2_policy) : 0;
-  const int64_t tiles = (p.n + 31) >> 5;
+  const int64_t tiles = p.tile_end;
   WarpStats ws;
 
   auto next_tile = [&]() {
     int64_t t = 0;
-    if (lane == 0) t = grab_tile(p.work);
+    if (lane == 0) t = p.tile_begin + grab_tile(p.work);
     return __shfl_sync(0xffffffffu, t, 0);
   };
   int64_t tile = next_tile();
@@ -404,13 +410,13 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_tma_kernel(const KParams p
     const LaneOut no = tile_lane<V>(p, ntile, lane, tiles, cls, cand, nvalid);
     if (p.mode == MODE_STEP) ws.add(nvalid, no);
     // ---- observation render (lmaze_env.py:208-234): the env's image is NSEG blob segments
-    unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render && p.obs != nullptr);
+    unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render);
     while (rmask) {
       const int l = __ffs(rmask) - 1;
       rmask &= rmask - 1;
       const uint32_t s = __shfl_sync(0xffffffffu, o.st, l);
       if (lane == 0) {
-        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + l) * V::OBS_BYTES;
+        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + l - p.win_lo) * V::OBS_BYTES;
         Seg sg[V::NSEG];
         V::segments(V::unpack(s), sg);
 #pragma unroll
@@ -452,17 +458,17 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_st_kernel(const KParams p)
   const uint8_t *cls = smem + V::CLS_OFF;
   const uint16_t *cand = reinterpret_cast<const uint16_t *>(smem + V::CAND_OFF);
   const uint32_t blob_s = smem_addr(smem);
-  const int64_t tiles = (p.n + 31) >> 5;
+  const int64_t tiles = p.tile_end;
   WarpStats ws;
 
   auto produce = [&](int buf) {                          // warp 0 only
     int64_t t = 0;
-    if (lane == 0) t = grab_tile(p.work);
+    if (lane == 0) t = p.tile_begin + grab_tile(p.work);
     t = __shfl_sync(0xffffffffu, t, 0);
     bool valid;
     const LaneOut o = tile_lane<V>(p, t, lane, tiles, cls, cand, valid);
     if (p.mode == MODE_STEP) ws.add(valid, o);
-    s_st[buf][lane] = (valid && o.render && p.obs != nullptr) ? o.st : NO_RENDER;
+    s_st[buf][lane] = (valid && o.render) ? o.st : NO_RENDER;
     if (lane == 0) s_tile[buf] = t;
   };
   if (warp == 0) produce(0);
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_st_kernel(const KParams p)
     for (int k = 0; k < 32; ++k) {
       const uint32_t s = s_st[buf][k];
       if (s == NO_RENDER) continue;
-      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + k) * V::OBS_BYTES;
+      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + (size_t)(tile * 32 + k - p.win_lo) * V::OBS_BYTES;
       Seg sg[V::NSEG];
       V::segments(V::unpack(s), sg);
       // 16-byte word f of the obs comes from blob byte 16*f + delta[q], q = the segment holding f
@@ -504,6 +510,49 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_st_kernel(const KParams p)
     if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
     if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
   }
+}
+
+// ---- render path 3: compact observation (u8, un-expanded layers) -------------------------------
+// obs_mode OBS_COMPACT: the env's observation is written as uint8 [C][G][G] -- the reference's
+// `state` layers before its xE upsample (lmaze_env.py:208-215) -- 576 B (v0) / 972 B (v3) per env
+// instead of 112,896 / 62,208.  The reference image is exactly repeat_interleave(compact, E) on both
+// axes.  Small CTAs (hardware-scheduled), one warp per 32-env tile, one thread per env for the
+// transition; the tile's compact rows are then stored as consecutive 32-bit words, lanes on
+// consecutive words (coalesced 128 B per warp store).
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams p) {
+  __shared__ __align__(16) unsigned char tab[V::TABLES_BYTES];
+  constexpr int WARPS = THREADS / 32;
+  constexpr uint32_t W = V::COMPACT_BYTES / 4;           // 32-bit words per env (v0 144, v3 243)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < V::TABLES_BYTES / 4; i += THREADS)
+    reinterpret_cast<uint32_t *>(tab)[i] = reinterpret_cast<const uint32_t *>(p.blob + V::TABLES_OFF)[i];
+  __syncthreads();
+  const uint8_t *cls = tab;
+  const uint16_t *cand = reinterpret_cast<const uint16_t *>(tab + (V::CAND_OFF - V::TABLES_OFF));
+  const uint32_t *tmpl = reinterpret_cast<const uint32_t *>(tab + (V::COMPACT_OFF - V::TABLES_OFF));
+  WarpStats ws;
+  const int64_t tile = p.tile_begin + (int64_t)blockIdx.x * WARPS + warp;
+  bool valid;
+  const LaneOut o = tile_lane<V>(p, tile, lane, p.tile_end, cls, cand, valid);
+  if (p.mode == MODE_STEP) ws.add(valid, o);
+  const unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render);
+  if (rmask) {
+    uint32_t hot[V::NHOT];
+    V::hot_bytes(V::unpack(o.st), hot);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.obs) + (size_t)(tile * 32 - p.win_lo) * W;
+    for (uint32_t f = lane; f < 32 * W; f += 32) {
+      const uint32_t env = f / W, w = f - env * W;       // which env of the tile, which word of its row
+      uint32_t v = tmpl[w];
+#pragma unroll
+      for (int q = 0; q < V::NHOT; ++q) {
+        const uint32_t h = __shfl_sync(0xffffffffu, hot[q], env);
+        if ((h >> 2) == w) v |= 1u << (8 * (h & 3));
+      }
+      if ((rmask >> env) & 1u) __stcs(dst + f, v);
+    }
+  }
+  if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
 }
 
 // ------------------------------------------------------------------ T-step rollout, no per-step obs

@@ -57,7 +57,11 @@ struct V0 {
   static constexpr uint32_t CLS_OFF = BAND_OFF + G * BAND_BYTES;
   static constexpr uint32_t CAND_OFF = CLS_OFF + align16(G * G);
   static constexpr int MAX_CAND = 80;
-  static constexpr uint32_t BLOB_BYTES = CAND_OFF + align16(MAX_CAND * 2);
+  static constexpr uint32_t COMPACT_OFF = CAND_OFF + align16(MAX_CAND * 2);   // u8 [C][G][G] un-expanded layers
+  static constexpr uint32_t COMPACT_BYTES = C * G * G;                         // 576
+  static constexpr uint32_t BLOB_BYTES = COMPACT_OFF + align16(COMPACT_BYTES);
+  static constexpr uint32_t TABLES_OFF = CLS_OFF, TABLES_BYTES = BLOB_BYTES - CLS_OFF;
+  static constexpr int NHOT = 1;                                               // one-hot bytes per env in the compact obs
   static constexpr int NSEG = 3;
   static constexpr uint32_t STEP_SAT = (1u << 20) - 1;
   static constexpr int STEP_LIMIT = 100;                             // lmaze_env.py:247
@@ -72,6 +76,8 @@ struct V0 {
   __host__ __device__ static inline uint32_t pack(const EnvRegs &r) {
     return (uint32_t)r.x | ((uint32_t)r.y << 5) | ((uint32_t)r.rcode << 10) | (r.step << 12);
   }
+  // compact obs = static u8 layers with the ball's byte set in layer 0 (lmaze_env.py:80)
+  __host__ __device__ static inline void hot_bytes(const EnvRegs &r, uint32_t *hot) { hot[0] = (uint32_t)(r.x * G + r.y); }
   __host__ __device__ static inline void segments(const EnvRegs &r, Seg *sg) {
     const uint32_t top = (uint32_t)r.x * E * ROW_BYTES;               // rows above the ball band
     sg[0] = {0u, ZERO_OFF, top};
@@ -95,7 +101,11 @@ struct V3 {
   static constexpr uint32_t CLS_OFF = BAND_OFF + G * BAND_BYTES;
   static constexpr uint32_t CAND_OFF = CLS_OFF + align16(G * G);
   static constexpr int MAX_CAND = 80;
-  static constexpr uint32_t BLOB_BYTES = CAND_OFF + align16(MAX_CAND * 2);
+  static constexpr uint32_t COMPACT_OFF = CAND_OFF + align16(MAX_CAND * 2);
+  static constexpr uint32_t COMPACT_BYTES = C * G * G;                         // 972
+  static constexpr uint32_t BLOB_BYTES = COMPACT_OFF + align16(COMPACT_BYTES);
+  static constexpr uint32_t TABLES_OFF = CLS_OFF, TABLES_BYTES = BLOB_BYTES - CLS_OFF;
+  static constexpr int NHOT = 2;
   static constexpr int NSEG = 5;
   static constexpr uint32_t STEP_SAT = (1u << 12) - 1;
   static constexpr int STEP_LIMIT = 100;                             // lmaze_env_v3.py:99
@@ -109,6 +119,10 @@ struct V3 {
   }
   __host__ __device__ static inline uint32_t pack(const EnvRegs &r) {
     return (uint32_t)r.x | ((uint32_t)r.y << 5) | ((uint32_t)r.gx << 10) | ((uint32_t)r.gy << 15) | (r.step << 20);
+  }
+  // compact obs: layer 1 = ball one-hot, layer 2 = goal one-hot (lmaze_env_v3.py:167,182)
+  __host__ __device__ static inline void hot_bytes(const EnvRegs &r, uint32_t *hot) {
+    hot[0] = (uint32_t)(G * G + r.x * G + r.y); hot[1] = (uint32_t)(2 * G * G + r.gx * G + r.gy);
   }
   __host__ __device__ static inline void segments(const EnvRegs &r, Seg *sg) {
     const uint32_t btop = (uint32_t)r.x * E * ROW_BYTES;

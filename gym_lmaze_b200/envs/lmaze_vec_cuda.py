@@ -23,6 +23,7 @@ from ..spaces import make_spaces
 _VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
              "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3}
 _RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128}
+_OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT}
 # lmaze_env_v3.py:236-247 -- the strings v3's step() accepts; anything else is its unmatched branch
 _V3_WORDS = {"left": 0, "0": 0, "right": 1, "1": 1, "up": 2, "2": 2, "down": 3, "3": 3}
 INVALID_ACTION = 255
@@ -43,11 +44,14 @@ class LmazeVecCuda(object):
     metadata = {"render.modes": ["human"]}          # lmaze_env.py:12
 
     def __init__(self, num_envs=1, variant="v0", device=None, seed=0, autoreset=True, render_mode="tma",
-                 env_id0=0, random_ball=True, random_goal=True, with_obs=True, tune=None):
+                 env_id0=0, random_ball=True, random_goal=True, with_obs=True, tune=None, obs_mode="full",
+                 obs_window=None):
         if variant not in _VARIANTS:
             raise ValueError("unknown variant %r (built: v0, v3)" % (variant,))
         if render_mode not in _RENDER:
             raise ValueError("render_mode must be 'tma' or 'st128'")
+        if obs_mode not in _OBS_MODE:
+            raise ValueError("obs_mode must be 'full' or 'compact'")
         self._lib = _abi.load()          # raises if the CUDA extension is missing: no fallback
         if not torch.cuda.is_available():
             raise RuntimeError("LmazeVecCuda needs a CUDA device; gym_lmaze_b200 has no CPU path")
@@ -64,9 +68,14 @@ class LmazeVecCuda(object):
 
         shape = (ctypes.c_int64 * 3)()
         _abi.check(self._lib.lmz_obs_shape(self.variant, ctypes.byref(shape)))
-        self.obs_shape = tuple(shape)
+        self.full_obs_shape = tuple(shape)               # the reference's observation_space shape
+        self.obs_mode = obs_mode
+        _abi.check(self._lib.lmz_obs_desc(self.variant, _OBS_MODE[obs_mode], ctypes.byref(shape), None))
+        self.obs_shape = tuple(shape)                    # shape of one row of `self.obs` in this obs_mode
+        self.obs_dtype = torch.float32 if obs_mode == "full" else torch.uint8
         self.grid_size = self._lib.lmz_grid_size(self.variant)
-        self.single_action_space, self.single_observation_space = make_spaces(4, self.obs_shape)
+        self.expansion = self.full_obs_shape[1] // self.grid_size
+        self.single_action_space, self.single_observation_space = make_spaces(4, self.full_obs_shape)
         self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
         self.VISUALIZE = False           # lmaze_env.py:26; cv2 display is out of scope
 
@@ -76,6 +85,7 @@ class LmazeVecCuda(object):
         cfg.seed, cfg.device = self.seed & 0xFFFFFFFFFFFFFFFF, self.device.index
         cfg.autoreset, cfg.random_ball, cfg.random_goal = int(autoreset), int(random_ball), int(random_goal)
         cfg.render_mode = _RENDER[render_mode]
+        cfg.obs_mode = _OBS_MODE[obs_mode]
         for i, v in enumerate(tune or ()):
             cfg.tune[i] = int(v)
         handle = ctypes.c_void_p()
@@ -84,7 +94,12 @@ class LmazeVecCuda(object):
 
         # caller-owned (PyTorch) output tensors, bound once; the kernels write them in place
         n = self.num_envs
-        self.obs = torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=self.device) if with_obs else None
+        self.obs_window = n if obs_window is None else int(obs_window)
+        if not (1 <= self.obs_window <= n):
+            raise ValueError("obs_window must be in [1, num_envs]")
+        self.window_lo = 0
+        self.obs = (torch.empty((self.obs_window,) + self.obs_shape, dtype=self.obs_dtype, device=self.device)
+                    if with_obs else None)
         self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
         self._done_u8 = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self.done = self._done_u8.view(torch.bool)
@@ -95,11 +110,46 @@ class LmazeVecCuda(object):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _bind(self):
-        po, ko = _abi.dl(self.obs)
+        windowed = self.obs is not None and self.obs_window < self.num_envs
+        po, ko = _abi.dl(None if windowed else self.obs)
         pr, kr = _abi.dl(self.reward)
         pd, kd = _abi.dl(self._done_u8)
         _abi.check(self._lib.lmz_bind_dl(self._h, po, pr, pd))
         self._bound_keepalive = (ko, kr, kd)
+        if windowed:
+            self.set_window(0)
+
+    def set_window(self, env_lo):
+        """Point the obs buffer at envs [env_lo, env_lo + obs_window): later steps / render_obs()
+        write only those rows (every env still steps).  For batches whose full observation
+        tensor does not fit in HBM."""
+        env_lo = int(env_lo)
+        po, ko = _abi.dl(self.obs)
+        _abi.check(self._lib.lmz_set_window_dl(self._h, po, env_lo))
+        self.window_lo = env_lo
+        self._window_keepalive = ko
+
+    def render_window(self, env_lo):
+        """set_window(env_lo) + render the current state of that window into `obs`."""
+        self.set_window(env_lo)
+        return self.render_obs()
+
+    def expand(self, obs=None):
+        """Compact u8 [n,C,G,G] -> the reference's f32 [n,C,G*E,G*E] image (torch plumbing;
+        exact, because the reference upsample is a pure xE replication, lmaze_env.py:219-234)."""
+        obs = self.obs if obs is None else obs
+        if obs.dtype != torch.uint8:
+            return obs
+        e = self.expansion
+        return obs.to(torch.float32).repeat_interleave(e, dim=2).repeat_interleave(e, dim=3)
+
+    def initState(self):
+        """Reference initState() (lmaze_env.py:243-244): the un-expanded state layers, last reward,
+        done flag and {'newState': True} -- batched: f32 [N, C*G*G].  Needs obs_mode='compact'."""
+        if self.obs_mode != "compact" or self.obs_window != self.num_envs:
+            raise RuntimeError("initState() needs obs_mode='compact' over the whole batch")
+        state = self.render_obs().to(torch.float32).reshape(self.num_envs, -1)
+        return state, self.reward, self.done, {"newState": True}
 
     def _as_actions(self, actions):
         """Anything the reference's `int(msg)` (lmaze_env.py:148) accepts, batched."""
@@ -169,9 +219,9 @@ class LmazeVecCuda(object):
             raise ValueError("host buffers must have num_envs elements")
         if reward_host.dtype != torch.float32 or done_host.dtype not in (torch.uint8, torch.bool):
             raise ValueError("reward_host must be float32 and done_host uint8/bool")
-        if obs_host is not None and (obs_host.dtype != torch.float32 or not obs_host.is_contiguous()
+        if obs_host is not None and (obs_host.dtype != self.obs_dtype or not obs_host.is_contiguous()
                                      or obs_host.numel() != self.obs.numel()):
-            raise ValueError("obs_host must be a contiguous float32 tensor shaped like obs")
+            raise ValueError("obs_host must be a contiguous tensor with obs's dtype and size")
         ad = _ACTION_DTYPES.index(actions_host.dtype)
         _abi.check(self._lib.lmz_step_host(
             self._h, actions_host.data_ptr(), ad, reward_host.data_ptr(), done_host.data_ptr(),

@@ -57,6 +57,13 @@ typedef enum {
   LMZ_RENDER_ST128 = 1    /* 128-bit vector stores (st.global.v4) fed from the shared-memory template */
 } lmz_render_mode;
 
+/* What the observation tensor holds. */
+typedef enum {
+  LMZ_OBS_FULL = 0,       /* f32 [N,C,G*E,G*E]: the reference's upsampled image (lmaze_env.py:217-234), bit-exact */
+  LMZ_OBS_COMPACT = 1     /* u8  [N,C,G,G]: the same layers BEFORE the xE upsample (lmaze_env.py:208-215);
+                             the reference image is exactly repeat_interleave(compact, E) on both axes */
+} lmz_obs_mode;
+
 /* Element type of an action buffer. */
 typedef enum { LMZ_ACT_U8 = 0, LMZ_ACT_I32 = 1, LMZ_ACT_I64 = 2 } lmz_action_dtype;
 
@@ -79,7 +86,8 @@ typedef struct lmz_config {
                              [1] L2 policy of the obs stores: 1 evict_first, 2 evict_normal, 3 evict_last, 4 none
                              [2] reserved (0): tiles of 32 envs are handed to SMs dynamically
                              [3] split bulk copies into pieces of at most this many bytes (multiple of 16) */
-  int32_t  reserved[3];   /* must be zero */
+  int32_t  obs_mode;      /* lmz_obs_mode */
+  int32_t  reserved[2];   /* must be zero */
 } lmz_config;
 
 /* Episode statistics kept on the device as integer counters (lmz_stats). */
@@ -112,6 +120,8 @@ void        lmz_default_config(lmz_config *cfg);                    /* fills str
  * lmaze_env.py:20 / lmaze_env_v3.py:91 -- and grid side. */
 int         lmz_obs_shape(int32_t variant, int64_t shape[3]);
 int         lmz_grid_size(int32_t variant);
+/* Shape (C,H,W) and element size of one env's observation in the given obs_mode. */
+int         lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *elem_bytes);
 /* Copies the maze rows (G*G cell letters, row-major, no terminator) -- lmaze_env.py:37-48. */
 int         lmz_layout(int32_t variant, char *cells);
 
@@ -119,10 +129,18 @@ int         lmz_layout(int32_t variant, char *cells);
 int lmz_create(const lmz_config *cfg, lmz_env **out);
 int lmz_destroy(lmz_env *env);
 
-/* Bind the output buffers every later call writes: obs f32 [N,C,H,W] (may be NULL:
- * transition only, nothing rendered), reward f32 [N], done u8 [N].  16-byte aligned. */
-int lmz_bind(lmz_env *env, float *obs, float *reward, uint8_t *done);
+/* Bind the output buffers every later call writes: obs (f32 [N,C,H,W], or u8 [N,C,G,G] in
+ * compact mode; may be NULL: transition only, nothing rendered), reward f32 [N], done u8 [N].
+ * obs must be 16-byte aligned. */
+int lmz_bind(lmz_env *env, void *obs, float *reward, uint8_t *done);
 int lmz_bind_dl(lmz_env *env, DLManagedTensor *obs, DLManagedTensor *reward, DLManagedTensor *done);
+
+/* Render window: re-point obs at a buffer of env_count rows that stands for envs
+ * [env_lo, env_lo + env_count).  Steps still advance EVERY env but only render the window;
+ * lmz_render re-renders whatever window is current, so a batch whose full observation tensor
+ * does not fit in HBM (8M v3 envs = 498 GB) is consumed window by window. */
+int lmz_set_window(lmz_env *env, void *obs, int64_t env_lo, int64_t env_count);
+int lmz_set_window_dl(lmz_env *env, DLManagedTensor *obs, int64_t env_lo);
 
 /* reset(): replaces LmazeEnv.reset (lmaze_env.py:64-141) / LmazeEnv_v3.reset
  * (lmaze_env_v3.py:134-206) for every env whose mask byte is non-zero (mask NULL =
@@ -145,7 +163,7 @@ int lmz_step_dl(lmz_env *env, DLManagedTensor *actions, DLManagedTensor *spawn, 
  * fused step, copies reward/done (and obs when obs_host != NULL) D2H and waits
  * for the stream.  Host buffers should be pinned for the copies to be asynchronous. */
 int lmz_step_host(lmz_env *env, const void *actions_host, int32_t action_dtype,
-                  float *reward_host, uint8_t *done_host, float *obs_host, void *stream);
+                  float *reward_host, uint8_t *done_host, void *obs_host, void *stream);
 
 /* Render the current state into the bound obs without stepping (the
  * upsample loop of lmaze_env.py:208-234 on its own). */

@@ -425,3 +425,75 @@ def test_one_million_envs_properties(lmz, oracle_mod):
     s = env.stats()
     assert s["steps"] == 3 * N and s["wall_bumps"] + s["moves"] + s["stale"] == 3 * N
     env.close()
+
+
+# ---------------------------------------------------------------- compact observations and render windows
+@pytest.mark.parametrize("variant", ["v0", "v3"])
+def test_compact_obs_reconstructs_reference_image(lmz, oracle_mod, variant):
+    """obs_mode='compact' (u8 un-expanded layers): expand() must equal the oracle's full image, per step."""
+    N, T = 1000, 130
+    ov = oracle_mod.V0 if variant == "v0" else oracle_mod.V3
+    ora = oracle_mod.OracleVec(ov, N, seed=21, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, variant, seed=21, autoreset=True, obs_mode="compact")
+    assert env.obs.dtype == torch.uint8 and tuple(env.obs.shape[1:]) == ((4, 12, 12) if variant == "v0" else (3, 18, 18))
+    assert torch.equal(env.expand(env.reset()).cpu(), torch.from_numpy(ora.reset()))
+    gen = torch.Generator().manual_seed(8)
+    for t in range(T):
+        a = torch.randint(0, 5, (N,), generator=gen)
+        o_ref, r_ref, d_ref = ora.step(a.numpy())
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)) and np.array_equal(done.cpu().numpy().view(np.uint8), d_ref)
+        assert torch.equal(env.expand(obs).cpu(), torch.from_numpy(o_ref)), t
+    s = env.stats()
+    assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist()
+    if variant == "v0":
+        # reference initState(): raw un-expanded state layers (lmaze_env.py:243-244)
+        state, rew, done, info = env.initState()
+        assert info == {"newState": True} and state.shape == (N, 576)
+        full = torch.from_numpy(np.stack([ora.render_one(i) for i in range(N)]))
+        assert torch.equal(state.view(N, 4, 12, 12).cpu(), full[:, :, ::7, ::7])
+    env.close()
+
+
+@pytest.mark.parametrize("render_mode,obs_mode", [("tma", "full"), ("st128", "full"), ("tma", "compact")])
+def test_render_window(lmz, oracle_mod, render_mode, obs_mode):
+    """A window of W rows stands for envs [lo, lo+W): every env steps, only the window is rendered."""
+    N, W = 1000, 300
+    ora = oracle_mod.OracleVec(oracle_mod.V3, N, seed=5, autoreset=True)
+    env = lmz.LmazeVecCuda(N, "v3", seed=5, autoreset=True, render_mode=render_mode, obs_mode=obs_mode, obs_window=W)
+    assert env.obs.shape[0] == W
+    ora.reset(want_obs=False); env.reset()
+    gen = torch.Generator().manual_seed(2)
+    for t in range(6):
+        a = torch.randint(0, 4, (N,), generator=gen)
+        o_ref, r_ref, d_ref = ora.step(a.numpy())
+        lo = (t * 173) % (N - W + 1)
+        env.set_window(lo)
+        env.obs.fill_(7)                                   # sentinel: rows must be fully rewritten
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32))          # all N envs stepped
+        assert torch.equal(env.expand(obs).cpu(), torch.from_numpy(o_ref[lo:lo + W])), t
+        # walk the rest of the batch window by window without stepping
+        for lo2 in (0, N - W, 350):
+            assert torch.equal(env.expand(env.render_window(lo2)).cpu(), torch.from_numpy(o_ref[lo2:lo2 + W]))
+    from gym_lmaze_b200._abi import LmzError
+    with pytest.raises(LmzError, match="window"):
+        env.set_window(N - W + 1)
+    env.close()
+
+
+def test_transition_only_mode(lmz, oracle_mod):
+    """with_obs=False: nothing is rendered, transitions/stat counters are unchanged."""
+    N = 2000
+    ora = oracle_mod.OracleVec(oracle_mod.V0, N, seed=9)
+    env = lmz.LmazeVecCuda(N, "v0", seed=9, with_obs=False)
+    ora.reset(want_obs=False); assert env.reset() is None
+    gen = torch.Generator().manual_seed(4)
+    for t in range(120):
+        a = torch.randint(0, 4, (N,), generator=gen)
+        _, r_ref, d_ref = ora.step(a.numpy(), want_obs=False)
+        obs, rew, done, _ = env.step(a)
+        assert obs is None and np.array_equal(rbits(rew), r_ref.view(np.uint32)) and \
+            np.array_equal(done.cpu().numpy().view(np.uint8), d_ref)
+    assert [env.stats()[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist()
+    env.close()
