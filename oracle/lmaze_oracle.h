@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 #define LMZO_V0 0
+#define LMZO_V2 2
 #define LMZO_V3 3
 #define LMZO_MAX_G 18
 
@@ -47,6 +48,14 @@ typedef struct lmzo_env {
   double reward;          /* Python float in the reference */
   int64_t step_count;     /* stepCount */
   int64_t goal_count;     /* goalCount, v0 only; survives reset (lmaze_env.py:24,195) */
+  /* ---- v2 (lmaze_env_v2.py): multi-layout foveal env ---- */
+  int layout;             /* 1..5: which maze setGrid() picked (lmaze_env_v2.py:303-405) */
+  int fovea;              /* 5 (lmaze_env_v2.py:27) */
+  float last_crop[2 * 25];/* retStatelast: the previous 2x5x5 observation (lmaze_env_v2.py:41,104,212-213) */
+  float shown_prev[2 * 25];/* the retStatelast that went into the CURRENT obs (before :212-213 replaced it) */
+  float action_plane[25]; /* action_value one-hot (lmaze_env_v2.py:87,136-137) */
+  int prev_x, prev_y;     /* where shown_prev was taken (bookkeeping for tests) */
+  int64_t bad_actions;    /* batched API: actions outside 0..24 are clamped and counted */
 } lmzo_env;
 
 /* Episode statistics, integers only (order-independent sums). */
@@ -80,6 +89,13 @@ int  lmzo_reset(lmzo_env *e, int sx, int sy, int gx, int gy);
  * `cls_out` (may be NULL) receives the branch taken: 0 W, 1 B/else, 2 X/goal, 3 none(S). */
 int  lmzo_step(lmzo_env *e, int64_t action, int *cls_out);
 
+/* v2 reset: goal (gx,gy) and ball (sx,sy) as drawn on the CURRENT maze, then the maze is
+ * re-rolled to `new_layout` (1..5) -- the order of lmaze_env_v2.py:90-92.  -1 if the reference's
+ * rejection loops (:277-299) would not have accepted the cells. */
+int  lmzo_reset_v2(lmzo_env *e, int sx, int sy, int gx, int gy, int new_layout);
+/* The five 18x18 mazes of lmaze_env_v2.py:303-405 (layout 1..5). */
+int  lmzo_layout_v2(int layout, char *cells);
+
 /* isEpisodeFinished() / the done expression (lmaze_env.py:246-249, lmaze_env_v3.py:398). */
 int  lmzo_done(const lmzo_env *e);
 
@@ -94,6 +110,8 @@ void lmzo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 /* Spawn for (seed, global env id, episode index).  v0: ball only.  v3: goal + ball. */
 void lmzo_rng_spawn(int variant, uint64_t seed, uint64_t env_id, uint32_t episode,
                     int *sx, int *sy, int *gx, int *gy);
+void lmzo_rng_spawn_v2(uint64_t seed, uint64_t env_id, uint32_t episode, int cur_layout,
+                       int *sx, int *sy, int *gx, int *gy, int *first_layout, int *new_layout);
 /* Rollout action for (seed, global env id, global rollout step t). */
 int  lmzo_rng_action(uint64_t seed, uint64_t env_id, uint64_t t);
 
@@ -101,7 +119,7 @@ int  lmzo_rng_action(uint64_t seed, uint64_t env_id, uint64_t t);
  * the single-env restatement above.  For each env i: step; record f32 reward and
  * done; if done and autoreset, reset (spawn from `spawn` if non-NULL, else the
  * Philox spec, bumping episode[i]); render into obs (if non-NULL).
- * spawn layout: int32 [N][4] = sx, sy, gx, gy.
+ * spawn layout: int32 [N][4] = sx, sy, gx, gy (v2: column 3 = gy | new_layout << 5).
  * actions: int64 [N].  stats: int64[LMZO_NUM_STATS], accumulated.  threads<=1 => serial; else a pthread pool over contiguous env ranges. */
 void lmzo_vec_step(lmzo_env *envs, int64_t n, const int64_t *actions, const int32_t *spawn,
                    uint64_t seed, uint64_t env_id0, uint32_t *episode, int autoreset,
@@ -115,6 +133,10 @@ lmzo_env *lmzo_env_at(lmzo_env *envs, int64_t i);
 /* pos: int32 [N][4] = x, y, goal_x, goal_y */
 void lmzo_vec_export(const lmzo_env *envs, int64_t n, int32_t *pos, int64_t *step_count,
                      int64_t *goal_count, double *reward);
+/* aux: int32 [N][4] = layout, prev_x, prev_y, bad_actions (v2) */
+void lmzo_vec_export_aux(const lmzo_env *envs, int64_t n, int32_t *aux);
+/* v2: force maze, ball, goal, previous-crop position and stepCount */
+int  lmzo_env_force_v2(lmzo_env *e, int layout, int sx, int sy, int gx, int gy, int px, int py, int64_t step_count);
 /* Put one env into an arbitrary reachable mid-episode state (incl. ball on the goal cell). */
 int  lmzo_env_force(lmzo_env *e, int variant, int sx, int sy, int gx, int gy,
                     int64_t step_count, double reward, int64_t goal_count);

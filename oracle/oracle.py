@@ -12,10 +12,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblmaze_oracle.so")
 
-V0, V3 = 0, 3
+V0, V2, V3 = 0, 2, 3
 NUM_STATS = 8
 STAT_NAMES = ("steps", "episodes", "goals", "timeouts", "wall_bumps", "moves", "stale", "eplen_sum")
-OBS_SHAPE = {V0: (4, 84, 84), V3: (3, 72, 72)}
+OBS_SHAPE = {V0: (4, 84, 84), V2: (5, 35, 35), V3: (3, 72, 72)}
 # f32 bit patterns of the only rewards the reference can emit
 REWARD_BITS = {"neg_zero": 0x80000000, "wall": 0xBF800000, "move": 0xBC23D70A, "goal": 0x42C80000}
 
@@ -74,6 +74,14 @@ def lib():
     L.lmzo_vec_export.restype = None
     L.lmzo_env_force.argtypes = [vp, ctypes.c_int] + [ctypes.c_int] * 4 + [i64, dbl, i64]
     L.lmzo_env_force.restype = ctypes.c_int
+    L.lmzo_env_force_v2.argtypes = [vp] + [ctypes.c_int] * 7 + [i64]
+    L.lmzo_env_force_v2.restype = ctypes.c_int
+    L.lmzo_vec_export_aux.argtypes = [vp, i64, vp]
+    L.lmzo_vec_export_aux.restype = None
+    L.lmzo_layout_v2.argtypes = [ctypes.c_int, ctypes.c_char_p]
+    L.lmzo_layout_v2.restype = ctypes.c_int
+    L.lmzo_rng_spawn_v2.argtypes = [u64, u64, u32, ctypes.c_int] + [ip] * 6
+    L.lmzo_rng_spawn_v2.restype = None
     _lib = L
     return L
 
@@ -90,6 +98,15 @@ def layout(variant):
     L.lmzo_layout(variant, buf)
     cells = buf.raw.decode("ascii")
     return [cells[i * G:(i + 1) * G] for i in range(G)]
+
+
+def layout_v2(k):
+    """Rows of v2 maze k (1..5)."""
+    buf = ctypes.create_string_buffer(18 * 18)
+    if lib().lmzo_layout_v2(k, buf) < 0:
+        raise ValueError(k)
+    cells = buf.raw.decode("ascii")
+    return [cells[i * 18:(i + 1) * 18] for i in range(18)]
 
 
 def philox(ctr, key):
@@ -174,6 +191,17 @@ class OracleVec(object):
         rc = self.L.lmzo_env_force(self._env(i), self.variant, sx, sy, gx, gy, step_count, reward, goal_count)
         if rc != 0:
             raise ValueError("oracle rejected forced state %r" % ((i, sx, sy, gx, gy),))
+
+    def force_v2(self, i, layout, sx, sy, gx, gy, px, py, step_count=0):
+        rc = self.L.lmzo_env_force_v2(self._env(i), layout, sx, sy, gx, gy, px, py, step_count)
+        if rc != 0:
+            raise ValueError("oracle rejected forced v2 state")
+
+    def export_aux(self):
+        """int32 [N,4]: layout, prev_x, prev_y, bad_actions (v2)."""
+        aux = np.empty((self.n, 4), dtype=np.int32)
+        self.L.lmzo_vec_export_aux(_ptr(self._mem), self.n, _ptr(aux))
+        return aux
 
     # single-env access for table tests
     def step_one(self, i, action):

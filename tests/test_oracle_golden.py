@@ -208,3 +208,61 @@ def test_live_reference_random_walk(oracle_mod):
         o_ref, r_ref, d_ref = o.step([a])
         assert np.array_equal(obs, o_ref[0]) and np.float32(r).view(np.uint32) == r_ref.view(np.uint32)[0]
         assert bool(d) == bool(d_ref[0]) and info == a
+
+
+# ---------------------------------------------------------------- v2 (multi-layout foveal env)
+def test_v2_layouts(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v2_layouts.npz"))
+    md5s = []
+    for k in range(5):
+        rows = oracle_mod.layout_v2(k + 1)
+        assert rows == [str(r) for r in z["layouts"][k]]
+        md5s.append(hashlib.md5("/".join(rows).encode()).hexdigest()[:8])
+    assert md5s == ["670a2974", "c7ab0302", "0f7e0ab0", "d82dd8d9", "19d9c0c4"]
+
+
+def test_v2_transition_table(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v2_table.npz"))
+    o = oracle_mod.OracleVec(oracle_mod.V2, 1, autoreset=False)
+    for row, bits in zip(z["table"], z["obs"]):
+        L, bx, by, gx, gy, px, py, a, sb, nx, ny, rb, d, sa = (int(v) for v in row)
+        o.force_v2(0, L, bx, by, gx, gy, px, py, step_count=sb)
+        dd, _ = o.step_one(0, a)
+        pos, sc, _, rw = o.export()
+        assert tuple(pos[0]) == (nx, ny, gx, gy) and rw.view(np.int64)[0] == rb and dd == d and sc[0] == sa
+        assert np.array_equal(o.render_one(0), unpack(bits, (5, 35, 35)))
+    rw = np.int64(z["table"][:, 11]).view(np.float64)
+    assert set(rw.tolist()) == {-1.0, -0.01, 100.0, 0.0}
+    assert np.signbit(rw[rw == 0.0]).all() and (rw == 0.0).sum() >= 20      # X-but-not-goal cells return -0.0
+
+
+def test_v2_traces(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v2_traces.npz"))
+    ne = int(z["n_envs"])
+    o = oracle_mod.OracleVec(oracle_mod.V2, ne, autoreset=True)
+    init = np.stack([z["e%d_init" % e] for e in range(ne)])        # bx, by, gx, gy, layout, layout-before
+    for e in range(ne):                                            # the maze the constructor rolled
+        oracle_mod.lib().lmzo_layout_v2(int(init[e, 5]), ctypes_grid(o, e))
+    sp = np.stack([init[:, 0], init[:, 1], init[:, 2], init[:, 3] | (init[:, 4] << 5)], axis=1)
+    obs = o.reset(spawn=sp)
+    for e in range(ne):
+        assert np.array_equal(obs[e], unpack(z["e%d_first_obs" % e], (5, 35, 35)))
+    T = len(z["e0_actions"])
+    for t in range(T):
+        acts = np.array([z["e%d_actions" % e][t] for e in range(ne)])
+        s5 = np.stack([z["e%d_spawn" % e][t] for e in range(ne)])
+        dref = np.array([z["e%d_done" % e][t] for e in range(ne)])
+        spawn = np.stack([s5[:, 0], s5[:, 1], s5[:, 2], s5[:, 3] | (s5[:, 4] << 5)], axis=1)
+        spawn = np.where(dref[:, None] > 0, spawn, 0)
+        obs, rew, done = o.step(acts, spawn=spawn)
+        for e in range(ne):
+            assert rew[e].view(np.uint32) == np.float32(f64(z["e%d_reward_bits" % e][t])).view(np.uint32), (t, e)
+            assert done[e] == dref[e], (t, e)
+            assert np.array_equal(obs[e], unpack(z["e%d_obs" % e][t], (5, 35, 35))), (t, e)
+    assert o.stats[1] == sum(int(z["e%d_done" % e].sum()) for e in range(ne)) >= 16
+
+
+def ctypes_grid(o, i):
+    """char* to env i's grid (offset of lmzo_env.grid = 7 ints)."""
+    import ctypes
+    return ctypes.cast(o._env(i) + 7 * 4, ctypes.c_char_p)
