@@ -30,8 +30,10 @@ def registered_ids():
 
 
 register("lmaze-v0", "v0", num_envs=1)
+register("lmaze-v2", "v2", num_envs=1)
 register("lmaze-v3", "v3", num_envs=1)
 register("lmaze-vec-v0", "v0", num_envs=4096)
+register("lmaze-vec-v2", "v2", num_envs=4096)
 register("lmaze-vec-v3", "v3", num_envs=4096)
 
 

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblmaze_b200.so")
 
-LMZ_V0, LMZ_V3 = 0, 3
+LMZ_V0, LMZ_V2, LMZ_V3 = 0, 2, 3
 RENDER_TMA, RENDER_ST128 = 0, 1
 OBS_FULL, OBS_COMPACT = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
@@ -21,7 +21,7 @@ STATE_COLS = ("x", "y", "goal_x", "goal_y", "step_count", "reward_code", "goal_c
 # every symbol include/lmaze_b200.h declares (tests/test_abi_symbols.py checks the header against this)
 EXPORTS = (
     "lmz_abi_version", "lmz_last_error", "lmz_default_config", "lmz_obs_shape", "lmz_grid_size", "lmz_obs_desc",
-    "lmz_layout", "lmz_set_window", "lmz_set_window_dl",
+    "lmz_layout", "lmz_num_layouts", "lmz_layout_ex", "lmz_num_actions", "lmz_set_window", "lmz_set_window_dl",
     "lmz_create", "lmz_destroy", "lmz_bind", "lmz_bind_dl", "lmz_reset", "lmz_reset_dl", "lmz_step",
     "lmz_step_dl", "lmz_step_host", "lmz_render", "lmz_rollout", "lmz_rollout_dl", "lmz_get_state",
     "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
@@ -76,6 +76,9 @@ def load():
     L.lmz_set_window.argtypes = [vp, vp, i64, i64]
     L.lmz_set_window_dl.argtypes = [vp, vp, i64]
     L.lmz_layout.argtypes = [i32, ctypes.c_char_p]
+    L.lmz_num_layouts.argtypes = [i32]
+    L.lmz_layout_ex.argtypes = [i32, i32, ctypes.c_char_p]
+    L.lmz_num_actions.argtypes = [i32]
     L.lmz_create.argtypes = [ctypes.POINTER(LmzConfig), ctypes.POINTER(vp)]
     L.lmz_destroy.argtypes = [vp]
     L.lmz_bind.argtypes = [vp, vp, vp, vp]

@@ -15,6 +15,7 @@
 
 #include "../../include/lmaze_b200.h"
 #include "lmz_kernels.cuh"
+#include "lmz_v2.cuh"
 
 namespace {
 
@@ -49,6 +50,21 @@ const char V3_CELLS[] =
     "WWWWBBBBXBBWWWWWWW" "WWWWBWBBBBBWBBWWWW" "WWWWBWBBBBBWBBWWWW" "WWWWBWBBBBBWBBWWWW"
     "WWWWBWWWWWBWBBWWWW" "WWWWBBBBWBBBBBWWWW" "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW"
     "WWWWWWWWWWWWWWWWWW" "WWWWWWWWWWWWWWWWWW";
+
+// v2: lmaze_env_v2.py:303-405.  Five 18x18 mazes whose rows/cols 0-3 and 14-17 are all wall; only the
+// 10x10 active region (rows 4..13, cols 4..13) is listed, row-major.
+const char *const V2_ACTIVE[5] = {
+    "SBBBWBBBBB" "BWWWWBWWBB" "BWBWBBBWBB" "BWBWBWBWBB" "BBBWXWBWWW" "BWBWBWBWBB" "BWBWBWBWBB" "BWBBBWBWBB" "BWWWWWBWBB" "BBBBWBBBBB",
+    "SBBBBBBBBB" "BWWWBWWWWB" "BWBBBBBWWB" "BWBWBWBWWB" "BWBWXWBWWB" "BWBWWWBWWB" "BWBWWWBBBB" "BWBBBBBWWB" "BWWWBWWWWB" "BBBBBBBBBB",
+    "SBBBBBBBBB" "BWBWWWWWBB" "BWBBBWBBBB" "BWBBBWBWBB" "BWBWXWBWBB" "BWBWBBBWBB" "BWBWBWBWBB" "BBBWBBBBBB" "BWWWWWWWBB" "BBBBBBBBBB",
+    "SBBBBBBBBB" "BBWWWBWWBB" "BBBWBBBWBB" "BWBWBWBWBB" "BWBWXWBWBB" "BWBWBWBWBB" "BWBWBWBBBB" "BWBBBWBWBB" "BWBWWWWWBB" "BBBBBBBBBB",
+    "SBBBBBBBBB" "BWWWWBWWBB" "BBWBBBBWBB" "BBBBWWBWBB" "BWWXWWWWBB" "BWWBWWBWBB" "BWWBWWBWBB" "BWBBBBBWBB" "BWBWWBWWBB" "BBBBBBBBBB",
+};
+
+void v2_cells(int layout, char *cells) {     // layout 1..5 -> 324 letters
+  memset(cells, 'W', 18 * 18);
+  for (int x = 0; x < 10; ++x) memcpy(cells + (x + 4) * 18 + 4, V2_ACTIVE[layout - 1] + 10 * x, 10);
+}
 
 const char *cells_of(int variant) {
   if (variant == LMZ_V0) return V0_CELLS;
@@ -106,6 +122,38 @@ void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand
     // spawn candidates: v0 not in {W,X} (lmaze_env.py:73); v3 not W (lmaze_env_v3.py:148,157)
     const bool ok = (V::ID == 0) ? (c != 'W' && c != 'X') : (c != 'W');
     if (ok && n_cand < V::MAX_CAND) cand[n_cand++] = (uint16_t)i;
+  }
+}
+
+void build_blob_v2(std::vector<unsigned char> &blob) {
+  using V = lmz::V2;
+  blob.assign(V::BLOB_BYTES, 0);
+  // (channel, cell) of every float of an env's (5,35,35) image: the x7 upsample of lmaze_env_v2.py:197-203
+  for (int c = 0; c < V::C; ++c)
+    for (int row = 0; row < V::S; ++row)
+      for (int col = 0; col < V::S; ++col)
+        blob[V::LUT_OFF + (c * V::S + row) * V::S + col] = (unsigned char)((c << 5) | ((row / V::E) * V::F + col / V::E));
+  uint32_t *rowbits = reinterpret_cast<uint32_t *>(blob.data() + V::ROWBITS_OFF);
+  uint16_t *gcand = reinterpret_cast<uint16_t *>(blob.data() + V::GCAND_OFF);
+  uint16_t *bcand = reinterpret_cast<uint16_t *>(blob.data() + V::BCAND_OFF);
+  signed char *brank = reinterpret_cast<signed char *>(blob.data() + V::BRANK_OFF);
+  for (int L = 0; L < V::NLAYOUT; ++L) {
+    char cells[18 * 18];
+    v2_cells(L + 1, cells);
+    int ng = 0, nb = 0;
+    for (int i = 0; i < V::G * V::G; ++i) {
+      const char c = cells[i];
+      blob[V::CLS_OFF + L * V::G * V::G + i] = (unsigned char)cls_of(c);
+      if (c != 'W') rowbits[L * V::G + i / V::G] |= 1u << (i % V::G);                 // state[0], :94
+      brank[L * V::G * V::G + i] = -1;
+      if (c != 'W' && c != 'S' && ng < V::MAX_CAND) gcand[L * V::MAX_CAND + ng++] = (uint16_t)i;   // setGoal, :280
+      if (c != 'W' && c != 'X' && nb < V::MAX_CAND) {                                 // setBall, :293
+        brank[L * V::G * V::G + i] = (signed char)nb;
+        bcand[L * V::MAX_CAND + nb++] = (uint16_t)i;
+      }
+    }
+    blob[V::COUNT_OFF + L] = (unsigned char)ng;
+    blob[V::COUNT_OFF + 5 + L] = (unsigned char)nb;
   }
 }
 
@@ -220,7 +268,28 @@ int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   }
 }
 
+int launch_v2(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  constexpr int THREADS = 512;
+  auto kern = lmz::lmz_env_v2_kernel<THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, lmz::V2::BLOB_BYTES));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "v2 kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  const int64_t units = p.tile_end - p.tile_begin;
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  if (grid > units) grid = units;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, lmz::V2::BLOB_BYTES, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.variant == LMZ_V2) return launch_v2(h, p, s);
   if (h->cfg.variant == LMZ_V0) return launch_env_v<lmz::V0>(h, p, s);
   return launch_env_v<lmz::V3>(h, p, s);
 }
@@ -330,7 +399,29 @@ int lmz_obs_shape(int32_t variant, int64_t shape[3]) {
   if (!shape) return fail(LMZ_ERR_INVALID, "shape is NULL");
   if (variant == LMZ_V0) { shape[0] = lmz::V0::C; shape[1] = shape[2] = lmz::V0::S; return LMZ_OK; }
   if (variant == LMZ_V3) { shape[0] = lmz::V3::C; shape[1] = shape[2] = lmz::V3::S; return LMZ_OK; }
+  if (variant == LMZ_V2) { shape[0] = lmz::V2::C; shape[1] = shape[2] = lmz::V2::S; return LMZ_OK; }
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+}
+
+int lmz_num_actions(int32_t variant) {
+  if (variant == LMZ_V0 || variant == LMZ_V3) return 4;      // lmaze_env.py:16, lmaze_env_v3.py:92
+  if (variant == LMZ_V2) return 25;                          // lmaze_env_v2.py:39
+  return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+}
+
+int lmz_num_layouts(int32_t variant) {
+  if (variant == LMZ_V0 || variant == LMZ_V3) return 1;
+  if (variant == LMZ_V2) return 5;                           // lmaze_env_v2.py:306
+  return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+}
+
+int lmz_layout_ex(int32_t variant, int32_t index, char *cells) {
+  if (!cells) return fail(LMZ_ERR_INVALID, "cells is NULL");
+  const int nl = lmz_num_layouts(variant);
+  if (nl < 0) return nl;
+  if (index < 1 || index > nl) return fail(LMZ_ERR_INVALID, "layout index %d outside 1..%d", index, nl);
+  if (variant == LMZ_V2) { v2_cells(index, cells); return LMZ_OK; }
+  return lmz_layout(variant, cells);
 }
 
 int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *elem_bytes) {
@@ -349,11 +440,12 @@ int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *e
 
 int lmz_grid_size(int32_t variant) {
   if (variant == LMZ_V0) return lmz::V0::G;
-  if (variant == LMZ_V3) return lmz::V3::G;
+  if (variant == LMZ_V3 || variant == LMZ_V2) return lmz::V3::G;
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_layout(int32_t variant, char *cells) {
+  if (variant == LMZ_V2) return lmz_layout_ex(variant, 1, cells);
   const char *c = cells_of(variant);
   if (!c) return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
   if (!cells) return fail(LMZ_ERR_INVALID, "cells is NULL");
@@ -368,8 +460,11 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (cfg->struct_size != (int32_t)sizeof(lmz_config))
     return fail(LMZ_ERR_INVALID, "lmz_config.struct_size %d != %d: header/library mismatch", cfg->struct_size,
                 (int)sizeof(lmz_config));
-  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3)
-    return fail(LMZ_ERR_UNSUPPORTED, "variant %d is not built (supported: 0 = lmaze-v0, 3 = lmaze-v3)", cfg->variant);
+  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3 && cfg->variant != LMZ_V2)
+    return fail(LMZ_ERR_UNSUPPORTED, "variant %d is not built (supported: 0 = lmaze-v0, 2 = lmaze-v2, 3 = lmaze-v3)",
+                cfg->variant);
+  if (cfg->variant == LMZ_V2 && cfg->obs_mode != LMZ_OBS_FULL)
+    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2 has no compact observation mode yet");
   if (cfg->num_envs < 1) return fail(LMZ_ERR_INVALID, "num_envs must be >= 1 (got %lld)", (long long)cfg->num_envs);
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
   if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128)
@@ -410,6 +505,11 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     h->G = lmz::V0::G; h->C = lmz::V0::C; h->S = lmz::V0::S; h->obs_bytes_per_env = lmz::V0::OBS_BYTES;
     h->compact_bytes_per_env = lmz::V0::COMPACT_BYTES;
     build_blob<lmz::V0>(V0_CELLS, blob, h->n_cand, h->s_cell, h->x_cell);
+  } else if (cfg->variant == LMZ_V2) {
+    h->G = lmz::V2::G; h->C = lmz::V2::C; h->S = lmz::V2::S; h->obs_bytes_per_env = lmz::V2::OBS_BYTES;
+    h->compact_bytes_per_env = 0;
+    build_blob_v2(blob);
+    h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
   } else {
     h->G = lmz::V3::G; h->C = lmz::V3::C; h->S = lmz::V3::S; h->obs_bytes_per_env = lmz::V3::OBS_BYTES;
     h->compact_bytes_per_env = lmz::V3::COMPACT_BYTES;
@@ -432,7 +532,18 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     lmz::EnvRegs r;
     r.x = h->s_cell / h->G; r.y = h->s_cell % h->G; r.gx = h->x_cell / h->G; r.gy = h->x_cell % h->G;
     r.step = 0; r.rcode = lmz::RC_NEG_ZERO;
-    const uint32_t packed = (cfg->variant == LMZ_V0) ? lmz::V0::pack(r) : lmz::V3::pack(r);
+    uint32_t packed = (cfg->variant == LMZ_V0) ? lmz::V0::pack(r) : lmz::V3::pack(r);
+    if (cfg->variant == LMZ_V2) {          // maze 1, ball on 'S', goal on 'X', no previous action
+      lmz::V2Regs v;
+      v.L = 1; v.x = v.px = 4; v.y = v.py = 4; v.gx = 8; v.gy = 8; v.a = -1; v.step = 0;
+      uint32_t aux;
+      lmz::v2_pack(v, packed, aux);
+      std::vector<uint32_t> auxv(n < (1u << 20) ? n : (1u << 20), aux);
+      for (size_t off = 0; off < n && e == cudaSuccess; off += auxv.size()) {
+        const size_t cnt = (n - off < auxv.size()) ? n - off : auxv.size();
+        e = cudaMemcpy(h->goal_count + off, auxv.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice);
+      }
+    }
     std::vector<uint32_t> init(n < (1u << 20) ? n : (1u << 20), packed);
     for (size_t off = 0; off < n && e == cudaSuccess; off += init.size()) {
       const size_t cnt = (n - off < init.size()) ? n - off : init.size();
@@ -605,6 +716,7 @@ int lmz_rollout(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype
                 void *stream) {
   if (int rc = check_handle(h)) return rc;
   if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
+  if (h->cfg.variant == LMZ_V2) return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2 yet");
   if (!rewards || !dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
   if (actions && (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64))
     return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
@@ -642,7 +754,9 @@ static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {
   const int64_t n = h->cfg.num_envs;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (h->cfg.variant == LMZ_V0)
+  if (h->cfg.variant == LMZ_V2)
+    lmz::lmz_state_v2_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
+  else if (h->cfg.variant == LMZ_V0)
     lmz::lmz_state_kernel<lmz::V0><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
   else
     lmz::lmz_state_kernel<lmz::V3><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);

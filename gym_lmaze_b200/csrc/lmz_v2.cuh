@@ -1,0 +1,287 @@
+// lmz_v2.cuh -- lmaze-v2: multi-layout foveal env (reference gym_lmaze/envs/lmaze_env_v2.py).
+//
+// Differences from v0/v3 that shape the kernel:
+//   * five 18x18 mazes, one re-rolled per episode (lmaze_env_v2.py:92,303-405): the per-layout
+//     tables (row bitmasks, cell classes, goal / ball candidate lists) are staged into shared
+//     memory with the same single bulk async (TMA) load as the other variants' blob;
+//   * Discrete(25) "teleport the fovea" actions (:39,151-169), reward by the cell the fovea was
+//     pointed at (:175-180), done at reward 100 or stepCount > 50 (:222);
+//   * the observation is five 5x5 BIT planes -- free-cell crop and goal crop around the ball, the
+//     action one-hot, and the previous step's two crops (:185-193) -- each upsampled x7 to 35x35
+//     floats: 6,125 floats = 24,500 B per env.  24,500 is not a multiple of 16, so neither bulk
+//     copies nor per-env vector stores are possible; instead a TILE of 32 envs (784,000 B, which
+//     IS 16-byte aligned) is written as one flat run of float4 stores, every float looked up as
+//     bit `cell` of mask `c` of env `e` through a 6,125-entry (c,cell) table in shared memory.
+#pragma once
+#include "lmz_kernels.cuh"
+
+namespace lmz {
+
+struct V2 {
+  static constexpr int ID = 2;
+  static constexpr int G = 18, E = 7, F = 5, C = 5, S = F * E;        // lmaze_env_v2.py:26-37
+  static constexpr int NLAYOUT = 5, MAX_CAND = 80;
+  static constexpr uint32_t OBS_FLOATS = C * S * S;                    // 6,125
+  static constexpr uint32_t OBS_BYTES = OBS_FLOATS * 4;                // 24,500
+  static constexpr uint32_t TILE_F4 = 32 * OBS_FLOATS / 4;             // 49,000 float4 per 32-env tile
+  static constexpr int STEP_LIMIT = 50;                                // lmaze_env_v2.py:43
+  static constexpr uint32_t STEP_SAT = 63;
+  // blob layout (bytes)
+  static constexpr uint32_t LUT_OFF = 0;                               // u8 [6125]: (c << 5) | cell
+  static constexpr uint32_t ROWBITS_OFF = align16(OBS_FLOATS);         // u32 [5][18]: bit y = cell (x,y) is B/S/X
+  static constexpr uint32_t CLS_OFF = ROWBITS_OFF + align16(NLAYOUT * G * 4);     // u8 [5][324]
+  static constexpr uint32_t GCAND_OFF = CLS_OFF + align16(NLAYOUT * G * G);       // u16 [5][80] cells not in {W,S}
+  static constexpr uint32_t BCAND_OFF = GCAND_OFF + NLAYOUT * MAX_CAND * 2;       // u16 [5][80] cells not in {W,X}
+  static constexpr uint32_t BRANK_OFF = BCAND_OFF + NLAYOUT * MAX_CAND * 2;       // i8 [5][324] index in BCAND or -1
+  static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5], scell... (16 B)
+  static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
+};
+
+struct V2Regs {
+  int L, x, y, gx, gy, px, py, a;     // a: last action, -1 right after a reset (action plane all zero)
+  uint32_t step;
+};
+
+// state word: L:3 | x:5 | y:5 | gx:5 | gy:5 | step:6 ; aux word: px:5 | py:5 | a:5 | a_valid:1
+__host__ __device__ inline V2Regs v2_unpack(uint32_t s, uint32_t aux) {
+  V2Regs r;
+  r.L = s & 7; r.x = (s >> 3) & 31; r.y = (s >> 8) & 31; r.gx = (s >> 13) & 31; r.gy = (s >> 18) & 31;
+  r.step = (s >> 23) & 63;
+  r.px = aux & 31; r.py = (aux >> 5) & 31; r.a = ((aux >> 15) & 1) ? (int)((aux >> 10) & 31) : -1;
+  return r;
+}
+__host__ __device__ inline void v2_pack(const V2Regs &r, uint32_t &s, uint32_t &aux) {
+  s = (uint32_t)r.L | ((uint32_t)r.x << 3) | ((uint32_t)r.y << 8) | ((uint32_t)r.gx << 13) | ((uint32_t)r.gy << 18) |
+      (r.step << 23);
+  aux = (uint32_t)r.px | ((uint32_t)r.py << 5) | (r.a >= 0 ? (((uint32_t)r.a << 10) | (1u << 15)) : 0u);
+}
+
+struct V2Tables {
+  const uint8_t *lut;
+  const uint32_t *rowbits;
+  const uint8_t *cls;
+  const uint16_t *gcand, *bcand;
+  const int8_t *brank;
+  const uint8_t *count;      // ng[0..4], nb[5..9]
+  __device__ __forceinline__ explicit V2Tables(const unsigned char *smem)
+      : lut(smem + V2::LUT_OFF), rowbits(reinterpret_cast<const uint32_t *>(smem + V2::ROWBITS_OFF)),
+        cls(smem + V2::CLS_OFF), gcand(reinterpret_cast<const uint16_t *>(smem + V2::GCAND_OFF)),
+        bcand(reinterpret_cast<const uint16_t *>(smem + V2::BCAND_OFF)),
+        brank(reinterpret_cast<const int8_t *>(smem + V2::BRANK_OFF)), count(smem + V2::COUNT_OFF) {}
+};
+
+// 5x5 crop of the free-cell layer around (x,y) as 25 bits, bit i*5+j = cell (x-2+i, y-2+j)
+__device__ __forceinline__ uint32_t v2_free_crop(const V2Tables &t, int L, int x, int y) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) m |= ((t.rowbits[(L - 1) * V2::G + x - 2 + i] >> (y - 2)) & 31u) << (5 * i);
+  return m;
+}
+__device__ __forceinline__ uint32_t v2_goal_crop(int x, int y, int gx, int gy) {
+  const int dx = gx - (x - 2), dy = gy - (y - 2);
+  return (dx >= 0 && dx < 5 && dy >= 0 && dy < 5) ? (1u << (dx * 5 + dy)) : 0u;
+}
+
+// reset(): goal and ball drawn on the maze of the episode that just ended, then the maze is
+// re-rolled (lmaze_env_v2.py:90-92,277-299).  Injected spawn: sx, sy, gx, gy | new_layout << 5.
+__device__ __forceinline__ void v2_respawn(V2Regs &r, const KParams &p, int64_t e, uint32_t &episode,
+                                           const V2Tables &t) {
+  int sx, sy, gx, gy, nl;
+  if (p.spawn) {
+    const int4 s = p.spawn[e];
+    sx = s.x; sy = s.y; gx = s.z; gy = s.w & 31; nl = s.w >> 5;
+    bool ok = nl >= 1 && nl <= 5;
+    const uint8_t *cls = t.cls + (r.L - 1) * V2::G * V2::G;
+    if (ok) ok = gx >= 1 && gx <= V2::G - 2 && gy >= 1 && gy <= V2::G - 2 && sx >= 1 && sx <= V2::G - 2 && sy >= 1 &&
+                 sy <= V2::G - 2;
+    if (ok) {
+      const int gc = cls[gx * V2::G + gy], bc = cls[sx * V2::G + sy];
+      ok = gc != CLS_W && gc != CLS_S && bc != CLS_W && bc != CLS_X && !(sx == gx && sy == gy);
+    }
+    if (!ok) {                                    // rejected: count it, fall back to the S / X cells of maze 1
+      atomicAdd(p.errors, 1u);
+      sx = 4; sy = 4; gx = 8; gy = 8; nl = (nl >= 1 && nl <= 5) ? nl : 1;
+    }
+  } else {
+    WordStream ws;
+    ws.init(p.seed, p.env_id0 + (uint64_t)e, episode);
+    if (episode == 0) r.L = 1 + (int)ws.uniform(5);               // the maze the constructor rolled (:75)
+    const int L0 = r.L - 1;
+    const int g = t.gcand[L0 * V2::MAX_CAND + ws.uniform(t.count[L0])];
+    const int rank = t.brank[L0 * V2::G * V2::G + g];
+    const uint32_t nb = t.count[5 + L0];
+    uint32_t k;
+    if (rank >= 0) { k = ws.uniform(nb - 1); if ((int)k >= rank) k += 1; }
+    else k = ws.uniform(nb);
+    const int b = t.bcand[L0 * V2::MAX_CAND + k];
+    gx = g / V2::G; gy = g % V2::G; sx = b / V2::G; sy = b % V2::G;
+    nl = 1 + (int)ws.uniform(5);
+  }
+  r.L = nl; r.x = sx; r.y = sy; r.gx = gx; r.gy = gy; r.px = sx; r.py = sy; r.a = -1; r.step = 0;
+  episode += 1;
+}
+
+struct V2Lane {
+  LaneOut o;
+  uint32_t mask[V2::C];     // the five 25-bit planes of the env's observation
+};
+
+template <int DUMMY = 0>
+__device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const V2Tables &t) {
+  V2Lane out;
+  LaneOut &o = out.o;
+  o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
+  V2Regs r = v2_unpack(p.state[e], p.goal_count[e]);
+  bool reset_now = false;
+  int reward_code = RC_NEG_ZERO;
+  if (p.mode == MODE_STEP) {
+    long long a64 = load_action(p.actions, p.action_dtype, e);
+    if (a64 < 0 || a64 > 24) { atomicAdd(p.errors, 1u); a64 = a64 < 0 ? 0 : 24; }   // reference raises IndexError
+    const int a = (int)a64;
+    r.step = r.step < V2::STEP_SAT ? r.step + 1 : V2::STEP_SAT;                      // :148
+    const int fx = r.x + a / 5 - 2, fy = r.y + a % 5 - 2;                            // :151-152
+    r.px = r.x; r.py = r.y; r.a = a;                                                 // this obs shows the old crop
+    if (fx < V2::G - 2 && fx > 1 && fy < V2::G - 2 && fy > 1) { r.x = fx; r.y = fy; }  // :157-159
+    else {                                                                           // :160-169 per-axis clamp
+      if (fx >= V2::G - 2) r.x = V2::G - 3;
+      if (fx <= 1) r.x = 2;
+      if (fy >= V2::G - 2) r.y = V2::G - 3;
+      if (fy <= 1) r.y = 2;
+    }
+    const int tc = t.cls[(r.L - 1) * V2::G * V2::G + fx * V2::G + fy];
+    if (fx == r.gx && fy == r.gy) { reward_code = RC_GOAL; o.cls = CLS_X; }          // :175-176
+    else if (tc == CLS_W) { reward_code = RC_WALL; o.cls = CLS_W; }                  // :177-178
+    else if (tc == CLS_B || tc == CLS_S) { reward_code = RC_MOVE; o.cls = CLS_B; }   // :179-180
+    else o.cls = CLS_S;                                                              // 'X' not the goal: -0.0
+    o.done = (reward_code == RC_GOAL) || (r.step > (uint32_t)V2::STEP_LIMIT);        // :222
+    p.reward[e] = __uint_as_float(reward_bits(reward_code));
+    p.done[e] = o.done ? 1 : 0;
+    if (o.done) o.eplen = r.step;
+    reset_now = o.done && p.autoreset;
+    o.render = true;
+  } else if (p.mode == MODE_RESET) {
+    reset_now = (p.mask == nullptr) || (p.mask[e] != 0);
+    o.render = reset_now;
+  } else {
+    o.render = true;
+  }
+  if (reset_now) {
+    uint32_t ep = p.episode[e];
+    v2_respawn(r, p, e, ep, t);
+    p.episode[e] = ep;
+  }
+  uint32_t s, aux;
+  v2_pack(r, s, aux);
+  o.st = s;
+  if (p.mode != MODE_RENDER) { p.state[e] = s; p.goal_count[e] = aux; }
+  o.render = o.render && p.obs != nullptr && e >= p.win_lo && e < p.win_lo + p.win_n;
+  out.mask[0] = v2_free_crop(t, r.L, r.x, r.y);                                      // :185-186
+  out.mask[1] = v2_goal_crop(r.x, r.y, r.gx, r.gy);
+  out.mask[2] = r.a >= 0 ? (1u << r.a) : 0u;                                         // :136-137 / :87
+  out.mask[3] = v2_free_crop(t, r.L, r.px, r.py);                                    // retStatelast (:193)
+  out.mask[4] = v2_goal_crop(r.px, r.py, r.gx, r.gy);
+  return out;
+}
+
+// CTA-cooperative fused reset / step / render for v2.  Warp 0 grabs a 32-env tile from the
+// global work counter, runs the transitions (one env per lane) and parks the five 25-bit planes
+// of every env in shared memory; all threads then write the tile's 784,000 contiguous bytes as
+// float4 stores (double-buffered: warp 0 is already on the next tile).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_env_v2_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_mask[2][32 * V2::C];
+  __shared__ uint32_t s_flags[2];            // bit l: env l of the tile is to be rendered
+  __shared__ long long s_tile[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_blob<V2>(smem, &bar, p.blob);
+  const V2Tables t(smem);
+  const int64_t tiles = p.tile_end;
+  WarpStats ws;
+
+  auto produce = [&](int buf) {              // warp 0 only
+    int64_t tl = 0;
+    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
+    tl = __shfl_sync(0xffffffffu, tl, 0);
+    const int64_t e = tl * 32 + lane;
+    const bool valid = tl < tiles && e < p.n;
+    V2Lane v;
+    v.o.st = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0;
+#pragma unroll
+    for (int c = 0; c < V2::C; ++c) v.mask[c] = 0;
+    if (valid) v = v2_lane(p, e, t);
+    if (p.mode == MODE_STEP) ws.add(valid, v.o);
+#pragma unroll
+    for (int c = 0; c < V2::C; ++c) s_mask[buf][lane * V2::C + c] = v.mask[c];
+    const unsigned fl = __ballot_sync(0xffffffffu, valid && v.o.render);
+    if (lane == 0) { s_flags[buf] = fl; s_tile[buf] = tl; }
+  };
+  if (warp == 0) produce(0);
+  for (int buf = 0;; buf ^= 1) {
+    __syncthreads();
+    const int64_t tile = s_tile[buf];
+    if (tile >= tiles) break;
+    if (warp == 0) produce(buf ^ 1);
+    const uint32_t flags = s_flags[buf];
+    if (flags == 0) continue;
+    const uint32_t *mk = s_mask[buf];
+    const int64_t row0 = tile * 32 - p.win_lo;                       // obs row of the tile's first env
+    float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)V2::OBS_FLOATS;
+    auto value = [&](uint32_t env, uint32_t r) -> uint32_t {         // float bits of obs[env][r]
+      const uint32_t code = t.lut[r];
+      return ((mk[env * V2::C + (code >> 5)] >> (code & 31u)) & 1u) ? 0x3f800000u : 0u;
+    };
+    if (flags == 0xffffffffu && (row0 & 3) == 0) {
+      // fast path: the whole tile is rendered and 16-byte aligned -> 49,000 float4 stores
+      for (uint32_t q = tid; q < V2::TILE_F4; q += THREADS) {
+        uint32_t g = q * 4, env = g / V2::OBS_FLOATS, r = g - env * V2::OBS_FLOATS;
+        uint4 v;
+        uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[k] = value(env, r);
+          if (++r == V2::OBS_FLOATS) { r = 0; ++env; }
+        }
+        st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), v);
+      }
+    } else {
+      // partial tile (batch tail, reset mask, render-window edge): guarded 32-bit stores
+      for (uint32_t g = tid; g < 32 * V2::OBS_FLOATS; g += THREADS) {
+        const uint32_t env = g / V2::OBS_FLOATS, r = g - env * V2::OBS_FLOATS;
+        if ((flags >> env) & 1u) __stcs(reinterpret_cast<unsigned int *>(dst) + g, value(env, r));
+      }
+    }
+  }
+  if (warp == 0) {
+    if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+    if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
+  }
+}
+
+// get/set_state for v2.  cols: x, y, goal_x, goal_y, step_count, layout, aux, episode
+// aux = prev_x | prev_y << 5 | last_action << 10 | action_valid << 15
+__global__ void lmz_state_v2_kernel(int64_t n, uint32_t *state, uint32_t *auxw, uint32_t *episode, int32_t *io, int set) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int32_t *row = io + e * 8;
+  if (set) {
+    auto clampi = [](int v) { return v < 2 ? 2 : (v > V2::G - 3 ? V2::G - 3 : v); };   // ball stays in [2, 15]
+    V2Regs r;
+    r.x = clampi(row[0]); r.y = clampi(row[1]); r.gx = row[2] & 31; r.gy = row[3] & 31;
+    r.step = (uint32_t)row[4] < V2::STEP_SAT ? (uint32_t)row[4] : V2::STEP_SAT;
+    r.L = row[5] < 1 ? 1 : (row[5] > 5 ? 5 : row[5]);
+    r.px = clampi(row[6] & 31); r.py = clampi((row[6] >> 5) & 31);
+    r.a = ((row[6] >> 15) & 1) ? ((row[6] >> 10) & 31) : -1;
+    if (r.a > 24) r.a = 24;
+    uint32_t s, aux;
+    v2_pack(r, s, aux);
+    state[e] = s; auxw[e] = aux; episode[e] = (uint32_t)row[7];
+  } else {
+    const V2Regs r = v2_unpack(state[e], auxw[e]);
+    row[0] = r.x; row[1] = r.y; row[2] = r.gx; row[3] = r.gy; row[4] = (int32_t)r.step; row[5] = r.L;
+    row[6] = (int32_t)auxw[e]; row[7] = (int32_t)episode[e];
+  }
+}
+
+}  // namespace lmz

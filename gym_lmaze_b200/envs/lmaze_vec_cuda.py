@@ -3,6 +3,7 @@
 Host-side mirror of the reference classes for the hot path:
   variant "v0" <-> LmazeEnv     (reference gym_lmaze/envs/lmaze_env.py:11-256)
   variant "v3" <-> LmazeEnv_v3  (reference gym_lmaze/envs/lmaze_env_v3.py:17-402)
+  variant "v2" <-> LmazeEnv_v2  (reference gym_lmaze/envs/lmaze_env_v2.py:17-405; Discrete(25), obs (5,35,35))
 
 Same method names and argument meaning -- `reset()` returns the observation,
 `step(action)` returns `(obs, reward, done, info)` (old-gym 4-tuple,
@@ -21,6 +22,7 @@ from .. import _abi
 from ..spaces import make_spaces
 
 _VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
+             "v2": _abi.LMZ_V2, 2: _abi.LMZ_V2, "lmaze-v2": _abi.LMZ_V2,
              "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3}
 _RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128}
 _OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT}
@@ -47,7 +49,7 @@ class LmazeVecCuda(object):
                  env_id0=0, random_ball=True, random_goal=True, with_obs=True, tune=None, obs_mode="full",
                  obs_window=None):
         if variant not in _VARIANTS:
-            raise ValueError("unknown variant %r (built: v0, v3)" % (variant,))
+            raise ValueError("unknown variant %r (built: v0, v2, v3)" % (variant,))
         if render_mode not in _RENDER:
             raise ValueError("render_mode must be 'tma' or 'st128'")
         if obs_mode not in _OBS_MODE:
@@ -75,7 +77,9 @@ class LmazeVecCuda(object):
         self.obs_dtype = torch.float32 if obs_mode == "full" else torch.uint8
         self.grid_size = self._lib.lmz_grid_size(self.variant)
         self.expansion = self.full_obs_shape[1] // self.grid_size
-        self.single_action_space, self.single_observation_space = make_spaces(4, self.full_obs_shape)
+        self.num_actions = self._lib.lmz_num_actions(self.variant)      # Discrete(4) / Discrete(25)
+        self.num_layouts = self._lib.lmz_num_layouts(self.variant)
+        self.single_action_space, self.single_observation_space = make_spaces(self.num_actions, self.full_obs_shape)
         self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
         self.VISUALIZE = False           # lmaze_env.py:26; cv2 display is out of scope
 
@@ -173,6 +177,8 @@ class LmazeVecCuda(object):
         spawn = torch.as_tensor(spawn)
         if spawn.dim() == 2 and spawn.shape[1] == 2:      # v0 convenience: (x, y) only
             spawn = torch.cat([spawn, torch.full_like(spawn, -1)], dim=1)
+        if spawn.dim() == 2 and spawn.shape[1] == 5:      # v2: (ball_x, ball_y, goal_x, goal_y, new_layout)
+            spawn = torch.cat([spawn[:, :3], (spawn[:, 3:4] | (spawn[:, 4:5] << 5))], dim=1)
         return spawn.to(device=self.device, dtype=torch.int32).contiguous()
 
     # ------------------------------------------------------------------ gym surface
@@ -278,7 +284,8 @@ class LmazeVecCuda(object):
         err = ctypes.c_int64()
         _abi.check(self._lib.lmz_stats(self._h, ctypes.byref(out), ctypes.byref(err), self._stream()))
         if check_errors and err.value:
-            raise ValueError("%d injected spawn cells were rejected (wall/goal/out of range)" % err.value)
+            raise ValueError("%d injected spawn cells were rejected (wall/goal/out of range) or actions were out "
+                             "of range" % err.value)
         return dict(zip(_abi.STAT_NAMES, (int(v) for v in out)))
 
     def stats_reset(self):
@@ -294,9 +301,9 @@ class LmazeVecCuda(object):
     def launch_count(self):
         return int(self._lib.lmz_launch_count(self._h))
 
-    def layout(self):
+    def layout(self, index=1):
         buf = ctypes.create_string_buffer(self.grid_size * self.grid_size)
-        _abi.check(self._lib.lmz_layout(self.variant, buf))
+        _abi.check(self._lib.lmz_layout_ex(self.variant, int(index), buf))
         s = buf.raw.decode("ascii")
         return [s[i * self.grid_size:(i + 1) * self.grid_size] for i in range(self.grid_size)]
 

@@ -48,6 +48,7 @@ typedef enum {
 /* Maze variants (reference class each one replaces). */
 typedef enum {
   LMZ_V0 = 0,   /* LmazeEnv     'lmaze-v0', 12x12, obs f32 (4,84,84)  -- lmaze_env.py:11-256    */
+  LMZ_V2 = 2,   /* LmazeEnv_v2  'lmaze-v2', 5 mazes of 18x18, Discrete(25), obs f32 (5,35,35) -- lmaze_env_v2.py:17-405 */
   LMZ_V3 = 3    /* LmazeEnv_v3  'lmaze-v3', 18x18, obs f32 (3,72,72)  -- lmaze_env_v3.py:17-402 */
 } lmz_variant;
 
@@ -124,6 +125,11 @@ int         lmz_grid_size(int32_t variant);
 int         lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *elem_bytes);
 /* Copies the maze rows (G*G cell letters, row-major, no terminator) -- lmaze_env.py:37-48. */
 int         lmz_layout(int32_t variant, char *cells);
+/* Variants with several mazes (v2: 5, lmaze_env_v2.py:303-405): index is 1-based. */
+int         lmz_num_layouts(int32_t variant);
+int         lmz_layout_ex(int32_t variant, int32_t index, char *cells);
+/* n of the variant's Discrete(n) action space (lmaze_env.py:16, lmaze_env_v2.py:39). */
+int         lmz_num_actions(int32_t variant);
 
 /* ---- handle lifecycle: replaces LmazeEnv.__init__ (lmaze_env.py:14-53) minus its first reset ---- */
 int lmz_create(const lmz_config *cfg, lmz_env **out);
@@ -146,7 +152,9 @@ int lmz_set_window_dl(lmz_env *env, DLManagedTensor *obs, int64_t env_lo);
  * (lmaze_env_v3.py:134-206) for every env whose mask byte is non-zero (mask NULL =
  * all).  spawn NULL => device RNG; else int32 [N][4] = ball_x, ball_y, goal_x,
  * goal_y (the cells the reference's rejection loop would have accepted; goal
- * ignored by v0).  Re-renders obs for the envs it resets. */
+ * ignored by v0; for v2 the last column is goal_y | new_layout << 5, because its
+ * reset also re-rolls the maze, lmaze_env_v2.py:90-92).  Re-renders obs for the
+ * envs it resets. */
 int lmz_reset(lmz_env *env, const uint8_t *mask, const int32_t *spawn, void *stream);
 int lmz_reset_dl(lmz_env *env, DLManagedTensor *mask, DLManagedTensor *spawn, void *stream);
 
@@ -178,7 +186,9 @@ int lmz_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedT
                    DLManagedTensor *dones, void *stream);
 
 /* Unpacked per-env state, int32 [N][LMZ_ST_COLS] on the device (checkpoint /
- * resume, and how parity tests start both sides from the same state). */
+ * resume, and how parity tests start both sides from the same state).  For v2 columns
+ * 5 and 6 are: layout (1..5), and prev_x | prev_y << 5 | last_action << 10 | action_valid << 15
+ * (the position of the previous crop and the action plane of the current obs). */
 int lmz_get_state(lmz_env *env, int32_t *out, void *stream);
 int lmz_set_state(lmz_env *env, const int32_t *in, void *stream);
 int lmz_get_state_dl(lmz_env *env, DLManagedTensor *out, void *stream);

@@ -64,7 +64,7 @@ def test_config_validation_and_no_cpu_fallback(abi):
     h = ctypes.c_void_p()
     bad = abi.LmzConfig.from_buffer_copy(cfg); bad.struct_size = 8
     assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -1 and b"struct_size" in L.lmz_last_error()
-    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.variant = 2
+    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.variant = 5
     assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -4
     bad = abi.LmzConfig.from_buffer_copy(cfg); bad.num_envs = 0
     assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -1

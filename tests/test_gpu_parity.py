@@ -497,3 +497,151 @@ def test_transition_only_mode(lmz, oracle_mod):
             np.array_equal(done.cpu().numpy().view(np.uint8), d_ref)
     assert [env.stats()[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist()
     env.close()
+
+
+# ---------------------------------------------------------------- lmaze-v2 (multi-layout foveal env)
+def _v2_state_rows(L, bx, by, gx, gy, px, py, step, a=None):
+    aux = px | (py << 5) | ((a << 10) | (1 << 15) if a is not None else 0)
+    return [bx, by, gx, gy, step, L, aux, 0]
+
+
+def test_v2_golden_table(lmz, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v2_table.npz"))
+    tab = z["table"]
+    n = len(tab)
+    env = lmz.LmazeVecCuda(n, "v2", autoreset=False)
+    assert env.num_actions == 25 and env.obs.shape[1:] == (5, 35, 35) and env.num_layouts == 5
+    st = np.array([_v2_state_rows(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[8]) for r in tab], np.int32)
+    env.set_state(st)
+    obs, rew, done, info = env.step(torch.as_tensor(tab[:, 7]))
+    out = env.get_state().cpu().numpy()
+    assert np.array_equal(out[:, 0], tab[:, 9]) and np.array_equal(out[:, 1], tab[:, 10])
+    want_bits = np.array([np.float32(np.int64(b).view(np.float64)).view(np.uint32) for b in tab[:, 11]])
+    assert np.array_equal(rbits(rew), want_bits)
+    assert np.array_equal(done.cpu().numpy().astype(np.int64), tab[:, 12])
+    assert np.array_equal(out[:, 4], tab[:, 13])
+    want = torch.from_numpy(np.stack([unpack(b, (5, 35, 35)) for b in z["obs"]]))
+    assert torch.equal(obs.cpu(), want)
+    # layouts exported by the library == the reference's five mazes
+    zl = np.load(os.path.join(golden_dir, "v2_layouts.npz"))["layouts"]
+    for k in range(5):
+        assert env.layout(k + 1) == [str(r) for r in zl[k]]
+    env.close()
+
+
+def test_v2_golden_traces(lmz, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v2_traces.npz"))
+    ne = int(z["n_envs"])
+    env = lmz.LmazeVecCuda(ne, "v2", autoreset=True)
+    init = np.stack([z["e%d_init" % e] for e in range(ne)])        # bx, by, gx, gy, layout, layout-before
+    st = np.array([_v2_state_rows(r[5], 4, 4, 8, 8, 4, 4, 0) for r in init], np.int32)
+    env.set_state(st)                                              # the maze the constructor rolled
+    obs = env.reset(spawn=init[:, :5])
+    want = np.stack([unpack(z["e%d_first_obs" % e], (5, 35, 35)) for e in range(ne)])
+    assert np.array_equal(obs.cpu().numpy(), want)
+    T = len(z["e0_actions"])
+    for t in range(T):
+        acts = np.array([z["e%d_actions" % e][t] for e in range(ne)])
+        s5 = np.stack([z["e%d_spawn" % e][t] for e in range(ne)])
+        dref = np.array([z["e%d_done" % e][t] for e in range(ne)])
+        s5 = np.where(dref[:, None] > 0, s5, 0)
+        obs, rew, done, _ = env.step(torch.as_tensor(acts), spawn=s5)
+        want_r = np.array([np.float32(np.int64(z["e%d_reward_bits" % e][t]).view(np.float64)).view(np.uint32)
+                           for e in range(ne)])
+        assert np.array_equal(rbits(rew), want_r), t
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), dref), t
+        want_o = np.stack([unpack(z["e%d_obs" % e][t], (5, 35, 35)) for e in range(ne)])
+        assert np.array_equal(obs.cpu().numpy(), want_o), t
+    assert env.stats()["episodes"] == sum(int(z["e%d_done" % e].sum()) for e in range(ne))
+    env.close()
+
+
+@pytest.mark.parametrize("inject", [True, False])
+def test_v2_4096_envs_vs_oracle(lmz, oracle_mod, inject):
+    """Config-2-style parity for v2: per step reward bits, done, whole obs; injected or device-RNG resets."""
+    N, T, seed = (512, 70, 31) if inject else (4096, 130, 31)
+    ora = oracle_mod.OracleVec(oracle_mod.V2, N, seed=seed, env_id0=77, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, "v2", seed=seed, env_id0=77, autoreset=True)
+    rng = np.random.RandomState(3)
+    cands = []
+    for k in range(1, 6):
+        rows = oracle_mod.layout_v2(k)
+        gc = [(x, y) for x in range(1, 17) for y in range(1, 17) if rows[x][y] not in "WS"]
+        bc = [(x, y) for x in range(1, 17) for y in range(1, 17) if rows[x][y] not in "WX"]
+        cands.append((gc, bc))
+
+    def draw_spawn(cur_layouts):
+        """what the reference's rejection loops could have produced on each env's CURRENT maze"""
+        out = np.zeros((N, 5), np.int64)
+        for i in range(N):
+            gc, bc = cands[cur_layouts[i] - 1]
+            g = gc[rng.randint(len(gc))]
+            b = g
+            while b == g:
+                b = bc[rng.randint(len(bc))]
+            out[i] = (b[0], b[1], g[0], g[1], rng.randint(1, 6))
+        return out
+
+    def packed(s5):
+        return np.stack([s5[:, 0], s5[:, 1], s5[:, 2], s5[:, 3] | (s5[:, 4] << 5)], 1)
+    if inject:
+        s5 = draw_spawn(np.ones(N, int))
+        o_ref = ora.reset(spawn=packed(s5)); o_gpu = env.reset(spawn=s5)
+    else:
+        o_ref = ora.reset(); o_gpu = env.reset()
+    assert torch.equal(o_gpu.cpu(), torch.from_numpy(o_ref))
+    gen = torch.Generator().manual_seed(9)
+    obs_buf = np.empty((N, 5, 35, 35), np.float32)
+    for t in range(T):
+        a = torch.randint(0, 25, (N,), generator=gen)
+        if inject:
+            s5 = draw_spawn(ora.export_aux()[:, 0])
+            _, r_ref, d_ref = ora.step(a.numpy(), spawn=packed(s5), obs_out=obs_buf)
+            obs, rew, done, _ = env.step(a, spawn=s5)
+        else:
+            _, r_ref, d_ref = ora.step(a.numpy(), obs_out=obs_buf)
+            obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)), t
+        assert np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
+        assert torch.equal(obs.cpu(), torch.from_numpy(obs_buf)), t
+    st = env.get_state().cpu().numpy()
+    pos, sc, _, _ = ora.export()
+    aux = ora.export_aux()
+    assert np.array_equal(st[:, 0:4], pos) and np.array_equal(st[:, 4], sc) and np.array_equal(st[:, 5], aux[:, 0])
+    assert np.array_equal(st[:, 7], ora.episode)
+    s = env.stats()
+    assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist()
+    assert s["episodes"] >= N and s["goals"] > 0
+    if not inject:
+        assert torch.equal(env.render_obs().cpu(), torch.from_numpy(np.stack([ora.render_one(i) for i in range(N)])))
+    env.close()
+
+
+def test_v2_windows_and_masks(lmz, oracle_mod):
+    """Partial tiles: batch tail (N % 32 != 0), render window edges, masked reset."""
+    N, W = 1003, 333
+    ora = oracle_mod.OracleVec(oracle_mod.V2, N, seed=2, autoreset=True)
+    env = lmz.LmazeVecCuda(N, "v2", seed=2, autoreset=True, obs_window=W)
+    ora.reset(want_obs=False); env.reset()
+    gen = torch.Generator().manual_seed(1)
+    for t in range(5):
+        a = torch.randint(0, 25, (N,), generator=gen)
+        o_ref, r_ref, d_ref = ora.step(a.numpy())
+        lo = (t * 211) % (N - W + 1)
+        env.set_window(lo)
+        env.obs.fill_(5)
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32))
+        assert torch.equal(obs.cpu(), torch.from_numpy(o_ref[lo:lo + W])), t
+        assert torch.equal(env.render_window(N - W).cpu(), torch.from_numpy(o_ref[N - W:]))
+    from gym_lmaze_b200._abi import LmzError
+    with pytest.raises(LmzError, match="not built"):
+        env.rollout(4)
+    env.close()
+    # out-of-range actions are clamped and reported
+    env = lmz.LmazeVecCuda(8, "v2", seed=1)
+    env.reset()
+    env.step(torch.tensor([0, 24, 25, -1, 7, 300, 12, 3]))
+    with pytest.raises(ValueError, match="3 "):
+        env.stats()
+    env.close()
