@@ -99,7 +99,9 @@ def main():
         goals = [free[i] for i in rng.choice(len(free), 2, replace=False)] + [(5, 5)]   # (5,5) is a wall in some mazes
         for ball in balls:
             for goal in goals:
-                prev = free[rng.randint(len(free))]
+                # retStatelast is normally the crop at the ball's own cell (that is what step()/reset()
+                # leave behind); every other goal uses an arbitrary cell to show the oracle does not care
+                prev = ball if (len(recs) // 25) % 2 == 0 else free[rng.randint(len(free))]
                 for a in range(25):
                     place(env, rows, ball, goal, prev, 7)
                     obs, r, d, info = env.step(a)
