@@ -556,8 +556,32 @@ __global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams 
 }
 
 // ------------------------------------------------------------------ T-step rollout, no per-step obs
+// One thread per env, state in registers for all T steps.  This kernel is issue-bound, not
+// HBM-bound (5.25 B of output per env-step), so the per-step path is kept to a few dozen
+// instructions: linear cell index + delta, branch-free move / reward code (CLS_* + 1 == RC_*),
+// reward bits from a 4-entry constant table, pointer-bumped [T][N] stores, and the next spawn
+// drawn ONCE before the loop so the divergent Philox path only runs when an env finishes a
+// second episode inside the same rollout.
+__constant__ uint32_t c_reward_bits[4] = {0x80000000u, 0xBF800000u, 0xBC23D70Au, 0x42C80000u};
+
+template <class V>
+__device__ __forceinline__ void draw_spawn(const KParams &p, uint64_t gid, uint32_t episode, const uint16_t *cand,
+                                           int &ball, int &goal) {
+  WordStream ws;
+  ws.init(p.seed, gid, episode);
+  if (V::ID == 0) {
+    ball = cand[ws.uniform((uint32_t)p.n_cand)];
+    goal = -1;
+  } else {
+    const uint32_t gi = ws.uniform((uint32_t)p.n_cand);
+    uint32_t bi = ws.uniform((uint32_t)p.n_cand - 1u);
+    if (bi >= gi) bi += 1;
+    goal = cand[gi]; ball = cand[bi];
+  }
+}
+
 template <class V, int THREADS>
-__global__ void __launch_bounds__(THREADS) lmz_rollout_kernel(const KParams p) {
+__global__ void __launch_bounds__(THREADS, 3) lmz_rollout_kernel(const KParams p) {
   __shared__ uint8_t cls[V::G * V::G];
   __shared__ uint16_t cand[V::MAX_CAND];
   __shared__ unsigned long long blk_stats[NUM_STATS];
@@ -567,49 +591,103 @@ __global__ void __launch_bounds__(THREADS) lmz_rollout_kernel(const KParams p) {
   if (threadIdx.x < NUM_STATS) blk_stats[threadIdx.x] = 0;
   __syncthreads();
 
-  uint32_t c_ep = 0, c_goal = 0, c_wall = 0, c_move = 0, c_stale = 0, c_steps = 0;
+  uint32_t c_ep = 0, c_goal = 0, c_wall = 0, c_stale = 0, c_steps = 0;
   unsigned long long c_len = 0;
   const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+  const bool fast_spawn = p.autoreset && p.spawn == nullptr && p.random_ball && (V::ID == 0 || p.random_goal);
 
   for (int64_t e = (int64_t)blockIdx.x * THREADS + threadIdx.x; e < p.n; e += (int64_t)gridDim.x * THREADS) {
     EnvRegs r = V::unpack(p.state[e]);
     uint32_t ep = p.episode[e];
     uint32_t hits = 0;
     const uint64_t gid = p.env_id0 + (uint64_t)e;
-    uint32_t w[4] = {0, 0, 0, 0};
-    for (int t = 0; t < p.T; ++t) {
-      long long a;
+    int pos = r.x * V::G + r.y, gpos = r.gx * V::G + r.gy, rcode = r.rcode;
+    uint32_t step = r.step;
+    int nball = 0, ngoal = 0;
+    bool have_next = false;
+    if (fast_spawn) { draw_spawn<V>(p, gid, ep, cand, nball, ngoal); have_next = true; }
+    float *rp = p.reward + e;
+    uint8_t *dp = p.done + e;
+    // action source: a [T][N] buffer, or Philox (one block = 64 two-bit actions, consumed 2 bits a step)
+    uint32_t w[4] = {0, 0, 0, 0}, cur = 0;
+    int left = 0;                       // actions left in `cur`
+    uint64_t tg = p.t0;
+    constexpr int CH = 8;               // caller-supplied actions are fetched CH steps ahead (independent loads)
+    long long abuf[CH];
+    for (int t = 0; t < p.T; ++t, ++tg, rp += p.n, dp += p.n) {
+      int d;                            // linear offset of the move: -G, +G, -1, +1 or 0 (lmaze_env.py:153-170)
       if (p.actions) {
-        a = load_action(p.actions, p.action_dtype, (int64_t)t * p.n + e);
-      } else {
-        const uint64_t tg = p.t0 + (uint64_t)t;
-        const uint32_t slot = (uint32_t)(tg & 63);
-        if (slot == 0 || t == 0) {      // one Philox block = 64 two-bit actions
-          const uint64_t blk = tg >> 6;
-          philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk,
-                        ((uint32_t)(blk >> 32) << 8) | TAG_ACTION, k0, k1, w);
+        if ((t & (CH - 1)) == 0) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            abuf[k] = (t + k < p.T) ? load_action(p.actions, p.action_dtype, (int64_t)(t + k) * p.n + e) : 0;
         }
-        const uint32_t word = (slot >> 4) == 0 ? w[0] : (slot >> 4) == 1 ? w[1] : (slot >> 4) == 2 ? w[2] : w[3];
-        a = (word >> (2 * (slot & 15))) & 3u;
+        long long a = abuf[0];
+#pragma unroll
+        for (int k = 1; k < CH; ++k) a = ((t & (CH - 1)) == k) ? abuf[k] : a;
+        d = a == 0 ? -V::G : a == 1 ? V::G : a == 2 ? -1 : a == 3 ? 1 : 0;
+      } else {
+        if (left == 0) {
+          const uint32_t slot = (uint32_t)(tg & 63);
+          if (slot == 0 || t == 0) {
+            const uint64_t blk = tg >> 6;
+            philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk,
+                          ((uint32_t)(blk >> 32) << 8) | TAG_ACTION, k0, k1, w);
+          }
+          const uint32_t wi = slot >> 4;
+          cur = (wi == 0 ? w[0] : wi == 1 ? w[1] : wi == 2 ? w[2] : w[3]) >> (2 * (slot & 15));
+          left = 16 - (int)(slot & 15);
+        }
+        const uint32_t a = cur & 3u;
+        cur >>= 2; left -= 1;
+        d = (a & 2u) ? ((a & 1u) ? 1 : -1) : ((a & 1u) ? V::G : -V::G);
       }
-      const StepOut o = transition<V>(r, a, cls, hits);
-      const int64_t oi = (int64_t)t * p.n + e;
-      __stcs(p.reward + oi, __uint_as_float(reward_bits(r.rcode)));
-      __stcs(p.done + oi, (uint8_t)(o.done ? 1 : 0));
-      c_steps += 1;
-      c_wall += (o.cls == CLS_W); c_move += (o.cls == CLS_B || o.cls == CLS_X); c_stale += (o.cls == CLS_S);
-      if (o.done) {
-        c_ep += 1; c_len += r.step; c_goal += (o.cls == CLS_X);
-        if (p.autoreset) respawn<V>(r, p, e, ep, cls, cand);
+      step = step < V::STEP_SAT ? step + 1 : V::STEP_SAT;
+      const int tcls = cls[pos + d];
+      bool done;
+      int branch;                       // CLS_W wall, CLS_B move, CLS_X goal, CLS_S none
+      if (V::ID == 0) {
+        // W: stay, -1 | B: move, -0.01 | X: move, 100 | S: nothing, reward kept (lmaze_env.py:172-196)
+        pos += (tcls == CLS_B || tcls == CLS_X) ? d : 0;
+        rcode = (tcls == CLS_S) ? rcode : tcls + 1;
+        hits += (tcls == CLS_X);
+        branch = tcls;
+        done = (rcode == RC_GOAL) || (step == (uint32_t)V::STEP_LIMIT);
+      } else {
+        // W: stay, -1 | else move, -0.01, and 100 if one more step would reach the goal (lmaze_env_v3.py:251-265)
+        const bool wall = tcls == CLS_W;
+        pos += wall ? 0 : d;
+        const bool goal = !wall && (pos + d == gpos);
+        rcode = wall ? RC_WALL : goal ? RC_GOAL : RC_MOVE;
+        branch = wall ? CLS_W : goal ? CLS_X : CLS_B;
+        done = goal || (step > (uint32_t)V::STEP_LIMIT);
+      }
+      __stcs(rp, __uint_as_float(c_reward_bits[rcode]));
+      __stcs(dp, (uint8_t)(done ? 1 : 0));
+      c_wall += (branch == CLS_W); c_stale += (branch == CLS_S);
+      if (done) {
+        c_ep += 1; c_len += step; c_goal += (branch == CLS_X);
+        if (p.autoreset) {
+          if (have_next) {              // the pre-drawn spawn of episode `ep`
+            pos = nball; if (V::ID == 3) gpos = ngoal;
+            step = 0; rcode = RC_NEG_ZERO; ep += 1; have_next = false;
+          } else {                      // slow path: injected spawns, pinned ball/goal, or a 2nd reset in this rollout
+            r.x = pos / V::G; r.y = pos % V::G; r.gx = gpos / V::G; r.gy = gpos % V::G; r.step = step; r.rcode = rcode;
+            respawn<V>(r, p, e, ep, cls, cand);
+            pos = r.x * V::G + r.y; gpos = r.gx * V::G + r.gy; step = r.step; rcode = r.rcode;
+          }
+        }
       }
     }
+    c_steps += (uint32_t)p.T;
+    r.x = pos / V::G; r.y = pos % V::G; r.gx = gpos / V::G; r.gy = gpos % V::G; r.step = step; r.rcode = rcode;
     p.state[e] = V::pack(r);
     p.episode[e] = ep;
     if (V::ID == 0 && hits) p.goal_count[e] += hits;
   }
   // statistics: warp reduce -> shared atomics -> one global atomic per counter per CTA
-  unsigned long long v[NUM_STATS] = {c_steps, c_ep, c_goal, (unsigned long long)(c_ep - c_goal), c_wall, c_move,
-                                     c_stale, c_len};
+  unsigned long long v[NUM_STATS] = {c_steps, c_ep, c_goal, (unsigned long long)(c_ep - c_goal), c_wall,
+                                     (unsigned long long)(c_steps - c_wall - c_stale), c_stale, c_len};
 #pragma unroll
   for (int k = 0; k < NUM_STATS; ++k) {
     unsigned long long x = v[k];
