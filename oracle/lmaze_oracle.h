@@ -29,6 +29,7 @@ extern "C" {
 #define LMZO_V0 0
 #define LMZO_V2 2
 #define LMZO_V3 3
+#define LMZO_V4 4
 #define LMZO_MAX_G 18
 
 /* One environment, holding the same mutable fields the reference keeps on `self`. */
@@ -93,6 +94,14 @@ int  lmzo_step(lmzo_env *e, int64_t action, int *cls_out);
  * re-rolled to `new_layout` (1..5) -- the order of lmaze_env_v2.py:90-92.  -1 if the reference's
  * rejection loops (:277-299) would not have accepted the cells. */
 int  lmzo_reset_v2(lmzo_env *e, int sx, int sy, int gx, int gy, int new_layout);
+/* v4 reset (lmaze_env_v4.py:89-149): the maze is re-rolled FIRST, goal and ball are drawn on the
+ * NEW maze, state[2] (the visit layer) restarts at visitMap/2. */
+int  lmzo_reset_v4(lmzo_env *e, int sx, int sy, int gx, int gy, int new_layout);
+void lmzo_rng_spawn_v4(uint64_t seed, uint64_t env_id, uint32_t episode,
+                       int *sx, int *sy, int *gx, int *gy, int *new_layout);
+/* v4 visit layer state[2] (float32 [G*G]) of every env: read / overwrite */
+void lmzo_vec_export_visit(const lmzo_env *envs, int64_t n, float *out);
+void lmzo_env_set_visit(lmzo_env *e, const float *visit);
 /* The five 18x18 mazes of lmaze_env_v2.py:303-405 (layout 1..5). */
 int  lmzo_layout_v2(int layout, char *cells);
 

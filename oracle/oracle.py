@@ -12,10 +12,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblmaze_oracle.so")
 
-V0, V2, V3 = 0, 2, 3
+V0, V2, V3, V4 = 0, 2, 3, 4
 NUM_STATS = 8
 STAT_NAMES = ("steps", "episodes", "goals", "timeouts", "wall_bumps", "moves", "stale", "eplen_sum")
-OBS_SHAPE = {V0: (4, 84, 84), V2: (5, 35, 35), V3: (3, 72, 72)}
+OBS_SHAPE = {V0: (4, 84, 84), V2: (5, 35, 35), V3: (3, 72, 72), V4: (7, 35, 35)}
 # f32 bit patterns of the only rewards the reference can emit
 REWARD_BITS = {"neg_zero": 0x80000000, "wall": 0xBF800000, "move": 0xBC23D70A, "goal": 0x42C80000}
 
@@ -78,6 +78,10 @@ def lib():
     L.lmzo_env_force_v2.restype = ctypes.c_int
     L.lmzo_vec_export_aux.argtypes = [vp, i64, vp]
     L.lmzo_vec_export_aux.restype = None
+    L.lmzo_vec_export_visit.argtypes = [vp, i64, vp]
+    L.lmzo_vec_export_visit.restype = None
+    L.lmzo_env_set_visit.argtypes = [vp, vp]
+    L.lmzo_env_set_visit.restype = None
     L.lmzo_layout_v2.argtypes = [ctypes.c_int, ctypes.c_char_p]
     L.lmzo_layout_v2.restype = ctypes.c_int
     L.lmzo_rng_spawn_v2.argtypes = [u64, u64, u32, ctypes.c_int] + [ip] * 6
@@ -196,6 +200,17 @@ class OracleVec(object):
         rc = self.L.lmzo_env_force_v2(self._env(i), layout, sx, sy, gx, gy, px, py, step_count)
         if rc != 0:
             raise ValueError("oracle rejected forced v2 state")
+
+    def export_visit(self):
+        """v4 visit layer state[2] of every env, float32 [N, 18, 18]."""
+        out = np.empty((self.n, 18, 18), dtype=np.float32)
+        self.L.lmzo_vec_export_visit(_ptr(self._mem), self.n, _ptr(out))
+        return out
+
+    def set_visit(self, i, visit):
+        v = np.ascontiguousarray(visit, dtype=np.float32)
+        assert v.size == 324
+        self.L.lmzo_env_set_visit(self._env(i), _ptr(v))
 
     def export_aux(self):
         """int32 [N,4]: layout, prev_x, prev_y, bad_actions (v2)."""

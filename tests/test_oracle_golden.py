@@ -266,3 +266,52 @@ def ctypes_grid(o, i):
     """char* to env i's grid (offset of lmzo_env.grid = 7 ints)."""
     import ctypes
     return ctypes.cast(o._env(i) + 7 * 4, ctypes.c_char_p)
+
+
+# ---------------------------------------------------------------- v4 (v2 + float visit layer)
+def v4_obs(bits, visit):
+    """Rebuild the reference's (7,35,35) obs from the fixture's packed binary channels + 5x5 visit crops."""
+    b = np.unpackbits(bits)[:125].reshape(5, 5, 5).astype(np.float32)
+    small = np.stack([b[0], b[1], visit[0], b[2], b[3], b[4], visit[1]])
+    return np.repeat(np.repeat(small, 7, 1), 7, 2)
+
+
+def test_v4_transition_table(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v4_table.npz"))
+    o = oracle_mod.OracleVec(oracle_mod.V4, 1, autoreset=False)
+    for k, row in enumerate(z["table"]):
+        L, bx, by, gx, gy, a, sb, nx, ny, rb, d, sa = (int(v) for v in row)
+        o.force_v2(0, L, bx, by, gx, gy, bx, by, step_count=sb)
+        o.set_visit(0, z["pre_visit"][k])
+        dd, _ = o.step_one(0, a)
+        pos, sc, _, rw = o.export()
+        assert tuple(pos[0]) == (nx, ny, gx, gy) and rw.view(np.int64)[0] == rb and dd == d and sc[0] == sa
+        assert np.array_equal(o.export_visit()[0].view(np.uint32), z["post_visit"][k].view(np.uint32))   # bit-exact f32
+        got = o.render_one(0)
+        assert np.array_equal(got.view(np.uint32), v4_obs(z["obs_bits"][k], z["obs_visit"][k]).view(np.uint32))
+
+
+def test_v4_traces(oracle_mod, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v4_traces.npz"))
+    ne = int(z["n_envs"])
+    o = oracle_mod.OracleVec(oracle_mod.V4, ne, autoreset=True)
+    init = np.stack([z["e%d_init" % e] for e in range(ne)])        # bx, by, gx, gy, layout
+    obs = o.reset(spawn=np.stack([init[:, 0], init[:, 1], init[:, 2], init[:, 3] | (init[:, 4] << 5)], 1))
+    for e in range(ne):
+        assert np.array_equal(obs[e], v4_obs(z["e%d_first_bits" % e], z["e%d_first_visit" % e]))
+    T = len(z["e0_actions"])
+    for t in range(T):
+        acts = np.array([z["e%d_actions" % e][t] for e in range(ne)])
+        s5 = np.stack([z["e%d_spawn" % e][t] for e in range(ne)])
+        dref = np.array([z["e%d_done" % e][t] for e in range(ne)])
+        spawn = np.where(dref[:, None] > 0, np.stack([s5[:, 0], s5[:, 1], s5[:, 2], s5[:, 3] | (s5[:, 4] << 5)], 1), 0)
+        obs, rew, done = o.step(acts, spawn=spawn)
+        vis = o.export_visit()
+        for e in range(ne):
+            assert rew[e].view(np.uint32) == np.float32(f64(z["e%d_reward_bits" % e][t])).view(np.uint32), (t, e)
+            assert done[e] == dref[e], (t, e)
+            want = v4_obs(z["e%d_obs_bits" % e][t], z["e%d_obs_visit" % e][t])
+            assert np.array_equal(obs[e].view(np.uint32), want.view(np.uint32)), (t, e)
+            assert float(vis[e].astype(np.float64).sum()) == z["e%d_visit_sum" % e][t]
+    for e in range(ne):
+        assert np.array_equal(vis[e].view(np.uint32), z["e%d_final_visit" % e].view(np.uint32))
