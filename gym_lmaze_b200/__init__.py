@@ -32,9 +32,11 @@ def registered_ids():
 register("lmaze-v0", "v0", num_envs=1)
 register("lmaze-v2", "v2", num_envs=1)
 register("lmaze-v3", "v3", num_envs=1)
+register("lmaze-v4", "v4", num_envs=1)
 register("lmaze-vec-v0", "v0", num_envs=4096)
 register("lmaze-vec-v2", "v2", num_envs=4096)
 register("lmaze-vec-v3", "v3", num_envs=4096)
+register("lmaze-vec-v4", "v4", num_envs=4096)
 
 
 def _register_with_gym():

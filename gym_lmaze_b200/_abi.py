@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblmaze_b200.so")
 
-LMZ_V0, LMZ_V2, LMZ_V3 = 0, 2, 3
+LMZ_V0, LMZ_V2, LMZ_V3, LMZ_V4 = 0, 2, 3, 4
 RENDER_TMA, RENDER_ST128 = 0, 1
 OBS_FULL, OBS_COMPACT = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
@@ -24,7 +24,8 @@ EXPORTS = (
     "lmz_layout", "lmz_num_layouts", "lmz_layout_ex", "lmz_num_actions", "lmz_set_window", "lmz_set_window_dl",
     "lmz_create", "lmz_destroy", "lmz_bind", "lmz_bind_dl", "lmz_reset", "lmz_reset_dl", "lmz_step",
     "lmz_step_dl", "lmz_step_host", "lmz_render", "lmz_rollout", "lmz_rollout_dl", "lmz_get_state",
-    "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
+    "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_get_visit", "lmz_set_visit", "lmz_get_visit_dl",
+    "lmz_set_visit_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
 )
 
 
@@ -95,6 +96,10 @@ def load():
     L.lmz_set_state.argtypes = [vp, vp, vp]
     L.lmz_get_state_dl.argtypes = [vp, vp, vp]
     L.lmz_set_state_dl.argtypes = [vp, vp, vp]
+    L.lmz_get_visit.argtypes = [vp, vp, vp]
+    L.lmz_set_visit.argtypes = [vp, vp, vp]
+    L.lmz_get_visit_dl.argtypes = [vp, vp, vp]
+    L.lmz_set_visit_dl.argtypes = [vp, vp, vp]
     L.lmz_stats.argtypes = [vp, ctypes.POINTER(i64 * NUM_STATS), ctypes.POINTER(i64), vp]
     L.lmz_stats_reset.argtypes = [vp, vp]
     L.lmz_launch_count.argtypes = [vp]

@@ -125,14 +125,21 @@ void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand
   }
 }
 
-void build_blob_v2(std::vector<unsigned char> &blob) {
-  using V = lmz::V2;
+template <class V>
+void build_blob_fov(std::vector<unsigned char> &blob) {
   blob.assign(V::BLOB_BYTES, 0);
-  // (channel, cell) of every float of an env's (5,35,35) image: the x7 upsample of lmaze_env_v2.py:197-203
+  // (slot, cell) of every float of an env's (C,35,35) image: the x7 upsample of lmaze_env_v2.py:197-203.
+  // slot = which per-env plane feeds the channel: bit planes 0 free, 1 goal, 2 action, 3 prev free,
+  // 4 prev goal; float planes 5 visit, 6 visit at the previous window (v4 channel order:
+  // crop(free, goal, visit), action, retStatelast(free, goal, visit) -- lmaze_env_v4.py:37-40,236-239).
+  static const int slot_v2[5] = {0, 1, 2, 3, 4};
+  static const int slot_v4[7] = {0, 1, 5, 2, 3, 4, 6};
+  const int *slot = (V::C == 7) ? slot_v4 : slot_v2;
   for (int c = 0; c < V::C; ++c)
     for (int row = 0; row < V::S; ++row)
       for (int col = 0; col < V::S; ++col)
-        blob[V::LUT_OFF + (c * V::S + row) * V::S + col] = (unsigned char)((c << 5) | ((row / V::E) * V::F + col / V::E));
+        blob[V::LUT_OFF + (c * V::S + row) * V::S + col] =
+            (unsigned char)((slot[c] << 5) | ((row / V::E) * V::F + col / V::E));
   uint32_t *rowbits = reinterpret_cast<uint32_t *>(blob.data() + V::ROWBITS_OFF);
   uint16_t *gcand = reinterpret_cast<uint16_t *>(blob.data() + V::GCAND_OFF);
   uint16_t *bcand = reinterpret_cast<uint16_t *>(blob.data() + V::BCAND_OFF);
@@ -167,6 +174,7 @@ struct lmz_env {
   int num_sms;
   // device memory owned by the handle
   uint32_t *state, *goal_count, *episode;
+  float *visit;                  // v4 only: f32 [N][324]
   unsigned char *blob;
   unsigned long long *stats;     // NUM_STATS counters + 1 error counter + 2 work-distribution words
   void *act_stage;               // lmz_step_host staging, lazily allocated (N * 8 bytes)
@@ -199,7 +207,7 @@ lmz::KParams base_params(lmz_env *h) {
   lmz::KParams p;
   memset(&p, 0, sizeof(p));
   p.n = h->cfg.num_envs;
-  p.state = h->state; p.goal_count = h->goal_count; p.episode = h->episode;
+  p.state = h->state; p.goal_count = h->goal_count; p.episode = h->episode; p.visit = h->visit;
   p.obs = h->obs; p.reward = h->reward; p.done = h->done;
   p.win_lo = h->win_lo; p.win_n = h->win_n;
   p.tile_begin = 0; p.tile_end = (p.n + 31) / 32;
@@ -268,28 +276,30 @@ int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   }
 }
 
-int launch_v2(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+template <class W>
+int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   constexpr int THREADS = 512;
-  auto kern = lmz::lmz_env_v2_kernel<THREADS>;
+  auto kern = lmz::lmz_env_fov_kernel<W, THREADS>;
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
   if (configured_dev != h->cfg.device) {
-    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, lmz::V2::BLOB_BYTES));
-    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "v2 kernel does not fit on an SM");
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, W::BLOB_BYTES));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal env kernel does not fit on an SM");
     configured_dev = h->cfg.device;
   }
   const int64_t units = p.tile_end - p.tile_begin;
   int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
   if (grid > units) grid = units;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, THREADS, lmz::V2::BLOB_BYTES, s>>>(p);
+  kern<<<(unsigned)grid, THREADS, W::BLOB_BYTES, s>>>(p);
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
 }
 
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (h->cfg.variant == LMZ_V2) return launch_v2(h, p, s);
+  if (h->cfg.variant == LMZ_V2) return launch_fov<lmz::V2>(h, p, s);
+  if (h->cfg.variant == LMZ_V4) return launch_fov<lmz::V4>(h, p, s);
   if (h->cfg.variant == LMZ_V0) return launch_env_v<lmz::V0>(h, p, s);
   return launch_env_v<lmz::V3>(h, p, s);
 }
@@ -400,18 +410,19 @@ int lmz_obs_shape(int32_t variant, int64_t shape[3]) {
   if (variant == LMZ_V0) { shape[0] = lmz::V0::C; shape[1] = shape[2] = lmz::V0::S; return LMZ_OK; }
   if (variant == LMZ_V3) { shape[0] = lmz::V3::C; shape[1] = shape[2] = lmz::V3::S; return LMZ_OK; }
   if (variant == LMZ_V2) { shape[0] = lmz::V2::C; shape[1] = shape[2] = lmz::V2::S; return LMZ_OK; }
+  if (variant == LMZ_V4) { shape[0] = lmz::V4::C; shape[1] = shape[2] = lmz::V4::S; return LMZ_OK; }
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_num_actions(int32_t variant) {
   if (variant == LMZ_V0 || variant == LMZ_V3) return 4;      // lmaze_env.py:16, lmaze_env_v3.py:92
-  if (variant == LMZ_V2) return 25;                          // lmaze_env_v2.py:39
+  if (variant == LMZ_V2 || variant == LMZ_V4) return 25;     // lmaze_env_v2.py:39 (commented out in v4, :43-44)
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_num_layouts(int32_t variant) {
   if (variant == LMZ_V0 || variant == LMZ_V3) return 1;
-  if (variant == LMZ_V2) return 5;                           // lmaze_env_v2.py:306
+  if (variant == LMZ_V2 || variant == LMZ_V4) return 5;      // lmaze_env_v2.py:306, lmaze_env_v4.py:351
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
@@ -420,7 +431,7 @@ int lmz_layout_ex(int32_t variant, int32_t index, char *cells) {
   const int nl = lmz_num_layouts(variant);
   if (nl < 0) return nl;
   if (index < 1 || index > nl) return fail(LMZ_ERR_INVALID, "layout index %d outside 1..%d", index, nl);
-  if (variant == LMZ_V2) { v2_cells(index, cells); return LMZ_OK; }
+  if (variant == LMZ_V2 || variant == LMZ_V4) { v2_cells(index, cells); return LMZ_OK; }
   return lmz_layout(variant, cells);
 }
 
@@ -440,12 +451,12 @@ int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *e
 
 int lmz_grid_size(int32_t variant) {
   if (variant == LMZ_V0) return lmz::V0::G;
-  if (variant == LMZ_V3 || variant == LMZ_V2) return lmz::V3::G;
+  if (variant == LMZ_V3 || variant == LMZ_V2 || variant == LMZ_V4) return lmz::V3::G;
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_layout(int32_t variant, char *cells) {
-  if (variant == LMZ_V2) return lmz_layout_ex(variant, 1, cells);
+  if (variant == LMZ_V2 || variant == LMZ_V4) return lmz_layout_ex(variant, 1, cells);
   const char *c = cells_of(variant);
   if (!c) return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
   if (!cells) return fail(LMZ_ERR_INVALID, "cells is NULL");
@@ -460,11 +471,12 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (cfg->struct_size != (int32_t)sizeof(lmz_config))
     return fail(LMZ_ERR_INVALID, "lmz_config.struct_size %d != %d: header/library mismatch", cfg->struct_size,
                 (int)sizeof(lmz_config));
-  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3 && cfg->variant != LMZ_V2)
-    return fail(LMZ_ERR_UNSUPPORTED, "variant %d is not built (supported: 0 = lmaze-v0, 2 = lmaze-v2, 3 = lmaze-v3)",
-                cfg->variant);
-  if (cfg->variant == LMZ_V2 && cfg->obs_mode != LMZ_OBS_FULL)
-    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2 has no compact observation mode yet");
+  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3 && cfg->variant != LMZ_V2 && cfg->variant != LMZ_V4)
+    return fail(LMZ_ERR_UNSUPPORTED,
+                "variant %d is not built (supported: 0 = lmaze-v0, 2 = lmaze-v2, 3 = lmaze-v3, 4 = lmaze-v4)", cfg->variant);
+  const bool foveal = cfg->variant == LMZ_V2 || cfg->variant == LMZ_V4;
+  if (foveal && cfg->obs_mode != LMZ_OBS_FULL)
+    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2/v4 have no compact observation mode yet");
   if (cfg->num_envs < 1) return fail(LMZ_ERR_INVALID, "num_envs must be >= 1 (got %lld)", (long long)cfg->num_envs);
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
   if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128)
@@ -508,7 +520,12 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   } else if (cfg->variant == LMZ_V2) {
     h->G = lmz::V2::G; h->C = lmz::V2::C; h->S = lmz::V2::S; h->obs_bytes_per_env = lmz::V2::OBS_BYTES;
     h->compact_bytes_per_env = 0;
-    build_blob_v2(blob);
+    build_blob_fov<lmz::V2>(blob);
+    h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
+  } else if (cfg->variant == LMZ_V4) {
+    h->G = lmz::V4::G; h->C = lmz::V4::C; h->S = lmz::V4::S; h->obs_bytes_per_env = lmz::V4::OBS_BYTES;
+    h->compact_bytes_per_env = 0;
+    build_blob_fov<lmz::V4>(blob);
     h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
   } else {
     h->G = lmz::V3::G; h->C = lmz::V3::C; h->S = lmz::V3::S; h->obs_bytes_per_env = lmz::V3::OBS_BYTES;
@@ -521,6 +538,10 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->goal_count, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->episode, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->blob, blob.size());
+  if (e == cudaSuccess && cfg->variant == LMZ_V4) {      // state[2], the float visit layer (lmaze_env_v4.py:106-113)
+    e = cudaMalloc(&h->visit, n * 324 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(h->visit, 0, n * 324 * sizeof(float));
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, (lmz::NUM_STATS + 3) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->goal_count, 0, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(h->episode, 0, n * sizeof(uint32_t));
@@ -533,7 +554,7 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     r.x = h->s_cell / h->G; r.y = h->s_cell % h->G; r.gx = h->x_cell / h->G; r.gy = h->x_cell % h->G;
     r.step = 0; r.rcode = lmz::RC_NEG_ZERO;
     uint32_t packed = (cfg->variant == LMZ_V0) ? lmz::V0::pack(r) : lmz::V3::pack(r);
-    if (cfg->variant == LMZ_V2) {          // maze 1, ball on 'S', goal on 'X', no previous action
+    if (foveal) {                          // maze 1, ball on 'S', goal on 'X', no previous action
       lmz::V2Regs v;
       v.L = 1; v.x = v.px = 4; v.y = v.py = 4; v.gx = 8; v.gy = 8; v.a = -1; v.step = 0;
       uint32_t aux;
@@ -563,7 +584,7 @@ int lmz_destroy(lmz_env *h) {
   if (!h) return LMZ_OK;
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->goal_count); cudaFree(h->episode); cudaFree(h->blob); cudaFree(h->stats);
-  cudaFree(h->act_stage);
+  cudaFree(h->act_stage); cudaFree(h->visit);
   delete h;
   return LMZ_OK;
 }
@@ -716,7 +737,8 @@ int lmz_rollout(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype
                 void *stream) {
   if (int rc = check_handle(h)) return rc;
   if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
-  if (h->cfg.variant == LMZ_V2) return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2 yet");
+  if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4)
+    return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2/v4 yet");
   if (!rewards || !dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
   if (actions && (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64))
     return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
@@ -754,7 +776,7 @@ static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {
   const int64_t n = h->cfg.num_envs;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (h->cfg.variant == LMZ_V2)
+  if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4)
     lmz::lmz_state_v2_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
   else if (h->cfg.variant == LMZ_V0)
     lmz::lmz_state_kernel<lmz::V0><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
@@ -779,6 +801,28 @@ static int state_xfer_dl(lmz_env *h, DLManagedTensor *t, int set, void *stream) 
 }
 int lmz_get_state_dl(lmz_env *h, DLManagedTensor *out, void *stream) { return state_xfer_dl(h, out, 0, stream); }
 int lmz_set_state_dl(lmz_env *h, DLManagedTensor *in, void *stream) { return state_xfer_dl(h, in, 1, stream); }
+
+static int visit_xfer(lmz_env *h, float *buf, int set, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V4) return fail(LMZ_ERR_UNSUPPORTED, "only lmaze-v4 has a visit layer");
+  if (!buf) return fail(LMZ_ERR_INVALID, "visit buffer is NULL");
+  DeviceGuard guard(h->cfg.device);
+  const size_t bytes = (size_t)h->cfg.num_envs * 324 * sizeof(float);
+  LMZ_CUDA(cudaMemcpyAsync(set ? (void *)h->visit : (void *)buf, set ? (const void *)buf : (const void *)h->visit, bytes,
+                           cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return LMZ_OK;
+}
+int lmz_get_visit(lmz_env *h, float *out, void *stream) { return visit_xfer(h, out, 0, stream); }
+int lmz_set_visit(lmz_env *h, const float *in, void *stream) { return visit_xfer(h, const_cast<float *>(in), 1, stream); }
+static int visit_xfer_dl(lmz_env *h, DLManagedTensor *t, int set, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  void *pt = nullptr;
+  Want w{"visit", kDLFloat, 32, 3, {h->cfg.num_envs, 18, 18, 0}, false, 4};
+  if (int rc = check_dl(h, t, w, &pt, nullptr)) return rc;
+  return visit_xfer(h, static_cast<float *>(pt), set, stream);
+}
+int lmz_get_visit_dl(lmz_env *h, DLManagedTensor *out, void *stream) { return visit_xfer_dl(h, out, 0, stream); }
+int lmz_set_visit_dl(lmz_env *h, DLManagedTensor *in, void *stream) { return visit_xfer_dl(h, in, 1, stream); }
 
 int lmz_stats(lmz_env *h, int64_t *out_host, int64_t *errors_host, void *stream) {
   if (int rc = check_handle(h)) return rc;

@@ -4,6 +4,7 @@ Host-side mirror of the reference classes for the hot path:
   variant "v0" <-> LmazeEnv     (reference gym_lmaze/envs/lmaze_env.py:11-256)
   variant "v3" <-> LmazeEnv_v3  (reference gym_lmaze/envs/lmaze_env_v3.py:17-402)
   variant "v2" <-> LmazeEnv_v2  (reference gym_lmaze/envs/lmaze_env_v2.py:17-405; Discrete(25), obs (5,35,35))
+  variant "v4" <-> LmazeEnv_v4  (reference gym_lmaze/envs/lmaze_env_v4.py:17-482; v2 + float visit layer, obs (7,35,35))
 
 Same method names and argument meaning -- `reset()` returns the observation,
 `step(action)` returns `(obs, reward, done, info)` (old-gym 4-tuple,
@@ -23,6 +24,7 @@ from ..spaces import make_spaces
 
 _VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
              "v2": _abi.LMZ_V2, 2: _abi.LMZ_V2, "lmaze-v2": _abi.LMZ_V2,
+             "v4": _abi.LMZ_V4, 4: _abi.LMZ_V4, "lmaze-v4": _abi.LMZ_V4,
              "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3}
 _RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128}
 _OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT}
@@ -49,7 +51,7 @@ class LmazeVecCuda(object):
                  env_id0=0, random_ball=True, random_goal=True, with_obs=True, tune=None, obs_mode="full",
                  obs_window=None):
         if variant not in _VARIANTS:
-            raise ValueError("unknown variant %r (built: v0, v2, v3)" % (variant,))
+            raise ValueError("unknown variant %r (built: v0, v2, v3, v4)" % (variant,))
         if render_mode not in _RENDER:
             raise ValueError("render_mode must be 'tma' or 'st128'")
         if obs_mode not in _OBS_MODE:
@@ -278,6 +280,18 @@ class LmazeVecCuda(object):
         state = torch.as_tensor(state).to(device=self.device, dtype=torch.int32).contiguous()
         p, k = _abi.dl(state)
         _abi.check(self._lib.lmz_set_state_dl(self._h, p, self._stream()))
+
+    def get_visit(self):
+        """v4: the float visit layer state[2] of every env, f32 [N, 18, 18]."""
+        out = torch.empty((self.num_envs, 18, 18), dtype=torch.float32, device=self.device)
+        p, k = _abi.dl(out)
+        _abi.check(self._lib.lmz_get_visit_dl(self._h, p, self._stream()))
+        return out
+
+    def set_visit(self, visit):
+        visit = torch.as_tensor(visit).to(device=self.device, dtype=torch.float32).contiguous()
+        p, k = _abi.dl(visit)
+        _abi.check(self._lib.lmz_set_visit_dl(self._h, p, self._stream()))
 
     def stats(self, check_errors=True):
         out = (ctypes.c_int64 * _abi.NUM_STATS)()

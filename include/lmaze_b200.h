@@ -49,7 +49,8 @@ typedef enum {
 typedef enum {
   LMZ_V0 = 0,   /* LmazeEnv     'lmaze-v0', 12x12, obs f32 (4,84,84)  -- lmaze_env.py:11-256    */
   LMZ_V2 = 2,   /* LmazeEnv_v2  'lmaze-v2', 5 mazes of 18x18, Discrete(25), obs f32 (5,35,35) -- lmaze_env_v2.py:17-405 */
-  LMZ_V3 = 3    /* LmazeEnv_v3  'lmaze-v3', 18x18, obs f32 (3,72,72)  -- lmaze_env_v3.py:17-402 */
+  LMZ_V3 = 3,   /* LmazeEnv_v3  'lmaze-v3', 18x18, obs f32 (3,72,72)  -- lmaze_env_v3.py:17-402 */
+  LMZ_V4 = 4    /* LmazeEnv_v4  'lmaze-v4', v2 + float visit layer, obs f32 (7,35,35) -- lmaze_env_v4.py:17-482 */
 } lmz_variant;
 
 /* How the fused kernel writes the observation tensor. */
@@ -193,6 +194,13 @@ int lmz_get_state(lmz_env *env, int32_t *out, void *stream);
 int lmz_set_state(lmz_env *env, const int32_t *in, void *stream);
 int lmz_get_state_dl(lmz_env *env, DLManagedTensor *out, void *stream);
 int lmz_set_state_dl(lmz_env *env, DLManagedTensor *in, void *stream);
+
+/* lmaze-v4 only: the float visit layer state[2] of every env (lmaze_env_v4.py:106-113,211-214),
+ * f32 [N][18][18] on the device -- part of the checkpoint next to lmz_get_state. */
+int lmz_get_visit(lmz_env *env, float *out, void *stream);
+int lmz_set_visit(lmz_env *env, const float *in, void *stream);
+int lmz_get_visit_dl(lmz_env *env, DLManagedTensor *out, void *stream);
+int lmz_set_visit_dl(lmz_env *env, DLManagedTensor *in, void *stream);
 
 /* Copies the device counters to out_host[LMZ_NUM_STATS] (synchronises `stream`).
  * *errors_host (may be NULL) receives the number of rejected injected spawns. */

@@ -651,3 +651,87 @@ def test_v2_windows_and_masks(lmz, oracle_mod):
     with pytest.raises(ValueError, match="3 "):
         env.stats()
     env.close()
+
+
+# ---------------------------------------------------------------- lmaze-v4 (v2 + float visit layer)
+def _v4_obs(bits, visit):
+    b = np.unpackbits(bits)[:125].reshape(5, 5, 5).astype(np.float32)
+    small = np.stack([b[0], b[1], visit[0], b[2], b[3], b[4], visit[1]])
+    return np.repeat(np.repeat(small, 7, 1), 7, 2)
+
+
+def test_v4_golden_table(lmz, golden_dir):
+    """Reference outputs incl. the float visit layer, compared as f32 BIT patterns."""
+    z = np.load(os.path.join(golden_dir, "v4_table.npz"))
+    tab = z["table"]
+    n = len(tab)
+    env = lmz.LmazeVecCuda(n, "v4", autoreset=False)
+    assert env.obs.shape[1:] == (7, 35, 35) and env.num_actions == 25
+    st = np.array([_v2_state_rows(r[0], r[1], r[2], r[3], r[4], r[1], r[2], r[6]) for r in tab], np.int32)
+    env.set_state(st)
+    env.set_visit(z["pre_visit"])
+    obs, rew, done, _ = env.step(torch.as_tensor(tab[:, 5]))
+    out = env.get_state().cpu().numpy()
+    assert np.array_equal(out[:, 0], tab[:, 7]) and np.array_equal(out[:, 1], tab[:, 8])
+    want_bits = np.array([np.float32(np.int64(b).view(np.float64)).view(np.uint32) for b in tab[:, 9]])
+    assert np.array_equal(rbits(rew), want_bits)
+    assert np.array_equal(done.cpu().numpy().astype(np.int64), tab[:, 10]) and np.array_equal(out[:, 4], tab[:, 11])
+    assert np.array_equal(env.get_visit().cpu().numpy().view(np.uint32), z["post_visit"].view(np.uint32))
+    want = np.stack([_v4_obs(z["obs_bits"][k], z["obs_visit"][k]) for k in range(n)])
+    assert np.array_equal(obs.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    env.close()
+
+
+def test_v4_golden_traces(lmz, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v4_traces.npz"))
+    ne = int(z["n_envs"])
+    env = lmz.LmazeVecCuda(ne, "v4", autoreset=True)
+    init = np.stack([z["e%d_init" % e] for e in range(ne)])        # bx, by, gx, gy, layout
+    obs = env.reset(spawn=init)
+    want = np.stack([_v4_obs(z["e%d_first_bits" % e], z["e%d_first_visit" % e]) for e in range(ne)])
+    assert np.array_equal(obs.cpu().numpy(), want)
+    T = len(z["e0_actions"])
+    for t in range(T):
+        acts = np.array([z["e%d_actions" % e][t] for e in range(ne)])
+        s5 = np.stack([z["e%d_spawn" % e][t] for e in range(ne)])
+        dref = np.array([z["e%d_done" % e][t] for e in range(ne)])
+        s5 = np.where(dref[:, None] > 0, s5, 0)
+        obs, rew, done, _ = env.step(torch.as_tensor(acts), spawn=s5)
+        want_r = np.array([np.float32(np.int64(z["e%d_reward_bits" % e][t]).view(np.float64)).view(np.uint32)
+                           for e in range(ne)])
+        assert np.array_equal(rbits(rew), want_r), t
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), dref), t
+        want_o = np.stack([_v4_obs(z["e%d_obs_bits" % e][t], z["e%d_obs_visit" % e][t]) for e in range(ne)])
+        assert np.array_equal(obs.cpu().numpy().view(np.uint32), want_o.view(np.uint32)), t
+    vis = env.get_visit().cpu().numpy()
+    for e in range(ne):
+        assert np.array_equal(vis[e].view(np.uint32), z["e%d_final_visit" % e].view(np.uint32))
+    env.close()
+
+
+def test_v4_4096_envs_vs_oracle(lmz, oracle_mod):
+    """Device-RNG resets, 130 steps, 4,099 envs (ragged last tile): reward bits, done, whole obs, visit layer."""
+    N, T, seed = 4099, 130, 13
+    ora = oracle_mod.OracleVec(oracle_mod.V4, N, seed=seed, env_id0=5, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, "v4", seed=seed, env_id0=5, autoreset=True)
+    assert torch.equal(env.reset().cpu(), torch.from_numpy(ora.reset()))
+    gen = torch.Generator().manual_seed(4)
+    obs_buf = np.empty((N, 7, 35, 35), np.float32)
+    for t in range(T):
+        a = torch.randint(0, 25, (N,), generator=gen)
+        _, r_ref, d_ref = ora.step(a.numpy(), obs_out=obs_buf)
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)), t
+        assert np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
+        assert torch.equal(obs.cpu().view(torch.int32), torch.from_numpy(obs_buf).view(torch.int32)), t
+        if t % 25 == 0:
+            assert np.array_equal(env.get_visit().cpu().numpy().view(np.uint32), ora.export_visit().view(np.uint32))
+    st = env.get_state().cpu().numpy()
+    pos, sc, _, _ = ora.export()
+    assert np.array_equal(st[:, 0:4], pos) and np.array_equal(st[:, 4], sc) and np.array_equal(st[:, 7], ora.episode)
+    s = env.stats()
+    assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist() and s["episodes"] >= 2 * N
+    # re-render and windowed render agree with the oracle as well
+    full = torch.from_numpy(np.stack([ora.render_one(i) for i in range(N)]))
+    assert torch.equal(env.render_obs().cpu(), full)
+    env.close()
