@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
-    ap.add_argument("--variant", default="v0", choices=["v0", "v2", "v3"])
+    ap.add_argument("--variant", default="v0", choices=["v0", "v2", "v3", "v4"])
     ap.add_argument("--render-mode", default="tma", choices=["tma", "st128"])
     ap.add_argument("--obs-mode", default="full", choices=["full", "compact"])
     ap.add_argument("--window", type=int, default=0,
@@ -128,12 +128,12 @@ def cpu_oracle_throughput(variant, n_envs, threads, budget_s, min_steps=2):
     """Steps/s of the C oracle port (full step + auto-reset + f32 render) on `threads` host threads."""
     import numpy as np
     from oracle import oracle as O
-    ov = {"v0": O.V0, "v2": O.V2, "v3": O.V3}[variant]
+    ov = {"v0": O.V0, "v2": O.V2, "v3": O.V3, "v4": O.V4}[variant]
     vec = O.OracleVec(ov, n_envs, seed=1, autoreset=True, threads=threads)
     obs = np.empty((n_envs,) + O.OBS_SHAPE[ov], dtype=np.float32)
     vec.reset(want_obs=False)
     rng = np.random.RandomState(1)
-    acts = rng.randint(0, 25 if variant == "v2" else 4, size=(8, n_envs)).astype(np.int64)
+    acts = rng.randint(0, 25 if variant in ("v2", "v4") else 4, size=(8, n_envs)).astype(np.int64)
     vec.step(acts[0], obs_out=obs)          # warm (touch pages)
     t0 = time.perf_counter()
     k = 0
@@ -167,12 +167,12 @@ def run_reference(args):
     O.build()
     threads = os.cpu_count() or 1
     sample_envs = 32768
-    ov = {"v0": O.V0, "v2": O.V2, "v3": O.V3}[args.variant]
+    ov = {"v0": O.V0, "v2": O.V2, "v3": O.V3, "v4": O.V4}[args.variant]
     import numpy as np
     vec = O.OracleVec(ov, sample_envs, seed=1, autoreset=True, threads=threads)
     obs = np.empty((sample_envs,) + O.OBS_SHAPE[ov], dtype=np.float32)
     vec.reset(want_obs=False)
-    acts = np.random.RandomState(1).randint(0, 25 if args.variant == "v2" else 4,
+    acts = np.random.RandomState(1).randint(0, 25 if args.variant in ("v2", "v4") else 4,
                                             size=(8, sample_envs)).astype(np.int64)
     for i in range(args.warmup):
         vec.step(acts[i % 8], obs_out=obs)
@@ -197,7 +197,7 @@ def run_reference(args):
 
 
 def workload_config(args, note=None):
-    G, E, C = {"v0": (12, 7, 4), "v3": (18, 4, 3), "v2": (5, 7, 5)}[args.variant]     # v2: 5x5 fovea crop
+    G, E, C = {"v0": (12, 7, 4), "v3": (18, 4, 3), "v2": (5, 7, 5), "v4": (5, 7, 7)}[args.variant]   # v2/v4: 5x5 fovea
     if args.obs_mode == "compact":
         obs, per_env = "u8 (%d,%d,%d) compact (un-expanded layers; reference image = x%d replication)" % (C, G, G, E), C * G * G
     else:
@@ -205,7 +205,8 @@ def workload_config(args, note=None):
     W = args.window if 0 < args.window < args.envs else args.envs
     which = ("BASELINE configs[2], HBM roofline run" if args.variant == "v0" and args.obs_mode == "full"
              else "BASELINE configs[3]-style: largest maze variant" if args.variant == "v3" and args.obs_mode == "full"
-             else "SURVEY 8f next #1: multi-layout foveal env" if args.variant == "v2" else "compact-observation mode")
+             else "SURVEY 8f next #1: multi-layout foveal env" if args.variant == "v2"
+             else "SURVEY 8f next #3: foveal env + float visit layer" if args.variant == "v4" else "compact-observation mode")
     cfg = {
         "workload": "lmaze_env_%s %d envs/GPU, fused step+auto-reset+obs render (%s)" % (args.variant, args.envs, which),
         "variant": args.variant, "envs_per_gpu": args.envs, "obs": obs, "actions": "u8 ring [4,N] resident in HBM",
@@ -243,7 +244,7 @@ def run_ours(args):
     if windows[-1] + W > N:
         windows[-1] = N - W
     obs_bytes = env.obs[0].numel() * env.obs.element_size()
-    step_bytes = obs_bytes + 14
+    step_bytes = obs_bytes + 14 + (2 * 324 * 4 if args.variant == "v4" else 0)   # v4: visit layer read + write
 
     def full_step(actions):
         """one step = transition of every env + every env's observation written once"""
@@ -347,7 +348,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.variant, args.render_mode)
                      if (args.obs_mode == "full" and W == N and N == 1 << 20) else None, "peak_source": peak_src,
-                     "kernel": "lmz_env_v2_kernel" if args.variant == "v2" else
+                     "kernel": "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4") else
                      "lmz_env_%s_kernel<%s>" % ("compact" if args.obs_mode == "compact" else
                                                 "tma" if args.render_mode == "tma" else "st", args.variant.upper()),
                      "launches_per_step": launches_per_step,
@@ -400,7 +401,7 @@ def side_measurements(env, args, torch, dev):
                                           "MEASURED_PEAKS hbm_gbs is a read+write copy, so a pure-write kernel "
                                           "can exceed it"}
     del scratch
-    if args.variant == "v2":
+    if args.variant in ("v2", "v4"):
         return out
     # (1) BASELINE configs[4]-style: T=64 fused rollout, device-side Philox actions, no per-step obs
     T = 64

@@ -276,9 +276,8 @@ int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   }
 }
 
-template <class W>
-int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  constexpr int THREADS = 512;
+template <class W, int THREADS>
+int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   auto kern = lmz::lmz_env_fov_kernel<W, THREADS>;
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
@@ -295,6 +294,13 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
+}
+
+template <class W>
+int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.tune[0] == 256) return launch_fov_t<W, 256>(h, p, s);
+  if (h->cfg.tune[0] == 128) return launch_fov_t<W, 128>(h, p, s);
+  return launch_fov_t<W, 512>(h, p, s);
 }
 
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {

@@ -253,20 +253,32 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
       const int64_t e0 = tile * 32;
       const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
       float *vis = p.visit + e0 * (W::G * W::G);
-      for (uint32_t idx = tid; idx < cells; idx += THREADS) {
-        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-        const int x = cell / W::G, y = cell - x * W::G;
-        const uint32_t info = s_info[buf][env];
-        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-        const uint32_t op = info >> 20;
-        const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-        const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-        float v = vis[idx];
-        if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
-        else if (op == 2) v = in_cur ? 0.5f : 0.0f;                   // fresh zeros, then the same update (:106-113)
-        if (op) vis[idx] = v;
-        if (in_cur) s_vis[env * 50 + dx * 5 + dy] = v;
-        if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) s_vis[env * 50 + 25 + qx * 5 + qy] = v;
+      constexpr uint32_t PER = (32 * W::G * W::G + THREADS - 1) / THREADS, UN = 8;
+      for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
+        float vv[UN];
+#pragma unroll
+        for (uint32_t j = 0; j < UN; ++j) {                            // UN independent loads in flight per thread
+          const uint32_t idx = tid + (k0 + j) * THREADS;
+          vv[j] = (idx < cells) ? __ldcs(vis + idx) : 0.0f;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < UN; ++j) {
+          const uint32_t idx = tid + (k0 + j) * THREADS;
+          if (idx >= cells) continue;
+          const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
+          const int x = cell / W::G, y = cell - x * W::G;
+          const uint32_t info = s_info[buf][env];
+          const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+          const uint32_t op = info >> 20;
+          const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
+          const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
+          float v = vv[j];
+          if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
+          else if (op == 2) v = in_cur ? 0.5f : 0.0f;                 // fresh zeros, then the same update (:106-113)
+          if (op) __stcs(vis + idx, v);
+          if (in_cur) s_vis[env * 50 + dx * 5 + dy] = v;
+          if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) s_vis[env * 50 + 25 + qx * 5 + qy] = v;
+        }
       }
       __syncthreads();
     }

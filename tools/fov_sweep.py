@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Threads-per-CTA sweep of the foveal kernel (v2 / v4) at scale (GPU box only)."""
+import os, sys, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import gym_lmaze_b200 as lmz
+for variant, N, nbytes in (("v4", 1 << 21, 36906), ("v2", 1 << 22, 24514)):
+    for thr in (128, 256, 512):
+        env = lmz.LmazeVecCuda(N, variant, seed=1, tune=(thr, 0, 0, 0))
+        env.reset()
+        a = torch.randint(0, 25, (4, N), device="cuda", dtype=torch.uint8)
+        for i in range(3):
+            env.step(a[i % 4])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(10):
+            env.step(a[i % 4])
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print("%s threads=%d: %.3f ms  %.1f M env-steps/s  %.0f GB/s" % (variant, thr, ms, N / ms / 1e3, N * nbytes / ms / 1e6), flush=True)
+        env.close(); del env
