@@ -298,8 +298,11 @@ int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 
 template <class W>
 int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (h->cfg.tune[0] == 256) return launch_fov_t<W, 256>(h, p, s);
-  if (h->cfg.tune[0] == 128) return launch_fov_t<W, 128>(h, p, s);
+  // CTA size (tools/fov_sweep.py): v2 renders best with one 1024-thread CTA per SM (7.2 TB/s); v4 wants two
+  // 512-thread CTAs per SM so that one CTA's producer warps overlap the other's render (5.9 TB/s)
+  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::NVIS > 0 ? 512 : 1024);
+  if (t == 256) return launch_fov_t<W, 256>(h, p, s);
+  if (t == 1024) return launch_fov_t<W, 1024>(h, p, s);
   return launch_fov_t<W, 512>(h, p, s);
 }
 
@@ -493,8 +496,8 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     return fail(LMZ_ERR_INVALID, "unknown obs_mode %d", cfg->obs_mode);
   {
     const int t = cfg->tune[0];
-    if (t != 0 && t != 32 && t != 64 && t != 128 && t != 256 && t != 512)
-      return fail(LMZ_ERR_INVALID, "tune[0] (threads per CTA) must be 0, 32, 64, 128, 256 or 512");
+    if (t != 0 && t != 32 && t != 64 && t != 128 && t != 256 && t != 512 && t != 1024)
+      return fail(LMZ_ERR_INVALID, "tune[0] (threads per CTA) must be 0, 32, 64, 128, 256, 512 or 1024");
     if (cfg->tune[1] < 0 || cfg->tune[1] > 4) return fail(LMZ_ERR_INVALID, "tune[1] (L2 policy) must be 0..4");
     if (cfg->tune[2] != 0) return fail(LMZ_ERR_INVALID, "tune[2] is reserved and must be 0");
     if (cfg->tune[3] < 0 || (cfg->tune[3] & 15)) return fail(LMZ_ERR_INVALID, "tune[3] (bulk split) must be a multiple of 16");

@@ -216,9 +216,16 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_mask[2][32 * W::NBIT];
   __shared__ uint32_t s_info[2][32];
-  __shared__ float s_vis[W::NVIS > 0 ? 32 * 50 : 1];     // [env][0: at the ball, 1: at the previous window][25]
+  __shared__ float s_vis[W::NVIS > 0 ? 2 * 32 * 50 : 1];   // [buf][env][0: at the ball, 1: at the previous window][25]
   __shared__ uint32_t s_flags[2];            // bit l: env l of the tile is to be rendered
   __shared__ long long s_tile[2];
+  // v2: warp 0 produces (transitions) and then renders with everybody else.
+  // v4: warps 0-3 are PRODUCERS -- warp 0 runs the next tile's transitions, then all four update that
+  //     tile's float visit layers -- while the remaining warps render the current tile, so the visit
+  //     pass (global read-modify-write latency) is hidden behind the obs stores.
+  constexpr int PROD = (W::NVIS > 0) ? (THREADS >= 512 ? 128 : 64) : 0;   // threads that never render
+  constexpr int CTHREADS = THREADS - PROD;
+  static_assert(CTHREADS >= 32, "need at least one rendering warp");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   stage_blob<W>(smem, &bar, p.blob);
   const FovTables<W> t(smem);
@@ -243,78 +250,90 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     const unsigned fl = __ballot_sync(0xffffffffu, valid && v.o.render);
     if (lane == 0) { s_flags[buf] = fl; s_tile[buf] = tl; }
   };
+  // v4 visit layers of one tile's 32 envs: 32 x 324 consecutive floats, coalesced read-modify-write by
+  // the PROD producer threads: state[2] = (state[2] + visitMap) / 2 in float64 (lmaze_env_v4.py:211-214)
+  auto visit_pass = [&](int buf) {
+    const int64_t tile = s_tile[buf];
+    if (tile >= tiles) return;
+    const int64_t e0 = tile * 32;
+    const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
+    float *vis = p.visit + e0 * (W::G * W::G);
+    float *sv = s_vis + buf * (32 * 50);
+    constexpr uint32_t NP = PROD > 0 ? PROD : 1, PER = (32 * W::G * W::G + NP - 1) / NP, UN = 8;
+    for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
+      float vv[UN];
+#pragma unroll
+      for (uint32_t j = 0; j < UN; ++j) {                            // UN independent loads in flight per thread
+        const uint32_t idx = tid + (k0 + j) * NP;
+        vv[j] = (idx < cells) ? __ldcs(vis + idx) : 0.0f;
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < UN; ++j) {
+        const uint32_t idx = tid + (k0 + j) * NP;
+        if (idx >= cells) continue;
+        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
+        const int x = cell / W::G, y = cell - x * W::G;
+        const uint32_t info = s_info[buf][env];
+        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+        const uint32_t op = info >> 20;
+        const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
+        const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
+        float v = vv[j];
+        if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
+        else if (op == 2) v = in_cur ? 0.5f : 0.0f;                 // fresh zeros, then the same update (:106-113)
+        if (op) __stcs(vis + idx, v);
+        if (in_cur) sv[env * 50 + dx * 5 + dy] = v;
+        if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) sv[env * 50 + 25 + qx * 5 + qy] = v;
+      }
+    }
+  };
+  auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };
+
   if (warp == 0) produce(0);
+  if (W::NVIS > 0 && tid < PROD) { producers_sync(); visit_pass(0); }
   for (int buf = 0;; buf ^= 1) {
-    __syncthreads();
+    __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
     const int64_t tile = s_tile[buf];
     if (tile >= tiles) break;
-    if (W::NVIS > 0) {
-      // ---- v4 visit layers of the tile's 32 envs: 32 x 324 consecutive floats, coalesced read-modify-write
-      const int64_t e0 = tile * 32;
-      const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
-      float *vis = p.visit + e0 * (W::G * W::G);
-      constexpr uint32_t PER = (32 * W::G * W::G + THREADS - 1) / THREADS, UN = 8;
-      for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
-        float vv[UN];
-#pragma unroll
-        for (uint32_t j = 0; j < UN; ++j) {                            // UN independent loads in flight per thread
-          const uint32_t idx = tid + (k0 + j) * THREADS;
-          vv[j] = (idx < cells) ? __ldcs(vis + idx) : 0.0f;
-        }
-#pragma unroll
-        for (uint32_t j = 0; j < UN; ++j) {
-          const uint32_t idx = tid + (k0 + j) * THREADS;
-          if (idx >= cells) continue;
-          const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-          const int x = cell / W::G, y = cell - x * W::G;
-          const uint32_t info = s_info[buf][env];
-          const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-          const uint32_t op = info >> 20;
-          const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-          const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-          float v = vv[j];
-          if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
-          else if (op == 2) v = in_cur ? 0.5f : 0.0f;                 // fresh zeros, then the same update (:106-113)
-          if (op) __stcs(vis + idx, v);
-          if (in_cur) s_vis[env * 50 + dx * 5 + dy] = v;
-          if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) s_vis[env * 50 + 25 + qx * 5 + qy] = v;
-        }
-      }
-      __syncthreads();
+    if (W::NVIS > 0 && tid < PROD) {
+      if (warp == 0) produce(buf ^ 1);
+      producers_sync();
+      visit_pass(buf ^ 1);
+      continue;
     }
-    if (warp == 0) produce(buf ^ 1);
+    if (W::NVIS == 0 && warp == 0) produce(buf ^ 1);
     const uint32_t flags = s_flags[buf];
-    if (flags != 0) {
-      const uint32_t *mk = s_mask[buf];
-      const int64_t row0 = tile * 32 - p.win_lo;                     // obs row of the tile's first env
-      float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)W::OBS_FLOATS;
-      auto value = [&](uint32_t env, uint32_t r) -> uint32_t {       // float bits of obs[env][r]
-        const uint32_t code = t.lut[r], slot = code >> 5, cell = code & 31u;
-        if (W::NVIS > 0 && slot >= (uint32_t)W::NBIT) return __float_as_uint(s_vis[env * 50 + (slot - W::NBIT) * 25 + cell]);
-        return ((mk[env * W::NBIT + slot] >> cell) & 1u) ? 0x3f800000u : 0u;
-      };
-      if (flags == 0xffffffffu && (row0 & 3) == 0) {
-        // fast path: the whole tile is rendered and 16-byte aligned -> TILE_F4 float4 stores
-        for (uint32_t q = tid; q < W::TILE_F4; q += THREADS) {
-          uint32_t g = q * 4, env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
-          uint4 v;
-          uint32_t *w = reinterpret_cast<uint32_t *>(&v);
+    if (flags == 0) continue;
+    const int ctid = tid - PROD;
+    const uint32_t *mk = s_mask[buf];
+    const float *sv = s_vis + (W::NVIS > 0 ? buf * (32 * 50) : 0);
+    const int64_t row0 = tile * 32 - p.win_lo;                     // obs row of the tile's first env
+    float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)W::OBS_FLOATS;
+    auto value = [&](uint32_t env, uint32_t r) -> uint32_t {       // float bits of obs[env][r]
+      const uint32_t code = t.lut[r], slot = code >> 5, cell = code & 31u;
+      if (W::NVIS > 0 && slot >= (uint32_t)W::NBIT) return __float_as_uint(sv[env * 50 + (slot - W::NBIT) * 25 + cell]);
+      return ((mk[env * W::NBIT + slot] >> cell) & 1u) ? 0x3f800000u : 0u;
+    };
+    if (flags == 0xffffffffu && (row0 & 3) == 0) {
+      // fast path: the whole tile is rendered and 16-byte aligned -> TILE_F4 float4 stores
+      for (uint32_t q = ctid; q < W::TILE_F4; q += CTHREADS) {
+        uint32_t g = q * 4, env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
+        uint4 v;
+        uint32_t *w = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            w[k] = value(env, r);
-            if (++r == W::OBS_FLOATS) { r = 0; ++env; }
-          }
-          st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), v);
+        for (int k = 0; k < 4; ++k) {
+          w[k] = value(env, r);
+          if (++r == W::OBS_FLOATS) { r = 0; ++env; }
         }
-      } else {
-        // partial tile (batch tail, reset mask, render-window edge): guarded 32-bit stores
-        for (uint32_t g = tid; g < 32 * W::OBS_FLOATS; g += THREADS) {
-          const uint32_t env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
-          if ((flags >> env) & 1u) __stcs(reinterpret_cast<unsigned int *>(dst) + g, value(env, r));
-        }
+        st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), v);
+      }
+    } else {
+      // partial tile (batch tail, reset mask, render-window edge): guarded 32-bit stores
+      for (uint32_t g = ctid; g < 32 * W::OBS_FLOATS; g += CTHREADS) {
+        const uint32_t env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
+        if ((flags >> env) & 1u) __stcs(reinterpret_cast<unsigned int *>(dst) + g, value(env, r));
       }
     }
-    if (W::NVIS > 0) __syncthreads();        // s_vis is single-buffered: finish reading before the next tile's pass
   }
   if (warp == 0) {
     if (p.mode == MODE_STEP) ws.flush(p.stats, lane);

@@ -4,7 +4,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import gym_lmaze_b200 as lmz
 for variant, N, nbytes in (("v4", 1 << 21, 36906), ("v2", 1 << 22, 24514)):
-    for thr in (128, 256, 512):
+    for thr in (256, 512, 1024):
         env = lmz.LmazeVecCuda(N, variant, seed=1, tune=(thr, 0, 0, 0))
         env.reset()
         a = torch.randint(0, 25, (4, N), device="cuda", dtype=torch.uint8)
