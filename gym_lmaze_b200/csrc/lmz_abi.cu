@@ -247,14 +247,24 @@ int launch_env_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return LMZ_OK;
 }
 
-// transition-only (no obs bound) and compact-obs launches: small hardware-scheduled CTAs
+// transition-only (no obs bound) and compact-obs launches: persistent 128-thread CTAs, dynamic tiles
 template <class V>
 int launch_compact(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   constexpr int THREADS = 128;
+  auto kern = lmz::lmz_env_compact_kernel<V, THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, 0));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "compact env kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
   const int64_t units = p.tile_end - p.tile_begin;
-  const int64_t grid = (units + THREADS / 32 - 1) / (THREADS / 32);
-  if (grid < 1) return LMZ_OK;
-  lmz::lmz_env_compact_kernel<V, THREADS><<<(unsigned)grid, THREADS, 0, s>>>(p);
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, 0, s>>>(p);
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;

@@ -518,42 +518,69 @@ __global__ void __launch_bounds__(THREADS, 1) lmz_env_st_kernel(const KParams p)
 // `state` layers before its xE upsample (lmaze_env.py:208-215) -- 576 B (v0) / 972 B (v3) per env
 // instead of 112,896 / 62,208.  The reference image is exactly repeat_interleave(compact, E) on both
 // axes.  Small CTAs (hardware-scheduled), one warp per 32-env tile, one thread per env for the
-// transition; the tile's compact rows are then stored as consecutive 32-bit words, lanes on
-// consecutive words (coalesced 128 B per warp store).
+// transition; the tile's compact rows are then stored row by row as 32-bit words, lanes on
+// consecutive words (coalesced 128 B per warp store), static words held in registers.
 template <class V, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams p) {
   __shared__ __align__(16) unsigned char tab[V::TABLES_BYTES];
   constexpr int WARPS = THREADS / 32;
   constexpr uint32_t W = V::COMPACT_BYTES / 4;           // 32-bit words per env (v0 144, v3 243)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int K = (W + 31) / 32;
+  const int lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < V::TABLES_BYTES / 4; i += THREADS)
     reinterpret_cast<uint32_t *>(tab)[i] = reinterpret_cast<const uint32_t *>(p.blob + V::TABLES_OFF)[i];
   __syncthreads();
   const uint8_t *cls = tab;
   const uint16_t *cand = reinterpret_cast<const uint16_t *>(tab + (V::CAND_OFF - V::TABLES_OFF));
   const uint32_t *tmpl = reinterpret_cast<const uint32_t *>(tab + (V::COMPACT_OFF - V::TABLES_OFF));
-  WarpStats ws;
-  const int64_t tile = p.tile_begin + (int64_t)blockIdx.x * WARPS + warp;
-  bool valid;
-  const LaneOut o = tile_lane<V>(p, tile, lane, p.tile_end, cls, cand, valid);
-  if (p.mode == MODE_STEP) ws.add(valid, o);
-  const unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render);
-  if (rmask) {
-    uint32_t hot[V::NHOT];
-    V::hot_bytes(V::unpack(o.st), hot);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(p.obs) + (size_t)(tile * 32 - p.win_lo) * W;
-    for (uint32_t f = lane; f < 32 * W; f += 32) {
-      const uint32_t env = f / W, w = f - env * W;       // which env of the tile, which word of its row
-      uint32_t v = tmpl[w];
+  // Lane l owns words l, l+32, l+64, ... of EVERY env row: the static layer words live in registers,
+  // and per env the only per-word work is "does this word hold the env's hot byte?" + one store.
+  uint32_t base[K];
 #pragma unroll
-      for (int q = 0; q < V::NHOT; ++q) {
-        const uint32_t h = __shfl_sync(0xffffffffu, hot[q], env);
-        if ((h >> 2) == w) v |= 1u << (8 * (h & 3));
+  for (int k = 0; k < K; ++k) base[k] = (lane + 32 * k < (int)W) ? tmpl[lane + 32 * k] : 0u;
+  const int64_t tiles = p.tile_end;
+  WarpStats ws;
+  // persistent warps, tiles handed out dynamically; software pipelined like the TMA kernel: the next
+  // tile's loads / transitions are issued before the current tile's rows are stored
+  auto next_tile = [&]() {
+    int64_t t = 0;
+    if (lane == 0) t = p.tile_begin + grab_tile(p.work);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  int64_t tile = next_tile();
+  bool valid;
+  LaneOut o = tile_lane<V>(p, tile, lane, tiles, cls, cand, valid);
+  if (p.mode == MODE_STEP) ws.add(valid, o);
+  while (tile < tiles) {
+    const int64_t ntile = next_tile();
+    bool nvalid;
+    const LaneOut no = tile_lane<V>(p, ntile, lane, tiles, cls, cand, nvalid);
+    if (p.mode == MODE_STEP) ws.add(nvalid, no);
+    const unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render);
+    if (rmask) {
+      uint32_t hot[V::NHOT];
+      V::hot_bytes(V::unpack(o.st), hot);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(p.obs) + (size_t)(tile * 32 - p.win_lo) * W;
+      for (unsigned m = rmask; m; m &= m - 1) {
+        const int env = __ffs(m) - 1;
+        uint32_t h[V::NHOT];
+#pragma unroll
+        for (int q = 0; q < V::NHOT; ++q) h[q] = __shfl_sync(0xffffffffu, hot[q], env);
+        uint32_t *row = dst + (size_t)env * W;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const uint32_t w = lane + 32 * k;
+          uint32_t v = base[k];
+#pragma unroll
+          for (int q = 0; q < V::NHOT; ++q) v |= ((h[q] >> 2) == w) ? (1u << (8 * (h[q] & 3))) : 0u;
+          if (w < W) __stcs(row + w, v);
+        }
       }
-      if ((rmask >> env) & 1u) __stcs(dst + f, v);
     }
+    tile = ntile; o = no; valid = nvalid;
   }
   if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+  if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
 }
 
 // ------------------------------------------------------------------ T-step rollout, no per-step obs

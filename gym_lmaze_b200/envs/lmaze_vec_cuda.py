@@ -214,6 +214,26 @@ class LmazeVecCuda(object):
         _abi.check(self._lib.lmz_step_dl(self._h, pa, ps, self._stream()))
         return self.obs, self.reward, self.done, {"action": actions}
 
+    def capture_step(self, actions_buf, spawn_buf=None):
+        """Capture one fused step into a CUDA graph and return `replay()`.
+
+        `actions_buf` (and `spawn_buf`) are static device tensors: write the next actions into
+        them (e.g. `actions_buf.copy_(a)`) and call `replay()`; obs / reward / done are the env's
+        bound tensors.  For small batches the step is launch-bound (a 4,096-env step is ~65 us of
+        GPU work), and a graph replay skips the Python + ctypes + validation cost.  The kernels
+        re-arm their own work counters, so a captured launch replays correctly any number of times.
+        """
+        actions_buf = self._as_actions(actions_buf)
+        spawn_buf = self._as_spawn(spawn_buf)
+        if self.obs is not None:
+            self.render_obs()            # warm the launch path (function attributes) without changing state
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(actions_buf, spawn=spawn_buf)
+        self._graphs = getattr(self, "_graphs", []) + [(graph, actions_buf, spawn_buf)]
+        return graph.replay
+
     def step_host(self, actions_host, reward_host, done_host, obs_host=None):
         """End-to-end step with HOST buffers (pinned CPU tensors): H2D actions, fused
         step, D2H reward/done (and obs if given), stream synchronised on return."""

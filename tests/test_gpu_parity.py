@@ -735,3 +735,30 @@ def test_v4_4096_envs_vs_oracle(lmz, oracle_mod):
     full = torch.from_numpy(np.stack([ora.render_one(i) for i in range(N)]))
     assert torch.equal(env.render_obs().cpu(), full)
     env.close()
+
+
+# ---------------------------------------------------------------- CUDA graph replay of the fused step
+@pytest.mark.parametrize("variant,render_mode", [("v0", "tma"), ("v0", "st128"), ("v2", "tma")])
+def test_cuda_graph_replay(lmz, oracle_mod, variant, render_mode):
+    """One captured launch replayed 150 times (the work counter re-arms itself) == 150 oracle steps."""
+    N = 4096
+    ov = {"v0": oracle_mod.V0, "v2": oracle_mod.V2}[variant]
+    ora = oracle_mod.OracleVec(ov, N, seed=6, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, variant, seed=6, autoreset=True, render_mode=render_mode)
+    ora.reset(want_obs=False); env.reset()
+    abuf = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    replay = env.capture_step(abuf)
+    launches = env.launch_count
+    gen = torch.Generator().manual_seed(12)
+    for t in range(150):
+        a = torch.randint(0, env.num_actions, (N,), generator=gen)
+        abuf.copy_(a.to(torch.uint8))
+        replay()
+        o_ref, r_ref, d_ref = ora.step(a.numpy(), want_obs=(t % 30 == 0))
+        assert np.array_equal(rbits(env.reward), r_ref.view(np.uint32)), t
+        assert np.array_equal(env.done.cpu().numpy().view(np.uint8), d_ref), t
+        if t % 30 == 0:
+            assert torch.equal(env.obs.cpu(), torch.from_numpy(o_ref)), t
+    assert env.launch_count == launches          # no host-side launches happened during the replays
+    assert env.stats()["steps"] == 150 * N       # capturing does not execute; the warm-up is a render, not a step
+    env.close()
