@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--variant", default="v0", choices=["v0", "v2", "v3", "v4"])
-    ap.add_argument("--render-mode", default="tma", choices=["tma", "st128"])
+    ap.add_argument("--render-mode", default="tma", choices=["tma", "st128", "incremental"])
     ap.add_argument("--obs-mode", default="full", choices=["full", "compact"])
     ap.add_argument("--window", type=int, default=0,
                     help="obs rows kept in HBM (render window); 0 = all envs.  A step then = fused step over "
@@ -245,6 +245,10 @@ def run_ours(args):
         windows[-1] = N - W
     obs_bytes = env.obs[0].numel() * env.obs.element_size()
     step_bytes = obs_bytes + 14 + (2 * 324 * 4 if args.variant == "v4" else 0)   # v4: visit layer read + write
+    if args.render_mode == "incremental":
+        # persistent obs tensor: at most the old and the new ExE ball block are rewritten (upper bound)
+        E = 7 if args.variant == "v0" else 4
+        step_bytes = 2 * E * E * 4 + 14
 
     def full_step(actions):
         """one step = transition of every env + every env's observation written once"""
@@ -328,6 +332,12 @@ def run_ours(args):
         extras = side_measurements(env, args, torch, dev)
 
     stats = env.stats_allreduce() if world > 1 else env.stats()
+    if extras and args.variant in ("v0", "v3") and args.obs_mode == "full" and args.render_mode != "incremental":
+        # (3) same workload, obs tensor kept PERSISTENT and patched in place (needs the 118 GB back first)
+        env.close()
+        del env
+        torch.cuda.empty_cache()
+        extras["incremental_render"] = incremental_measurement(args, torch, dev, N, ring)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -349,6 +359,7 @@ def run_ours(args):
                      "traffic": recorded_traffic(args.variant, args.render_mode)
                      if (args.obs_mode == "full" and W == N and N == 1 << 20) else None, "peak_source": peak_src,
                      "kernel": "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4") else
+                     "lmz_env_incr_kernel<%s>" % args.variant.upper() if args.render_mode == "incremental" else
                      "lmz_env_%s_kernel<%s>" % ("compact" if args.obs_mode == "compact" else
                                                 "tma" if args.render_mode == "tma" else "st", args.variant.upper()),
                      "launches_per_step": launches_per_step,
@@ -380,6 +391,35 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def incremental_measurement(args, torch, dev, N, ring):
+    """render_mode='incremental': full f32 obs tensor, bit-identical to a re-render after every step, but a
+    step only rewrites the ball's old and new ExE block (its own bytes figure; not the headline)."""
+    import gym_lmaze_b200 as lmz
+    try:
+        env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, autoreset=True, render_mode="incremental")
+        env.reset()
+        for i in range(5):
+            env.step(ring[i % ring.shape[0]])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        e0.record()
+        for i in range(reps):
+            env.step(ring[i % ring.shape[0]])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        E = 7 if args.variant == "v0" else 4
+        out = {"value": N / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "envs": N,
+               "bytes_per_env_step": 2 * E * E * 4 + 14,
+               "mode": "lmz_env_incr_kernel: persistent f32 obs tensor patched in place (old block erased, new block "
+                       "drawn); tensor content identical to the full render after every step"}
+        env.close()
+        return out
+    except Exception as exc:  # pragma: no cover
+        return {"error": repr(exc)}
 
 
 def side_measurements(env, args, torch, dev):

@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblmaze_b200.so")
 
 LMZ_V0, LMZ_V2, LMZ_V3, LMZ_V4 = 0, 2, 3, 4
-RENDER_TMA, RENDER_ST128 = 0, 1
+RENDER_TMA, RENDER_ST128, RENDER_INCREMENTAL = 0, 1, 2
 OBS_FULL, OBS_COMPACT = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 NUM_STATS = 8

@@ -185,6 +185,7 @@ struct lmz_env {
   bool bound;
   int64_t win_lo, win_n;         // obs rows hold envs [win_lo, win_lo + win_n)
   size_t compact_bytes_per_env;
+  bool obs_synced;               // incremental render: obs currently holds a full render of the window
   int n_cand, s_cell, x_cell;
   uint64_t rollout_t;            // rollout steps taken so far (keys the action RNG)
   int64_t launches;
@@ -270,9 +271,40 @@ int launch_compact(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return LMZ_OK;
 }
 
+// incremental render (LMZ_RENDER_INCREMENTAL): only the ball / goal blocks that moved are rewritten
+template <class V>
+int launch_incremental(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  constexpr int THREADS = 128;
+  auto kern = lmz::lmz_env_incr_kernel<V, THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, 0));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "incremental env kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  const int64_t units = p.tile_end - p.tile_begin;
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, 0, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
 template <class V>
 int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (p.obs == nullptr || h->cfg.obs_mode == LMZ_OBS_COMPACT) return launch_compact<V>(h, p, s);
+  if (h->cfg.render_mode == LMZ_RENDER_INCREMENTAL) {
+    if (p.mode == lmz::MODE_STEP && h->obs_synced) return launch_incremental<V>(h, p, s);
+    // not in sync yet (first call after bind / set_window / set_state), or a reset / render call:
+    // full TMA render.  A call that renders every env of the window leaves the tensor in sync.
+    const int rc = launch_env_t<V, lmz::RENDER_TMA, TMA_THREADS>(h, p, s);
+    if (rc == LMZ_OK && (p.mode != lmz::MODE_RESET || p.mask == nullptr)) h->obs_synced = true;
+    return rc;
+  }
   if (h->cfg.render_mode == LMZ_RENDER_ST128) {
     if (h->cfg.tune[0] == 512) return launch_env_t<V, lmz::RENDER_ST128, 512>(h, p, s);
     if (h->cfg.tune[0] == 256) return launch_env_t<V, lmz::RENDER_ST128, 256>(h, p, s);
@@ -498,8 +530,11 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2/v4 have no compact observation mode yet");
   if (cfg->num_envs < 1) return fail(LMZ_ERR_INVALID, "num_envs must be >= 1 (got %lld)", (long long)cfg->num_envs);
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
-  if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128)
+  if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128 &&
+      cfg->render_mode != LMZ_RENDER_INCREMENTAL)
     return fail(LMZ_ERR_INVALID, "unknown render_mode %d", cfg->render_mode);
+  if (cfg->render_mode == LMZ_RENDER_INCREMENTAL && (cfg->variant == LMZ_V2 || cfg->variant == LMZ_V4))
+    return fail(LMZ_ERR_UNSUPPORTED, "incremental render needs a full-view variant (v0, v3): a foveal crop changes entirely every step");
   for (int i = 0; i < 2; ++i)
     if (cfg->reserved[i] != 0) return fail(LMZ_ERR_INVALID, "lmz_config.reserved must be zero");
   if (cfg->obs_mode != LMZ_OBS_FULL && cfg->obs_mode != LMZ_OBS_COMPACT)
@@ -615,6 +650,7 @@ int lmz_bind(lmz_env *h, void *obs, float *reward, uint8_t *done) {
   if ((reinterpret_cast<uintptr_t>(reward) & 3u) != 0) return fail(LMZ_ERR_INVALID, "reward must be 4-byte aligned");
   h->obs = obs; h->reward = reward; h->done = done; h->bound = true;
   h->win_lo = 0; h->win_n = h->cfg.num_envs;
+  h->obs_synced = false;
   return LMZ_OK;
 }
 
@@ -649,6 +685,7 @@ int lmz_set_window(lmz_env *h, void *obs, int64_t env_lo, int64_t env_count) {
     return fail(LMZ_ERR_INVALID, "window [%lld, %lld) outside [0, %lld)", (long long)env_lo,
                 (long long)(env_lo + env_count), (long long)h->cfg.num_envs);
   h->obs = obs; h->win_lo = env_lo; h->win_n = env_count;
+  h->obs_synced = false;
   return LMZ_OK;
 }
 
@@ -808,6 +845,7 @@ static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {
 
 int lmz_get_state(lmz_env *h, int32_t *out, void *stream) { return state_xfer(h, out, 0, stream); }
 int lmz_set_state(lmz_env *h, const int32_t *in, void *stream) {
+  if (h) h->obs_synced = false;            // positions change behind the obs tensor's back
   return state_xfer(h, const_cast<int32_t *>(in), 1, stream);
 }
 
@@ -819,7 +857,10 @@ static int state_xfer_dl(lmz_env *h, DLManagedTensor *t, int set, void *stream) 
   return state_xfer(h, static_cast<int32_t *>(pt), set, stream);
 }
 int lmz_get_state_dl(lmz_env *h, DLManagedTensor *out, void *stream) { return state_xfer_dl(h, out, 0, stream); }
-int lmz_set_state_dl(lmz_env *h, DLManagedTensor *in, void *stream) { return state_xfer_dl(h, in, 1, stream); }
+int lmz_set_state_dl(lmz_env *h, DLManagedTensor *in, void *stream) {
+  if (h) h->obs_synced = false;
+  return state_xfer_dl(h, in, 1, stream);
+}
 
 static int visit_xfer(lmz_env *h, float *buf, int set, void *stream) {
   if (int rc = check_handle(h)) return rc;

@@ -23,7 +23,7 @@ namespace lmz {
 
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
 enum : int { ACT_U8 = 0, ACT_I32 = 1, ACT_I64 = 2 };
-enum : int { RENDER_TMA = 0, RENDER_ST128 = 1 };
+enum : int { RENDER_TMA = 0, RENDER_ST128 = 1, RENDER_INCREMENTAL = 2 };
 enum : int { OBS_FULL = 0, OBS_COMPACT = 1 };
 enum : int {
   STAT_STEPS = 0, STAT_EPISODES, STAT_GOALS, STAT_TIMEOUTS, STAT_WALL_BUMPS, STAT_MOVES, STAT_STALE,
@@ -265,6 +265,7 @@ __device__ __forceinline__ void respawn(EnvRegs &r, const KParams &p, int64_t e,
 // Everything one env does in a fused call except writing its observation.
 struct LaneOut {
   uint32_t st;        // packed state after the call
+  uint32_t st_old;    // packed state before the call (the incremental render erases its blocks)
   bool render;        // obs row must be (re)written
   bool done;
   int cls;            // branch taken by the transition (-1: no step)
@@ -275,7 +276,8 @@ template <class V>
 __device__ __forceinline__ LaneOut env_lane(const KParams &p, int64_t e, const uint8_t *cls, const uint16_t *cand) {
   LaneOut o;
   o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
-  EnvRegs r = V::unpack(p.state[e]);
+  o.st_old = p.state[e];
+  EnvRegs r = V::unpack(o.st_old);
   bool reset_now = false;
   if (p.mode == MODE_STEP) {
     const long long a = load_action(p.actions, p.action_dtype, e);
@@ -367,7 +369,7 @@ template <class V>
 __device__ __forceinline__ LaneOut tile_lane(const KParams &p, int64_t tile, int lane, int64_t tiles,
                                              const uint8_t *cls, const uint16_t *cand, bool &valid) {
   LaneOut o;
-  o.st = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
+  o.st = 0; o.st_old = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
   const int64_t e = tile * 32 + lane;
   valid = tile < tiles && e < p.n;
   if (valid) {
@@ -580,6 +582,94 @@ __global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams 
     tile = ntile; o = no; valid = nvalid;
   }
   if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+  if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
+}
+
+// ---- render path 4: incremental patches into a persistent observation ---------------------------
+// LMZ_RENDER_INCREMENTAL.  The bound obs tensor persists between calls, and a step changes at most
+// the ball's ExE block (v3: also the goal block, on a reset): walls / goal / blank channels never
+// change (lmaze_env.py:92-107), and ch0 is one block of ones on a zero plane.  So once the tensor
+// holds a full render, a step only has to erase the old block and draw the new one -- 2*E*E floats
+// (392 B for v0) instead of 112,896 B, with the tensor bit-identical to a full re-render afterwards.
+// The host only selects this kernel for MODE_STEP and only while the tensor is known to be in sync
+// (after a full reset / render through the same handle); otherwise it falls back to the full render.
+// One thread per env for the transition; then, env by env, the warp writes the <= 49 elements of
+// each block cooperatively (lanes on consecutive floats of the block's rows).
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) {
+  __shared__ __align__(16) unsigned char tab[V::TABLES_BYTES];
+  constexpr int WARPS = THREADS / 32;
+  constexpr int NBLK = (V::ID == 0) ? 1 : 2;                // v0: ball in ch0; v3: ball in ch1, goal in ch2
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < V::TABLES_BYTES / 4; i += THREADS)
+    reinterpret_cast<uint32_t *>(tab)[i] = reinterpret_cast<const uint32_t *>(p.blob + V::TABLES_OFF)[i];
+  __syncthreads();
+  const uint8_t *cls = tab;
+  const uint16_t *cand = reinterpret_cast<const uint16_t *>(tab + (V::CAND_OFF - V::TABLES_OFF));
+  const int64_t tiles = p.tile_end;
+  WarpStats ws;
+  auto next_tile = [&]() {
+    int64_t t = 0;
+    if (lane == 0) t = p.tile_begin + grab_tile(p.work);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  // block b of a packed state: channel and top-left element
+  auto block_of = [](uint32_t st, int b, int &ch, int &row, int &col) {
+    const EnvRegs r = V::unpack(st);
+    if (V::ID == 0) { ch = 0; row = r.x * V::E; col = r.y * V::E; }
+    else if (b == 0) { ch = 1; row = r.x * V::E; col = r.y * V::E; }
+    else { ch = 2; row = r.gx * V::E; col = r.gy * V::E; }
+  };
+  int64_t tile = next_tile();
+  bool valid;
+  LaneOut o = tile_lane<V>(p, tile, lane, tiles, cls, cand, valid);
+  ws.add(valid, o);
+  while (tile < tiles) {
+    const int64_t ntile = next_tile();
+    bool nvalid;
+    const LaneOut no = tile_lane<V>(p, ntile, lane, tiles, cls, cand, nvalid);
+    ws.add(nvalid, no);
+    // which envs of the tile have a block that moved?
+    bool moved = false;
+    if (valid && o.render) {
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        int c0, r0, q0, c1, r1, q1;
+        block_of(o.st_old, b, c0, r0, q0); block_of(o.st, b, c1, r1, q1);
+        moved = moved || r0 != r1 || q0 != q1;
+      }
+    }
+    for (unsigned m = __ballot_sync(0xffffffffu, moved); m; m &= m - 1) {
+      const int l = __ffs(m) - 1;
+      const uint32_t so = __shfl_sync(0xffffffffu, o.st_old, l), sn = __shfl_sync(0xffffffffu, o.st, l);
+      float *img = reinterpret_cast<float *>(p.obs) + (size_t)(tile * 32 + l - p.win_lo) * (V::OBS_BYTES / 4);
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        int ch, r0, q0, r1, q1;
+        block_of(so, b, ch, r0, q0); block_of(sn, b, ch, r1, q1);
+        if (r0 == r1 && q0 == q1) continue;
+#pragma unroll
+        for (int k0 = 0; k0 < V::E * V::E; k0 += 32) {
+          const int k = k0 + lane;
+          if (k < V::E * V::E) {
+            const int rr = k / V::E, cc = k - rr * V::E;
+            img[((size_t)ch * V::S + r0 + rr) * V::S + q0 + cc] = 0.0f;       // erase the old block ...
+          }
+        }
+        __syncwarp();                                                          // ... before drawing the new one
+#pragma unroll
+        for (int k0 = 0; k0 < V::E * V::E; k0 += 32) {
+          const int k = k0 + lane;
+          if (k < V::E * V::E) {
+            const int rr = k / V::E, cc = k - rr * V::E;
+            img[((size_t)ch * V::S + r1 + rr) * V::S + q1 + cc] = 1.0f;
+          }
+        }
+      }
+    }
+    tile = ntile; o = no; valid = nvalid;
+  }
+  ws.flush(p.stats, lane);
   if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
 }
 

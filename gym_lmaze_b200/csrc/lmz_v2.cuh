@@ -147,7 +147,7 @@ template <class W>
 __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const FovTables<W> &t) {
   V2Lane out;
   LaneOut &o = out.o;
-  o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
+  o.st_old = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
   V2Regs r = v2_unpack(p.state[e], p.goal_count[e]);
   bool reset_now = false;
   int reward_code = RC_NEG_ZERO;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     const int64_t e = tl * 32 + lane;
     const bool valid = tl < tiles && e < p.n;
     V2Lane v;
-    v.o.st = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
+    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
 #pragma unroll
     for (int c = 0; c < W::NBIT; ++c) v.mask[c] = 0;
     if (valid) v = v2_lane<W>(p, e, t);

@@ -26,7 +26,7 @@ _VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
              "v2": _abi.LMZ_V2, 2: _abi.LMZ_V2, "lmaze-v2": _abi.LMZ_V2,
              "v4": _abi.LMZ_V4, 4: _abi.LMZ_V4, "lmaze-v4": _abi.LMZ_V4,
              "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3}
-_RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128}
+_RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128, "incremental": _abi.RENDER_INCREMENTAL}
 _OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT}
 # lmaze_env_v3.py:236-247 -- the strings v3's step() accepts; anything else is its unmatched branch
 _V3_WORDS = {"left": 0, "0": 0, "right": 1, "1": 1, "up": 2, "2": 2, "down": 3, "3": 3}
@@ -53,7 +53,7 @@ class LmazeVecCuda(object):
         if variant not in _VARIANTS:
             raise ValueError("unknown variant %r (built: v0, v2, v3, v4)" % (variant,))
         if render_mode not in _RENDER:
-            raise ValueError("render_mode must be 'tma' or 'st128'")
+            raise ValueError("render_mode must be 'tma', 'st128' or 'incremental'")
         if obs_mode not in _OBS_MODE:
             raise ValueError("obs_mode must be 'full' or 'compact'")
         self._lib = _abi.load()          # raises if the CUDA extension is missing: no fallback
@@ -184,13 +184,20 @@ class LmazeVecCuda(object):
         return spawn.to(device=self.device, dtype=torch.int32).contiguous()
 
     # ------------------------------------------------------------------ gym surface
-    def reset(self, spawn=None, mask=None):
+    def reset(self, spawn=None, mask=None, mode="train"):
         """Start new episodes (all envs, or those where `mask` is true) and return obs.
+
+        mode="test" is the v3 reference's fixed evaluation start (lmaze_env_v3.py:145-146,154-155):
+        goal (8,8), ball (7,8).
 
         spawn: optional int [N, 4] (ball_x, ball_y, goal_x, goal_y) -- the cells the
         reference's rejection sampling (lmaze_env.py:70-78) would have drawn; default is
         the device RNG.
         """
+        if mode == "test":
+            if self.variant != _abi.LMZ_V3:
+                raise ValueError("reset(mode='test') exists only in lmaze-v3")
+            spawn = torch.tensor([[7, 8, 8, 8]], dtype=torch.int32).expand(self.num_envs, 4)
         spawn = self._as_spawn(spawn)
         if mask is not None:
             mask = torch.as_tensor(mask).to(device=self.device).to(torch.uint8).contiguous()

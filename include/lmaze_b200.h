@@ -56,7 +56,12 @@ typedef enum {
 /* How the fused kernel writes the observation tensor. */
 typedef enum {
   LMZ_RENDER_TMA = 0,     /* bulk async shared->global copies (cp.async.bulk) of template segments */
-  LMZ_RENDER_ST128 = 1    /* 128-bit vector stores (st.global.v4) fed from the shared-memory template */
+  LMZ_RENDER_ST128 = 1,   /* 128-bit vector stores (st.global.v4) fed from the shared-memory template */
+  LMZ_RENDER_INCREMENTAL = 2  /* v0/v3: the bound obs tensor persists, so a step only erases the ball's old ExE block
+                             and draws the new one (2*E*E floats instead of the whole image); the tensor stays
+                             bit-identical to a full render.  Full renders (TMA) are used for reset / render calls
+                             and whenever the tensor may be stale (after bind, set_window, set_state).  The caller
+                             must not write into obs. */
 } lmz_render_mode;
 
 /* What the observation tensor holds. */

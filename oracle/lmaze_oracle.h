@@ -139,6 +139,7 @@ void lmzo_vec_reset(lmzo_env *envs, int64_t n, int variant, const int32_t *spawn
 /* ---- array plumbing used by the ctypes wrapper (oracle/oracle.py) ---- */
 int64_t lmzo_sizeof_env(void);
 lmzo_env *lmzo_env_at(lmzo_env *envs, int64_t i);
+void lmzo_env_set_flags(lmzo_env *e, int random_ball, int random_goal);
 /* pos: int32 [N][4] = x, y, goal_x, goal_y */
 void lmzo_vec_export(const lmzo_env *envs, int64_t n, int32_t *pos, int64_t *step_count,
                      int64_t *goal_count, double *reward);

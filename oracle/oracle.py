@@ -70,6 +70,8 @@ def lib():
     L.lmzo_sizeof_env.restype = i64
     L.lmzo_env_at.argtypes = [vp, i64]
     L.lmzo_env_at.restype = vp
+    L.lmzo_env_set_flags.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.lmzo_env_set_flags.restype = None
     L.lmzo_vec_export.argtypes = [vp, i64, vp, vp, vp, vp]
     L.lmzo_vec_export.restype = None
     L.lmzo_env_force.argtypes = [vp, ctypes.c_int] + [ctypes.c_int] * 4 + [i64, dbl, i64]
@@ -140,7 +142,7 @@ class OracleVec(object):
     drive both with the same calls.
     """
 
-    def __init__(self, variant, n, seed=0, env_id0=0, autoreset=True, threads=1):
+    def __init__(self, variant, n, seed=0, env_id0=0, autoreset=True, threads=1, random_ball=True, random_goal=True):
         self.L = lib()
         self.variant, self.n, self.seed, self.env_id0 = variant, int(n), int(seed), int(env_id0)
         self.autoreset, self.threads = bool(autoreset), int(threads)
@@ -148,6 +150,8 @@ class OracleVec(object):
         self._mem = np.zeros(self.n * self.env_bytes, dtype=np.uint8)  # zero => lazily lmzo_init'ed
         for i in range(self.n):
             self.L.lmzo_init(self._env(i), variant)
+            if not (random_ball and random_goal):
+                self.L.lmzo_env_set_flags(self._env(i), int(random_ball), int(random_goal))
         self.episode = np.zeros(self.n, dtype=np.uint32)
         self.stats = np.zeros(NUM_STATS, dtype=np.int64)
         self.obs_shape = OBS_SHAPE[variant]

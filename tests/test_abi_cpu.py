@@ -108,3 +108,11 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 3, 3)
+
+
+def test_missing_extension_fails_loudly(abi, monkeypatch):
+    """No .so -> ImportError naming the build command; never a silent fallback."""
+    monkeypatch.setattr(abi, "_lib", None)
+    monkeypatch.setattr(abi, "LIB_PATH", os.path.join(ROOT, "gym_lmaze_b200", "does_not_exist.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        abi.load()

@@ -762,3 +762,94 @@ def test_cuda_graph_replay(lmz, oracle_mod, variant, render_mode):
     assert env.launch_count == launches          # no host-side launches happened during the replays
     assert env.stats()["steps"] == 150 * N       # capturing does not execute; the warm-up is a render, not a step
     env.close()
+
+
+# ---------------------------------------------------------------- the reference's attribute switches
+@pytest.mark.parametrize("variant,random_ball,random_goal", [("v0", False, True), ("v3", False, True),
+                                                             ("v3", True, False), ("v3", False, False)])
+def test_fixed_ball_and_goal_switches(lmz, oracle_mod, variant, random_ball, random_goal):
+    """RANDOM_BALL / RANDOM_GOAL = False (lmaze_env.py:25,82-89; lmaze_env_v3.py:103-104,162-164)."""
+    N = 600
+    ov = oracle_mod.V0 if variant == "v0" else oracle_mod.V3
+    ora = oracle_mod.OracleVec(ov, N, seed=3, random_ball=random_ball, random_goal=random_goal)
+    env = lmz.LmazeVecCuda(N, variant, seed=3, random_ball=random_ball, random_goal=random_goal)
+    assert torch.equal(env.reset().cpu(), torch.from_numpy(ora.reset()))
+    gen = torch.Generator().manual_seed(1)
+    for t in range(210):
+        a = torch.randint(0, 4, (N,), generator=gen)
+        o_ref, r_ref, d_ref = ora.step(a.numpy(), want_obs=(t % 20 == 0))
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)) and np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
+        if t % 20 == 0:
+            assert torch.equal(obs.cpu(), torch.from_numpy(o_ref)), t
+    st = env.get_state().cpu().numpy()
+    pos = ora.export()[0]
+    assert np.array_equal(st[:, 0:2], pos[:, 0:2])
+    if variant == "v3":
+        assert np.array_equal(st[:, 2:4], pos[:, 2:4])
+        if not random_goal:
+            assert (st[:, 2] == 8).all() and (st[:, 3] == 8).all()      # the 'X' cell
+    env.close()
+
+
+def test_v3_reset_test_mode(lmz, golden_dir):
+    z = np.load(os.path.join(golden_dir, "v3_table.npz"))
+    env = lmz.LmazeVecCuda(5, "v3")
+    obs = env.reset(mode="test")
+    st = env.get_state().cpu().numpy()
+    assert (st[:, 0:4] == np.array(z["test_info"])).all()
+    assert np.array_equal(obs[0].cpu().numpy(), unpack(z["test_obs"], (3, 72, 72)))
+    env.close()
+    with pytest.raises(ValueError):
+        lmz.LmazeVecCuda(2, "v0").reset(mode="test")
+
+
+# ---------------------------------------------------------------- incremental render into a persistent obs tensor
+@pytest.mark.parametrize("variant", ["v0", "v3"])
+def test_incremental_render_stays_bit_identical(lmz, oracle_mod, variant):
+    """render_mode='incremental': only the moved ExE blocks are rewritten, yet after every step the whole
+    obs tensor equals the oracle's full image (auto-resets, invalid actions, windows, set_state resync)."""
+    N, T = 2500, 260
+    ov = oracle_mod.V0 if variant == "v0" else oracle_mod.V3
+    ora = oracle_mod.OracleVec(ov, N, seed=17, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, variant, seed=17, autoreset=True, render_mode="incremental")
+    assert torch.equal(env.reset().cpu(), torch.from_numpy(ora.reset()))
+    gen = torch.Generator().manual_seed(3)
+    obs_buf = np.empty((N,) + oracle_mod.OBS_SHAPE[ov], np.float32)
+    for t in range(T):
+        a = torch.randint(0, 5, (N,), generator=gen)
+        want_obs = t % 7 == 0 or t > T - 4
+        _, r_ref, d_ref = ora.step(a.numpy(), obs_out=obs_buf if want_obs else None, want_obs=want_obs)
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)) and np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
+        if want_obs:
+            assert torch.equal(obs.cpu(), torch.from_numpy(obs_buf)), t
+        if t == 100:                              # move envs behind the tensor's back: must resync with a full render
+            st = env.get_state()
+            env.set_state(st.roll(1, 0))
+            for i, row in enumerate(st.roll(1, 0).cpu().numpy()):
+                ora.force(i, int(row[0]), int(row[1]), int(row[2]), int(row[3]), step_count=int(row[4]),
+                          reward=RC_VALUE[row[5]], goal_count=int(row[6]))
+            ora.episode[:] = st.roll(1, 0).cpu().numpy()[:, 7]
+        if t == 150:                              # masked reset in the middle (full render of the masked rows only)
+            mask = torch.rand(N, generator=gen) < 0.3
+            sp = _random_spawn(np.random.RandomState(t), _spawn_cells(oracle_mod.layout(ov), variant), N, variant)
+            env.reset(spawn=sp, mask=mask)
+            for i in np.nonzero(mask.numpy())[0]:
+                oracle_mod.lib().lmzo_reset(ora._env(int(i)), int(sp[i, 0]), int(sp[i, 1]), int(sp[i, 2]), int(sp[i, 3]))
+                ora.episode[i] += 1
+    s = env.stats()
+    assert s["steps"] == T * N and s["episodes"] == int(ora.stats[1])
+    env.close()
+    # windowed: the window is re-synced by a full render after every set_window
+    env = lmz.LmazeVecCuda(N, variant, seed=17, render_mode="incremental", obs_window=700)
+    ora = oracle_mod.OracleVec(ov, N, seed=17)
+    env.reset(); ora.reset(want_obs=False)
+    for t in range(12):
+        a = torch.randint(0, 4, (N,), generator=gen)
+        o_ref, _, _ = ora.step(a.numpy())
+        if t % 4 == 0:
+            env.set_window(300 * (t // 4))
+        obs, _, _, _ = env.step(a)
+        assert torch.equal(obs.cpu(), torch.from_numpy(o_ref[env.window_lo:env.window_lo + 700])), t
+    env.close()
