@@ -853,3 +853,59 @@ def test_incremental_render_stays_bit_identical(lmz, oracle_mod, variant):
         obs, _, _, _ = env.step(a)
         assert torch.equal(obs.cpu(), torch.from_numpy(o_ref[env.window_lo:env.window_lo + 700])), t
     env.close()
+
+
+# ---------------------------------------------------------------- long soak: 65,536 envs x 1,000 steps
+@pytest.mark.parametrize("variant", ["v0", "v3"])
+def test_soak_rollout_65k_envs_1000_steps(lmz, oracle_mod, variant):
+    """Device-RNG actions and spawns for 65.5 M env-steps: every reward / done of every step, the final
+    states, goal counts, episode counters and the integer statistics must equal the oracle's."""
+    N, T, calls, seed, id0 = 1 << 16, 250, 4, 2027, 10 ** 12
+    ov = oracle_mod.V0 if variant == "v0" else oracle_mod.V3
+    ora = oracle_mod.OracleVec(ov, N, seed=seed, env_id0=id0, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, variant, seed=seed, env_id0=id0, autoreset=True, with_obs=False)
+    ora.reset(want_obs=False); env.reset()
+    L = oracle_mod.lib()
+    ids = np.arange(N, dtype=np.uint64) + np.uint64(id0)
+    t_global = 0
+    for c in range(calls):
+        rew, done = env.rollout(T)
+        rew_h = rew.cpu().numpy().view(np.uint32); done_h = done.cpu().numpy().view(np.uint8)
+        for t in range(T):
+            acts = np.fromiter((L.lmzo_rng_action(seed, int(g), t_global + t) for g in ids[:64]), dtype=np.int64)
+            # the full action row comes from the vectorised twin below; the first 64 are cross-checked here
+            row = _rng_actions(seed, ids, t_global + t)
+            assert np.array_equal(row[:64], acts)
+            _, r_ref, d_ref = ora.step(row, want_obs=False)
+            assert np.array_equal(rew_h[t], r_ref.view(np.uint32)), (c, t)
+            assert np.array_equal(done_h[t], d_ref), (c, t)
+        t_global += T
+    st = env.get_state().cpu().numpy()
+    pos, sc, gc, _ = ora.export()
+    assert np.array_equal(st[:, 0:2], pos[:, 0:2]) and np.array_equal(st[:, 4], sc) and np.array_equal(st[:, 7], ora.episode)
+    if variant == "v0":
+        assert np.array_equal(st[:, 6], gc)
+    s = env.stats()
+    assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist() and s["steps"] == N * T * calls
+    env.close()
+
+
+def _philox_np(c0, c1, c2, c3, k0, k1):
+    """numpy Philox-4x32-10 over arrays of counters (same spec as DESIGN.md section 4)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & mask, lo1, (hi0 ^ c3 ^ k1) & mask, lo0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c0, c1, c2, c3
+
+
+def _rng_actions(seed, ids, t):
+    blk, slot = t >> 6, t & 63
+    w = _philox_np(ids & np.uint64(0xFFFFFFFF), ids >> np.uint64(32), np.full(len(ids), blk & 0xFFFFFFFF, np.uint64),
+                   np.full(len(ids), ((blk >> 32) << 8) | 0x41, np.uint64), seed & 0xFFFFFFFF, seed >> 32)
+    return ((w[slot >> 4] >> np.uint64(2 * (slot & 15))) & np.uint64(3)).astype(np.int64)
