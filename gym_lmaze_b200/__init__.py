@@ -5,6 +5,7 @@ variants that are built and adds vectorised ids.  `make(id, num_envs=...)` works
 gym; when gym or gymnasium is importable the ids are registered there as well.
 """
 from .envs import LmazeVecCuda, shard_range, allreduce_stats, INVALID_ACTION  # noqa: F401
+from .envs import LmazeEnv, LmazeEnv_v2, LmazeEnv_v3, LmazeEnv_v4  # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -16,12 +17,20 @@ def register(id, variant, **defaults):
     _REGISTRY[id] = (variant, defaults)
 
 
+_SINGLE = {"v0": LmazeEnv, "v2": LmazeEnv_v2, "v3": LmazeEnv_v3, "v4": LmazeEnv_v4}
+
+
 def make(id, **kwargs):
+    """'lmaze-vK' -> the reference's single-maze surface (numpy obs, float reward, bool done, action);
+    'lmaze-vec-vK' (or num_envs=...) -> the batched LmazeVecCuda."""
     if id not in _REGISTRY:
         raise KeyError("unknown env id %r; built ids: %s" % (id, ", ".join(sorted(_REGISTRY))))
     variant, defaults = _REGISTRY[id]
     kw = dict(defaults)
     kw.update(kwargs)
+    if "-vec-" not in id and "num_envs" not in kwargs:
+        kw.pop("num_envs", None)
+        return _SINGLE[variant](**kw)
     return LmazeVecCuda(variant=variant, **kw)
 
 
