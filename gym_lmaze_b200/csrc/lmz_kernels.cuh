@@ -648,21 +648,25 @@ __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) 
         int ch, r0, q0, r1, q1;
         block_of(so, b, ch, r0, q0); block_of(sn, b, ch, r1, q1);
         if (r0 == r1 && q0 == q1) continue;
+        // The plane holds ONE block of ones, so every element's value follows from the new position.  Rewrite
+        // whole aligned 32-byte sectors around the old and the new block (values computed, not read): full-sector
+        // writes need no read-modify-write in L2/DRAM, and the two passes may overlap freely (same values).
+        float *plane = img + (size_t)ch * V::S * V::S;            // 32-byte aligned (plane = 28,224 / 20,736 B)
 #pragma unroll
-        for (int k0 = 0; k0 < V::E * V::E; k0 += 32) {
-          const int k = k0 + lane;
-          if (k < V::E * V::E) {
-            const int rr = k / V::E, cc = k - rr * V::E;
-            img[((size_t)ch * V::S + r0 + rr) * V::S + q0 + cc] = 0.0f;       // erase the old block ...
-          }
-        }
-        __syncwarp();                                                          // ... before drawing the new one
+        for (int pass = 0; pass < 2; ++pass) {
+          const int brow = pass ? r1 : r0, bcol = pass ? q1 : q0;
 #pragma unroll
-        for (int k0 = 0; k0 < V::E * V::E; k0 += 32) {
-          const int k = k0 + lane;
-          if (k < V::E * V::E) {
-            const int rr = k / V::E, cc = k - rr * V::E;
-            img[((size_t)ch * V::S + r1 + rr) * V::S + q1 + cc] = 1.0f;
+          for (int k0 = 0; k0 < V::E * 16; k0 += 32) {
+            const int k = k0 + lane, rr = k >> 4, j = k & 15;       // row of the block, float slot in its <= 64-byte span
+            if (rr < V::E) {
+              const int first = (brow + rr) * V::S + bcol;          // the row segment [first, first + E)
+              const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
+              const int e = lo + j;
+              if (e < hi) {
+                const int er = e / V::S, ec = e - er * V::S;
+                plane[e] = (er >= r1 && er < r1 + V::E && ec >= q1 && ec < q1 + V::E) ? 1.0f : 0.0f;
+              }
+            }
           }
         }
       }
