@@ -30,6 +30,7 @@ extern "C" {
 #define LMZO_V2 2
 #define LMZO_V3 3
 #define LMZO_V4 4
+#define LMZO_V5 5   /* also stands for v6, which only adds safeFovealGoal() */
 #define LMZO_MAX_G 18
 
 /* One environment, holding the same mutable fields the reference keeps on `self`. */
@@ -57,6 +58,15 @@ typedef struct lmzo_env {
   float action_plane[25]; /* action_value one-hot (lmaze_env_v2.py:87,136-137) */
   int prev_x, prev_y;     /* where shown_prev was taken (bookkeeping for tests) */
   int64_t bad_actions;    /* batched API: actions outside 0..24 are clamped and counted */
+  /* ---- v5 / v6 (lmaze_env_v5.py): planner / actor protocol ---- */
+  int ball_x1, ball_y1;   /* previous ball (lmaze_env_v5.py:192-193) */
+  int fovea_x1, fovea_y1; /* fovea centre at the last plannerStep (:176-178); fovea_x0/y0 always equal the ball */
+  int fgoal_x, fgoal_y;   /* f_goal_x0/y0: the cell the planner pointed at (:170-171) */
+  int fgoal_action;       /* which cell of fovealGoal is hot (:166-168); 12 after reset (:131-132) */
+  int last_x, last_y;     /* where retStatelast (a VIEW of state) was taken (:327-328,:351-352) */
+  int64_t foveal_step_count;
+  int local_done, global_done;
+  double global_reward;
 } lmzo_env;
 
 /* Episode statistics, integers only (order-independent sums). */
@@ -102,6 +112,29 @@ void lmzo_rng_spawn_v4(uint64_t seed, uint64_t env_id, uint32_t episode,
 /* v4 visit layer state[2] (float32 [G*G]) of every env: read / overwrite */
 void lmzo_vec_export_visit(const lmzo_env *envs, int64_t n, float *out);
 void lmzo_env_set_visit(lmzo_env *e, const float *visit);
+/* ---- v5 / v6 ---- */
+int  lmzo_reset_v5(lmzo_env *e, int sx, int sy, int gx, int gy, int new_layout);   /* lmaze_env_v5.py:102-153 */
+int  lmzo_planner_v5(lmzo_env *e, int64_t goal);                                   /* plannerStep, :158-182 */
+/* step(), :187-292.  Returns global_done | local_done << 1; rewards are left in e->reward (originalReward)
+ * and e->global_reward.  Also performs the state change of the buildFovealObservation() call inside step
+ * (the visit-layer update when the local episode is over, :308-312, and retStatelast, :351-352). */
+int  lmzo_step_v5(lmzo_env *e, int64_t action);
+void lmzo_render_fov_v5(const lmzo_env *e, float *obs);      /* (7,35,35), :306-354 */
+int  lmzo_render_loc_v5(const lmzo_env *e, float *obs);      /* (4,35,35), :356-380; -1 where the reference raises IndexError */
+int  lmzo_step_full_v5(lmzo_env *e, int64_t action, float *fov, float *loc, int *loc_error);
+/* Batched drivers (serial).  mask NULL = all envs.  spawn: int32 [N][4] (sx, sy, gx, gy | layout << 5) or NULL =
+ * the Philox spec (same stream as v4: maze, goal, ball).  loc_err[i] = 1 where the reference would raise. */
+void lmzo_vec_reset_v5(lmzo_env *envs, int64_t n, const uint8_t *mask, const int32_t *spawn, uint64_t seed,
+                       uint64_t env_id0, uint32_t *episode, float *fov);
+void lmzo_vec_planner_v5(lmzo_env *envs, int64_t n, const int64_t *goals, const uint8_t *mask, float *loc,
+                         uint8_t *loc_err);
+void lmzo_vec_step_v5(lmzo_env *envs, int64_t n, const int64_t *actions, const uint8_t *mask, float *fov, float *loc,
+                      float *greward, float *lreward, uint8_t *gdone, uint8_t *ldone, uint8_t *loc_err);
+/* int32 [N][16]: x, y, x1, y1, fx1, fy1, gx, gy, fgx, fgy, last_x, last_y, fgoal_action, step, foveal_step, flags */
+void lmzo_vec_export_v5(const lmzo_env *envs, int64_t n, int32_t *out);
+/* v6 safeFovealGoal (lmaze_env_v6.py:505-523): consumes draws[] (each in 0..24) until a non-wall cell of
+ * the 5x5 window around the ball comes up; returns it and stores how many draws were used. */
+int  lmzo_safe_goal_v6(const lmzo_env *e, const int64_t *draws, int n_draws, int *used);
 /* The five 18x18 mazes of lmaze_env_v2.py:303-405 (layout 1..5). */
 int  lmzo_layout_v2(int layout, char *cells);
 

@@ -12,10 +12,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblmaze_oracle.so")
 
-V0, V2, V3, V4 = 0, 2, 3, 4
+V0, V2, V3, V4, V5 = 0, 2, 3, 4, 5
 NUM_STATS = 8
 STAT_NAMES = ("steps", "episodes", "goals", "timeouts", "wall_bumps", "moves", "stale", "eplen_sum")
-OBS_SHAPE = {V0: (4, 84, 84), V2: (5, 35, 35), V3: (3, 72, 72), V4: (7, 35, 35)}
+OBS_SHAPE = {V0: (4, 84, 84), V2: (5, 35, 35), V3: (3, 72, 72), V4: (7, 35, 35), V5: (7, 35, 35)}
 # f32 bit patterns of the only rewards the reference can emit
 REWARD_BITS = {"neg_zero": 0x80000000, "wall": 0xBF800000, "move": 0xBC23D70A, "goal": 0x42C80000}
 
@@ -84,6 +84,17 @@ def lib():
     L.lmzo_vec_export_visit.restype = None
     L.lmzo_env_set_visit.argtypes = [vp, vp]
     L.lmzo_env_set_visit.restype = None
+    u8p = vp
+    L.lmzo_vec_reset_v5.argtypes = [vp, i64, u8p, vp, u64, u64, vp, vp]
+    L.lmzo_vec_reset_v5.restype = None
+    L.lmzo_vec_planner_v5.argtypes = [vp, i64, vp, u8p, vp, vp]
+    L.lmzo_vec_planner_v5.restype = None
+    L.lmzo_vec_step_v5.argtypes = [vp, i64, vp, u8p] + [vp] * 7
+    L.lmzo_vec_step_v5.restype = None
+    L.lmzo_vec_export_v5.argtypes = [vp, i64, vp]
+    L.lmzo_vec_export_v5.restype = None
+    L.lmzo_safe_goal_v6.argtypes = [vp, vp, ctypes.c_int, ip]
+    L.lmzo_safe_goal_v6.restype = ctypes.c_int
     L.lmzo_layout_v2.argtypes = [ctypes.c_int, ctypes.c_char_p]
     L.lmzo_layout_v2.restype = ctypes.c_int
     L.lmzo_rng_spawn_v2.argtypes = [u64, u64, u32, ctypes.c_int] + [ip] * 6
@@ -232,3 +243,62 @@ class OracleVec(object):
         obs = np.empty(self.obs_shape, dtype=np.float32)
         self.L.lmzo_render(self._env(i), _ptr(obs))
         return obs
+
+
+class OracleHier(object):
+    """N oracle envs of the planner/actor variant (lmaze-v5 / v6), batched like LmazeHierCuda."""
+
+    def __init__(self, n, seed=0, env_id0=0):
+        self.L = lib()
+        self.n, self.seed, self.env_id0 = int(n), int(seed), int(env_id0)
+        self.env_bytes = self.L.lmzo_sizeof_env()
+        self._mem = np.zeros(self.n * self.env_bytes, dtype=np.uint8)
+        for i in range(self.n):
+            self.L.lmzo_init(self._env(i), V5)
+        self.episode = np.zeros(self.n, dtype=np.uint32)
+
+    def _env(self, i):
+        return self._mem.ctypes.data + i * self.env_bytes
+
+    @staticmethod
+    def _mask(mask, n):
+        return None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(n)
+
+    def reset(self, spawn=None, mask=None, want_obs=True):
+        s = None if spawn is None else np.ascontiguousarray(spawn, dtype=np.int32).reshape(self.n, 4)
+        fov = np.zeros((self.n, 7, 35, 35), dtype=np.float32) if want_obs else None
+        self.L.lmzo_vec_reset_v5(_ptr(self._mem), self.n, _ptr(self._mask(mask, self.n)), _ptr(s), self.seed,
+                                 self.env_id0, _ptr(self.episode), _ptr(fov))
+        return fov
+
+    def planner_step(self, goals, mask=None):
+        g = np.ascontiguousarray(goals, dtype=np.int64).reshape(self.n)
+        loc = np.zeros((self.n, 4, 35, 35), dtype=np.float32)
+        err = np.zeros(self.n, dtype=np.uint8)
+        self.L.lmzo_vec_planner_v5(_ptr(self._mem), self.n, _ptr(g), _ptr(self._mask(mask, self.n)), _ptr(loc), _ptr(err))
+        return loc, err
+
+    def step(self, actions, mask=None):
+        a = np.ascontiguousarray(actions, dtype=np.int64).reshape(self.n)
+        fov = np.zeros((self.n, 7, 35, 35), dtype=np.float32)
+        loc = np.zeros((self.n, 4, 35, 35), dtype=np.float32)
+        gr = np.zeros(self.n, np.float32); lr = np.zeros(self.n, np.float32)
+        gd = np.zeros(self.n, np.uint8); ld = np.zeros(self.n, np.uint8); err = np.zeros(self.n, np.uint8)
+        self.L.lmzo_vec_step_v5(_ptr(self._mem), self.n, _ptr(a), _ptr(self._mask(mask, self.n)), _ptr(fov), _ptr(loc),
+                                _ptr(gr), _ptr(lr), _ptr(gd), _ptr(ld), _ptr(err))
+        return fov, loc, gr, lr, gd, ld, err
+
+    def export(self):
+        out = np.zeros((self.n, 16), dtype=np.int32)
+        self.L.lmzo_vec_export_v5(_ptr(self._mem), self.n, _ptr(out))
+        return out
+
+    def export_visit(self):
+        out = np.empty((self.n, 18, 18), dtype=np.float32)
+        self.L.lmzo_vec_export_visit(_ptr(self._mem), self.n, _ptr(out))
+        return out
+
+    def safe_goal(self, i, draws):
+        d = np.ascontiguousarray(draws, dtype=np.int64)
+        used = ctypes.c_int()
+        return self.L.lmzo_safe_goal_v6(self._env(i), _ptr(d), len(d), ctypes.byref(used)), used.value

@@ -26,6 +26,8 @@ _FILES = {
     "v2": ("gym_lmaze/envs/lmaze_env_v2.py", "LmazeEnv_v2"),
     "v3": ("gym_lmaze/envs/lmaze_env_v3.py", "LmazeEnv_v3"),
     "v4": ("gym_lmaze/envs/lmaze_env_v4.py", "LmazeEnv_v4"),
+    "v5": ("gym_lmaze/envs/lmaze_env_v5.py", "LmazeEnv_v5"),
+    "v6": ("gym_lmaze/envs/lmaze_env_v6.py", "LmazeEnv_v6"),
 }
 
 

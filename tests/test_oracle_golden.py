@@ -315,3 +315,52 @@ def test_v4_traces(oracle_mod, golden_dir):
             assert float(vis[e].astype(np.float64).sum()) == z["e%d_visit_sum" % e][t]
     for e in range(ne):
         assert np.array_equal(vis[e].view(np.uint32), z["e%d_final_visit" % e].view(np.uint32))
+
+
+# ---------------------------------------------------------------- v5 / v6 (planner / actor protocol)
+def _loc_obs(bits):
+    small = np.unpackbits(bits)[:100].reshape(4, 5, 5).astype(np.float32)
+    return np.repeat(np.repeat(small, 7, 1), 7, 2)
+
+
+@pytest.mark.parametrize("variant", ["v5", "v6"])
+def test_v5_traces(oracle_mod, golden_dir, variant):
+    """Every value the reference returned from reset / plannerStep / step over 4 x ~730 events."""
+    z = np.load(os.path.join(golden_dir, variant + "_traces.npz"))
+    n_events = 0
+    for e in range(int(z["n_envs"])):
+        o = oracle_mod.OracleHier(1)
+        ev = z["e%d_events" % e]
+        for k, row in enumerate(ev):
+            kind, arg, grb, orb, gd, ld, bx, by = (int(v) for v in row[:8])
+            sp = row[8:13]
+            if kind == 0:
+                fov = o.reset(spawn=[[sp[0], sp[1], sp[2], sp[3] | (sp[4] << 5)]])
+                assert np.array_equal(fov[0].view(np.uint32), v4_obs(z["e%d_fov_bits" % e][k], z["e%d_fov_visit" % e][k]).view(np.uint32)), (e, k)
+            elif kind == 1:
+                loc, err = o.planner_step([arg])
+                assert not err[0] and np.array_equal(loc[0], _loc_obs(z["e%d_loc_bits" % e][k])), (e, k)
+            else:
+                fov, loc, gr, lr, gdo, ldo, err = o.step([arg])
+                assert not err[0]
+                assert gr.view(np.uint32)[0] == np.float32(f64(grb)).view(np.uint32), (e, k)
+                assert lr.view(np.uint32)[0] == np.float32(f64(orb)).view(np.uint32), (e, k)
+                assert (gdo[0], ldo[0]) == (gd, ld), (e, k)
+                assert np.array_equal(fov[0].view(np.uint32), v4_obs(z["e%d_fov_bits" % e][k], z["e%d_fov_visit" % e][k]).view(np.uint32)), (e, k)
+                assert np.array_equal(loc[0], _loc_obs(z["e%d_loc_bits" % e][k])), (e, k)
+            st = o.export()[0]
+            assert (st[0], st[1]) == (bx, by), (e, k)
+            assert float(o.export_visit()[0].astype(np.float64).sum()) == z["e%d_visit_sum" % e][k], (e, k)
+            n_events += 1
+    assert n_events > 2500
+    if variant == "v6":       # safeFovealGoal(): re-draw until the window cell is not a wall (lmaze_env_v6.py:505-523)
+        o = oracle_mod.OracleHier(1)
+        rows = [str(r) for r in z["safe_layout"]]
+        k = [i for i in range(1, 6) if oracle_mod.layout_v2(i) == rows][0]
+        draws, pos = z["safe_draws"], 0
+        for bx, by, want, used in z["safe_results"]:
+            o.reset(spawn=[[4, 4, 8, 8 | (k << 5)]], want_obs=False)
+            oracle_mod.lib().lmzo_env_force_v2(o._env(0), k, int(bx), int(by), 8, 8, int(bx), int(by), 0)
+            got, n_used = o.safe_goal(0, draws[pos:pos + 40])
+            assert (got, n_used) == (want, used)
+            pos += used
