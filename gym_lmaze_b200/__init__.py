@@ -5,7 +5,8 @@ variants that are built and adds vectorised ids.  `make(id, num_envs=...)` works
 gym; when gym or gymnasium is importable the ids are registered there as well.
 """
 from .envs import LmazeVecCuda, shard_range, allreduce_stats, INVALID_ACTION  # noqa: F401
-from .envs import LmazeEnv, LmazeEnv_v2, LmazeEnv_v3, LmazeEnv_v4  # noqa: F401
+from .envs import LmazeEnv, LmazeEnv_v2, LmazeEnv_v3, LmazeEnv_v4, LmazeEnv_v5, LmazeEnv_v6  # noqa: F401
+from .envs import LmazeHierCuda  # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -17,7 +18,7 @@ def register(id, variant, **defaults):
     _REGISTRY[id] = (variant, defaults)
 
 
-_SINGLE = {"v0": LmazeEnv, "v2": LmazeEnv_v2, "v3": LmazeEnv_v3, "v4": LmazeEnv_v4}
+_SINGLE = {"v0": LmazeEnv, "v2": LmazeEnv_v2, "v3": LmazeEnv_v3, "v4": LmazeEnv_v4, "v5": LmazeEnv_v5, "v6": LmazeEnv_v6}
 
 
 def make(id, **kwargs):
@@ -31,6 +32,8 @@ def make(id, **kwargs):
     if "-vec-" not in id and "num_envs" not in kwargs:
         kw.pop("num_envs", None)
         return _SINGLE[variant](**kw)
+    if variant in ("v5", "v6"):
+        return LmazeHierCuda(variant=variant, **kw)
     return LmazeVecCuda(variant=variant, **kw)
 
 
@@ -42,6 +45,10 @@ register("lmaze-v0", "v0", num_envs=1)
 register("lmaze-v2", "v2", num_envs=1)
 register("lmaze-v3", "v3", num_envs=1)
 register("lmaze-v4", "v4", num_envs=1)
+register("lmaze-v5", "v5", num_envs=1)
+register("lmaze-v6", "v6", num_envs=1)
+register("lmaze-vec-v5", "v5", num_envs=4096)
+register("lmaze-vec-v6", "v6", num_envs=4096)
 register("lmaze-vec-v0", "v0", num_envs=4096)
 register("lmaze-vec-v2", "v2", num_envs=4096)
 register("lmaze-vec-v3", "v3", num_envs=4096)
@@ -56,7 +63,8 @@ def _register_with_gym():
                 continue
             for env_id, (variant, defaults) in _REGISTRY.items():
                 try:
-                    mod.register(id=env_id, entry_point="gym_lmaze_b200:LmazeVecCuda",
+                    mod.register(id=env_id, entry_point="gym_lmaze_b200:LmazeHierCuda" if variant in ("v5", "v6")
+                                 else "gym_lmaze_b200:LmazeVecCuda",
                                  kwargs=dict(defaults, variant=variant))
                 except Exception:
                     pass

@@ -9,14 +9,17 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblmaze_b200.so")
 
-LMZ_V0, LMZ_V2, LMZ_V3, LMZ_V4 = 0, 2, 3, 4
+LMZ_V0, LMZ_V2, LMZ_V3, LMZ_V4, LMZ_V5 = 0, 2, 3, 4, 5
 RENDER_TMA, RENDER_ST128, RENDER_INCREMENTAL = 0, 1, 2
 OBS_FULL, OBS_COMPACT = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 NUM_STATS = 8
 ST_COLS = 8
+ST_COLS_HIER = 17
 STAT_NAMES = ("steps", "episodes", "goals", "timeouts", "wall_bumps", "moves", "stale", "eplen_sum")
 STATE_COLS = ("x", "y", "goal_x", "goal_y", "step_count", "reward_code", "goal_count", "episode")
+STATE_COLS_HIER = ("x", "y", "prev_x", "prev_y", "fovea_x1", "fovea_y1", "goal_x", "goal_y", "fgoal_x", "fgoal_y",
+                   "last_x", "last_y", "fgoal_action", "step_count", "foveal_step_count", "flags", "episode")
 
 # every symbol include/lmaze_b200.h declares (tests/test_abi_symbols.py checks the header against this)
 EXPORTS = (
@@ -26,6 +29,8 @@ EXPORTS = (
     "lmz_step_dl", "lmz_step_host", "lmz_render", "lmz_rollout", "lmz_rollout_dl", "lmz_get_state",
     "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_get_visit", "lmz_set_visit", "lmz_get_visit_dl",
     "lmz_set_visit_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
+    "lmz_state_cols", "lmz_local_obs_shape", "lmz_bind_local", "lmz_bind_local_dl", "lmz_planner_step",
+    "lmz_planner_step_dl", "lmz_safe_goal", "lmz_safe_goal_dl",
 )
 
 
@@ -100,6 +105,14 @@ def load():
     L.lmz_set_visit.argtypes = [vp, vp, vp]
     L.lmz_get_visit_dl.argtypes = [vp, vp, vp]
     L.lmz_set_visit_dl.argtypes = [vp, vp, vp]
+    L.lmz_state_cols.argtypes = [i32]
+    L.lmz_local_obs_shape.argtypes = [i32, ctypes.POINTER(i64 * 3)]
+    L.lmz_bind_local.argtypes = [vp] * 6
+    L.lmz_bind_local_dl.argtypes = [vp] * 6
+    L.lmz_planner_step.argtypes = [vp, vp, i32, vp, vp]
+    L.lmz_planner_step_dl.argtypes = [vp, vp, vp, vp]
+    L.lmz_safe_goal.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.lmz_safe_goal_dl.argtypes = [vp, vp, vp, vp, vp]
     L.lmz_stats.argtypes = [vp, ctypes.POINTER(i64 * NUM_STATS), ctypes.POINTER(i64), vp]
     L.lmz_stats_reset.argtypes = [vp, vp]
     L.lmz_launch_count.argtypes = [vp]

@@ -16,6 +16,7 @@
 #include "../../include/lmaze_b200.h"
 #include "lmz_kernels.cuh"
 #include "lmz_v2.cuh"
+#include "lmz_v5.cuh"
 
 namespace {
 
@@ -164,6 +165,26 @@ void build_blob_fov(std::vector<unsigned char> &blob) {
   }
 }
 
+// v5/v6: v4's foveal tables + the local observation's LUT (lmaze_env_v5.py:356-380) + each maze's 'X' cell
+void build_blob_v5(std::vector<unsigned char> &blob) {
+  using V = lmz::V5;
+  build_blob_fov<V>(blob);
+  // local obs channels: free crop (bit plane 0), ball rel. fovea_x1 (5), previous ball (6), fovealGoal (2)
+  static const int plane[4] = {0, 5, 6, 2};
+  for (int c = 0; c < V::CL; ++c)
+    for (int row = 0; row < V::S; ++row)
+      for (int col = 0; col < V::S; ++col)
+        blob[V::LOCLUT_OFF + (c * V::S + row) * V::S + col] =
+            (unsigned char)((plane[c] << 5) | ((row / V::E) * V::F + col / V::E));
+  uint16_t *xcell = reinterpret_cast<uint16_t *>(blob.data() + V::XCELL_OFF);
+  for (int L = 0; L < V::NLAYOUT; ++L) {
+    char cells[18 * 18];
+    v2_cells(L + 1, cells);
+    for (int i = 0; i < V::G * V::G; ++i)
+      if (cells[i] == 'X') xcell[L] = (uint16_t)i;
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ handle
@@ -174,7 +195,12 @@ struct lmz_env {
   int num_sms;
   // device memory owned by the handle
   uint32_t *state, *goal_count, *episode;
-  float *visit;                  // v4 only: f32 [N][324]
+  float *visit;                  // v4 / v5: f32 [N][324]
+  uint32_t *aux2;                // v5: third packed state word
+  // v5 local outputs (caller-owned), lmz_bind_local
+  float *loc_obs, *reward2;
+  uint8_t *done2, *loc_err, *fgoal_out;
+  bool local_bound;
   unsigned char *blob;
   unsigned long long *stats;     // NUM_STATS counters + 1 error counter + 2 work-distribution words
   void *act_stage;               // lmz_step_host staging, lazily allocated (N * 8 bytes)
@@ -220,6 +246,8 @@ lmz::KParams base_params(lmz_env *h) {
   p.l2_policy = h->cfg.tune[1] ? h->cfg.tune[1] : lmz::DEFAULT_L2_POLICY;
   p.work = h->stats + lmz::NUM_STATS + 1;
   p.bulk_split = (uint32_t)h->cfg.tune[3];
+  p.aux2 = h->aux2; p.obs2 = h->loc_obs; p.reward2 = h->reward2; p.done2 = h->done2; p.loc_err = h->loc_err;
+  p.fgoal_out = h->fgoal_out;
   return p;
 }
 
@@ -348,7 +376,37 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return launch_fov_t<W, 512>(h, p, s);
 }
 
+template <int THREADS>
+int launch_v5_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  using W = lmz::V5;
+  auto kern = lmz::lmz_env_v5_kernel<W, THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, W::BLOB_BYTES));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "planner/actor env kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  const int64_t units = p.tile_end - p.tile_begin;
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  if (grid > units) grid = units;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, W::BLOB_BYTES, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+int launch_v5(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (!h->local_bound) return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
+  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : 512;
+  if (t == 256) return launch_v5_t<256>(h, p, s);
+  if (t == 1024) return launch_v5_t<1024>(h, p, s);
+  return launch_v5_t<512>(h, p, s);
+}
+
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.variant == LMZ_V5) return launch_v5(h, p, s);
   if (h->cfg.variant == LMZ_V2) return launch_fov<lmz::V2>(h, p, s);
   if (h->cfg.variant == LMZ_V4) return launch_fov<lmz::V4>(h, p, s);
   if (h->cfg.variant == LMZ_V0) return launch_env_v<lmz::V0>(h, p, s);
@@ -462,18 +520,33 @@ int lmz_obs_shape(int32_t variant, int64_t shape[3]) {
   if (variant == LMZ_V3) { shape[0] = lmz::V3::C; shape[1] = shape[2] = lmz::V3::S; return LMZ_OK; }
   if (variant == LMZ_V2) { shape[0] = lmz::V2::C; shape[1] = shape[2] = lmz::V2::S; return LMZ_OK; }
   if (variant == LMZ_V4) { shape[0] = lmz::V4::C; shape[1] = shape[2] = lmz::V4::S; return LMZ_OK; }
+  if (variant == LMZ_V5) { shape[0] = lmz::V5::C; shape[1] = shape[2] = lmz::V5::S; return LMZ_OK; }
+  return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
+}
+
+int lmz_local_obs_shape(int32_t variant, int64_t shape[3]) {
+  if (!shape) return fail(LMZ_ERR_INVALID, "shape is NULL");
+  if (variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "only lmaze-v5/v6 have a local observation");
+  shape[0] = lmz::V5::CL; shape[1] = shape[2] = lmz::V5::S;       // lmaze_env_v5.py:357-358
+  return LMZ_OK;
+}
+
+int lmz_state_cols(int32_t variant) {
+  if (variant == LMZ_V5) return LMZ_ST_COLS_HIER;
+  if (variant == LMZ_V0 || variant == LMZ_V2 || variant == LMZ_V3 || variant == LMZ_V4) return LMZ_ST_COLS;
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_num_actions(int32_t variant) {
   if (variant == LMZ_V0 || variant == LMZ_V3) return 4;      // lmaze_env.py:16, lmaze_env_v3.py:92
   if (variant == LMZ_V2 || variant == LMZ_V4) return 25;     // lmaze_env_v2.py:39 (commented out in v4, :43-44)
+  if (variant == LMZ_V5) return 4;                           // step() moves by one cell (lmaze_env_v5.py:205-217); plannerStep takes 25
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_num_layouts(int32_t variant) {
   if (variant == LMZ_V0 || variant == LMZ_V3) return 1;
-  if (variant == LMZ_V2 || variant == LMZ_V4) return 5;      // lmaze_env_v2.py:306, lmaze_env_v4.py:351
+  if (variant == LMZ_V2 || variant == LMZ_V4 || variant == LMZ_V5) return 5;      // lmaze_env_v2.py:306, lmaze_env_v4.py:351
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
@@ -482,7 +555,7 @@ int lmz_layout_ex(int32_t variant, int32_t index, char *cells) {
   const int nl = lmz_num_layouts(variant);
   if (nl < 0) return nl;
   if (index < 1 || index > nl) return fail(LMZ_ERR_INVALID, "layout index %d outside 1..%d", index, nl);
-  if (variant == LMZ_V2 || variant == LMZ_V4) { v2_cells(index, cells); return LMZ_OK; }
+  if (variant == LMZ_V2 || variant == LMZ_V4 || variant == LMZ_V5) { v2_cells(index, cells); return LMZ_OK; }
   return lmz_layout(variant, cells);
 }
 
@@ -502,12 +575,12 @@ int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *e
 
 int lmz_grid_size(int32_t variant) {
   if (variant == LMZ_V0) return lmz::V0::G;
-  if (variant == LMZ_V3 || variant == LMZ_V2 || variant == LMZ_V4) return lmz::V3::G;
+  if (variant == LMZ_V3 || variant == LMZ_V2 || variant == LMZ_V4 || variant == LMZ_V5) return lmz::V3::G;
   return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
 }
 
 int lmz_layout(int32_t variant, char *cells) {
-  if (variant == LMZ_V2 || variant == LMZ_V4) return lmz_layout_ex(variant, 1, cells);
+  if (variant == LMZ_V2 || variant == LMZ_V4 || variant == LMZ_V5) return lmz_layout_ex(variant, 1, cells);
   const char *c = cells_of(variant);
   if (!c) return fail(LMZ_ERR_UNSUPPORTED, "unknown variant %d", variant);
   if (!cells) return fail(LMZ_ERR_INVALID, "cells is NULL");
@@ -522,18 +595,21 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (cfg->struct_size != (int32_t)sizeof(lmz_config))
     return fail(LMZ_ERR_INVALID, "lmz_config.struct_size %d != %d: header/library mismatch", cfg->struct_size,
                 (int)sizeof(lmz_config));
-  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3 && cfg->variant != LMZ_V2 && cfg->variant != LMZ_V4)
+  if (cfg->variant != LMZ_V0 && cfg->variant != LMZ_V3 && cfg->variant != LMZ_V2 && cfg->variant != LMZ_V4 &&
+      cfg->variant != LMZ_V5)
     return fail(LMZ_ERR_UNSUPPORTED,
-                "variant %d is not built (supported: 0 = lmaze-v0, 2 = lmaze-v2, 3 = lmaze-v3, 4 = lmaze-v4)", cfg->variant);
+                "variant %d is not built (supported: 0 = lmaze-v0, 2 = lmaze-v2, 3 = lmaze-v3, 4 = lmaze-v4, "
+                "5 = lmaze-v5/v6)", cfg->variant);
+  const bool hier = cfg->variant == LMZ_V5;
   const bool foveal = cfg->variant == LMZ_V2 || cfg->variant == LMZ_V4;
-  if (foveal && cfg->obs_mode != LMZ_OBS_FULL)
-    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2/v4 have no compact observation mode yet");
+  if ((foveal || hier) && cfg->obs_mode != LMZ_OBS_FULL)
+    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2/v4/v5 have no compact observation mode yet");
   if (cfg->num_envs < 1) return fail(LMZ_ERR_INVALID, "num_envs must be >= 1 (got %lld)", (long long)cfg->num_envs);
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
   if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128 &&
       cfg->render_mode != LMZ_RENDER_INCREMENTAL)
     return fail(LMZ_ERR_INVALID, "unknown render_mode %d", cfg->render_mode);
-  if (cfg->render_mode == LMZ_RENDER_INCREMENTAL && (cfg->variant == LMZ_V2 || cfg->variant == LMZ_V4))
+  if (cfg->render_mode == LMZ_RENDER_INCREMENTAL && (foveal || hier))
     return fail(LMZ_ERR_UNSUPPORTED, "incremental render needs a full-view variant (v0, v3): a foveal crop changes entirely every step");
   for (int i = 0; i < 2; ++i)
     if (cfg->reserved[i] != 0) return fail(LMZ_ERR_INVALID, "lmz_config.reserved must be zero");
@@ -581,6 +657,11 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     h->compact_bytes_per_env = 0;
     build_blob_fov<lmz::V4>(blob);
     h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
+  } else if (cfg->variant == LMZ_V5) {
+    h->G = lmz::V5::G; h->C = lmz::V5::C; h->S = lmz::V5::S; h->obs_bytes_per_env = lmz::V5::OBS_BYTES;
+    h->compact_bytes_per_env = 0;
+    build_blob_v5(blob);
+    h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
   } else {
     h->G = lmz::V3::G; h->C = lmz::V3::C; h->S = lmz::V3::S; h->obs_bytes_per_env = lmz::V3::OBS_BYTES;
     h->compact_bytes_per_env = lmz::V3::COMPACT_BYTES;
@@ -592,7 +673,8 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->goal_count, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->episode, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->blob, blob.size());
-  if (e == cudaSuccess && cfg->variant == LMZ_V4) {      // state[2], the float visit layer (lmaze_env_v4.py:106-113)
+  if (e == cudaSuccess && hier) e = cudaMalloc(&h->aux2, n * sizeof(uint32_t));
+  if (e == cudaSuccess && (cfg->variant == LMZ_V4 || hier)) {      // state[2], the float visit layer (lmaze_env_v4.py:106-113)
     e = cudaMalloc(&h->visit, n * 324 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(h->visit, 0, n * 324 * sizeof(float));
   }
@@ -619,6 +701,23 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
         e = cudaMemcpy(h->goal_count + off, auxv.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice);
       }
     }
+    if (hier) {                            // maze 1, everything on 'S', goal on 'X' (the state reset() would leave there)
+      lmz::V5Regs v;
+      v.L = 1; v.x = v.x1 = v.fx1 = v.fgx = v.lx = 4; v.y = v.y1 = v.fy1 = v.fgy = v.ly = 4; v.gx = 8; v.gy = 8;
+      v.fga = 12; v.step = 0; v.fstep = 0; v.ld = 0; v.gd = 0;
+      uint32_t w1, w2;
+      lmz::v5_pack(v, packed, w1, w2);
+      std::vector<uint32_t> tmp(n < (1u << 20) ? n : (1u << 20), w1);
+      for (size_t off = 0; off < n && e == cudaSuccess; off += tmp.size()) {
+        const size_t cnt = (n - off < tmp.size()) ? n - off : tmp.size();
+        e = cudaMemcpy(h->goal_count + off, tmp.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice);
+      }
+      tmp.assign(tmp.size(), w2);
+      for (size_t off = 0; off < n && e == cudaSuccess; off += tmp.size()) {
+        const size_t cnt = (n - off < tmp.size()) ? n - off : tmp.size();
+        e = cudaMemcpy(h->aux2 + off, tmp.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice);
+      }
+    }
     std::vector<uint32_t> init(n < (1u << 20) ? n : (1u << 20), packed);
     for (size_t off = 0; off < n && e == cudaSuccess; off += init.size()) {
       const size_t cnt = (n - off < init.size()) ? n - off : init.size();
@@ -638,7 +737,7 @@ int lmz_destroy(lmz_env *h) {
   if (!h) return LMZ_OK;
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->goal_count); cudaFree(h->episode); cudaFree(h->blob); cudaFree(h->stats);
-  cudaFree(h->act_stage); cudaFree(h->visit);
+  cudaFree(h->act_stage); cudaFree(h->visit); cudaFree(h->aux2);
   delete h;
   return LMZ_OK;
 }
@@ -679,6 +778,7 @@ int lmz_bind_dl(lmz_env *h, DLManagedTensor *obs, DLManagedTensor *reward, DLMan
 int lmz_set_window(lmz_env *h, void *obs, int64_t env_lo, int64_t env_count) {
   if (int rc = check_handle(h)) return rc;
   if (int rc = check_bound(h)) return rc;
+  if (h->cfg.variant == LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_set_window is not built for lmaze-v5/v6");
   if (!obs) return fail(LMZ_ERR_INVALID, "obs is NULL");
   if ((reinterpret_cast<uintptr_t>(obs) & 15u) != 0) return fail(LMZ_ERR_INVALID, "obs must be 16-byte aligned");
   if (env_lo < 0 || env_count < 1 || env_lo + env_count > h->cfg.num_envs)
@@ -760,6 +860,7 @@ int lmz_step_host(lmz_env *h, const void *actions_host, int32_t action_dtype, fl
   if (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64)
     return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
   if (obs_host && !h->obs) return fail(LMZ_ERR_STATE, "obs_host given but no device obs buffer is bound");
+  if (h->cfg.variant == LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_step_host is not built for lmaze-v5/v6");
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = (size_t)h->cfg.num_envs;
@@ -793,8 +894,8 @@ int lmz_rollout(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype
                 void *stream) {
   if (int rc = check_handle(h)) return rc;
   if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
-  if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4)
-    return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2/v4 yet");
+  if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4 || h->cfg.variant == LMZ_V5)
+    return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2/v4/v5 yet");
   if (!rewards || !dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
   if (actions && (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64))
     return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
@@ -832,7 +933,9 @@ static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {
   const int64_t n = h->cfg.num_envs;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4)
+  if (h->cfg.variant == LMZ_V5)
+    lmz::lmz_state_v5_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->aux2, h->episode, io, set);
+  else if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4)
     lmz::lmz_state_v2_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
   else if (h->cfg.variant == LMZ_V0)
     lmz::lmz_state_kernel<lmz::V0><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
@@ -852,7 +955,7 @@ int lmz_set_state(lmz_env *h, const int32_t *in, void *stream) {
 static int state_xfer_dl(lmz_env *h, DLManagedTensor *t, int set, void *stream) {
   if (int rc = check_handle(h)) return rc;
   void *pt = nullptr;
-  Want w{"state", kDLInt, 32, 2, {h->cfg.num_envs, LMZ_ST_COLS, 0, 0}, false, 4};
+  Want w{"state", kDLInt, 32, 2, {h->cfg.num_envs, lmz_state_cols(h->cfg.variant), 0, 0}, false, 4};
   if (int rc = check_dl(h, t, w, &pt, nullptr)) return rc;
   return state_xfer(h, static_cast<int32_t *>(pt), set, stream);
 }
@@ -864,7 +967,8 @@ int lmz_set_state_dl(lmz_env *h, DLManagedTensor *in, void *stream) {
 
 static int visit_xfer(lmz_env *h, float *buf, int set, void *stream) {
   if (int rc = check_handle(h)) return rc;
-  if (h->cfg.variant != LMZ_V4) return fail(LMZ_ERR_UNSUPPORTED, "only lmaze-v4 has a visit layer");
+  if (h->cfg.variant != LMZ_V4 && h->cfg.variant != LMZ_V5)
+    return fail(LMZ_ERR_UNSUPPORTED, "only lmaze-v4/v5/v6 have a visit layer");
   if (!buf) return fail(LMZ_ERR_INVALID, "visit buffer is NULL");
   DeviceGuard guard(h->cfg.device);
   const size_t bytes = (size_t)h->cfg.num_envs * 324 * sizeof(float);
@@ -883,6 +987,108 @@ static int visit_xfer_dl(lmz_env *h, DLManagedTensor *t, int set, void *stream) 
 }
 int lmz_get_visit_dl(lmz_env *h, DLManagedTensor *out, void *stream) { return visit_xfer_dl(h, out, 0, stream); }
 int lmz_set_visit_dl(lmz_env *h, DLManagedTensor *in, void *stream) { return visit_xfer_dl(h, in, 1, stream); }
+
+// ---- lmaze-v5 / v6 -------------------------------------------------------------------------------
+int lmz_bind_local(lmz_env *h, float *loc_obs, float *local_reward, uint8_t *local_done, uint8_t *loc_err,
+                   uint8_t *foveal_goal) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_bind_local: only lmaze-v5/v6 have local outputs");
+  if (!local_reward || !local_done) return fail(LMZ_ERR_INVALID, "local_reward/local_done must not be NULL");
+  if ((reinterpret_cast<uintptr_t>(loc_obs) & 15u) != 0) return fail(LMZ_ERR_INVALID, "loc_obs must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(local_reward) & 3u) != 0)
+    return fail(LMZ_ERR_INVALID, "local_reward must be 4-byte aligned");
+  h->loc_obs = loc_obs; h->reward2 = local_reward; h->done2 = local_done; h->loc_err = loc_err;
+  h->fgoal_out = foveal_goal; h->local_bound = true;
+  return LMZ_OK;
+}
+
+int lmz_bind_local_dl(lmz_env *h, DLManagedTensor *loc_obs, DLManagedTensor *local_reward, DLManagedTensor *local_done,
+                      DLManagedTensor *loc_err, DLManagedTensor *foveal_goal) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *po = nullptr, *pr = nullptr, *pd = nullptr, *pe = nullptr, *pg = nullptr;
+  if (loc_obs) {
+    Want w{"loc_obs", kDLFloat, 32, 4, {n, lmz::V5::CL, lmz::V5::S, lmz::V5::S}, false, 16};
+    if (int rc = check_dl(h, loc_obs, w, &po, nullptr)) return rc;
+  }
+  Want wr{"local_reward", kDLFloat, 32, 1, {n, 0, 0, 0}, false, 4};
+  if (int rc = check_dl(h, local_reward, wr, &pr, nullptr)) return rc;
+  Want wd{"local_done", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+  if (int rc = check_dl(h, local_done, wd, &pd, nullptr)) return rc;
+  if (loc_err) {
+    Want w{"loc_err", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+    if (int rc = check_dl(h, loc_err, w, &pe, nullptr)) return rc;
+  }
+  if (foveal_goal) {
+    Want w{"foveal_goal", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+    if (int rc = check_dl(h, foveal_goal, w, &pg, nullptr)) return rc;
+  }
+  return lmz_bind_local(h, static_cast<float *>(po), static_cast<float *>(pr), static_cast<uint8_t *>(pd),
+                        static_cast<uint8_t *>(pe), static_cast<uint8_t *>(pg));
+}
+
+int lmz_planner_step(lmz_env *h, const void *goals, int32_t goal_dtype, const uint8_t *mask, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_planner_step: only lmaze-v5/v6 have a planner level");
+  if (int rc = check_bound(h)) return rc;
+  if (!goals) return fail(LMZ_ERR_INVALID, "goals is NULL");
+  if (goal_dtype < LMZ_ACT_U8 || goal_dtype > LMZ_ACT_I64) return fail(LMZ_ERR_INVALID, "unknown goal dtype %d", goal_dtype);
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_PLANNER; p.actions = goals; p.action_dtype = goal_dtype; p.mask = mask;
+  return launch_env(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int lmz_planner_step_dl(lmz_env *h, DLManagedTensor *goals, DLManagedTensor *mask, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pg = nullptr, *pm = nullptr;
+  int ad = 0;
+  Want wg{"goals", 255, 0, 1, {n, 0, 0, 0}, false, 1};
+  if (int rc = check_dl(h, goals, wg, &pg, &ad)) return rc;
+  if (mask) {
+    Want w{"mask", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+    if (int rc = check_dl(h, mask, w, &pm, nullptr)) return rc;
+  }
+  return lmz_planner_step(h, pg, ad, static_cast<const uint8_t *>(pm), stream);
+}
+
+int lmz_safe_goal(lmz_env *h, const int64_t *draws, int32_t n_draws, uint8_t *goals_out, int32_t *used_out, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_safe_goal: only lmaze-v6 (variant 5) has safeFovealGoal");
+  if (!goals_out) return fail(LMZ_ERR_INVALID, "goals_out is NULL");
+  if (draws && n_draws < 1) return fail(LMZ_ERR_INVALID, "n_draws must be >= 1 when draws are given");
+  DeviceGuard guard(h->cfg.device);
+  const int64_t n = h->cfg.num_envs;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  lmz::lmz_safe_goal_kernel<lmz::V5><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n, h->state, h->aux2, h->episode, h->blob, reinterpret_cast<const long long *>(draws), n_draws, goals_out, used_out,
+      h->cfg.seed, (uint64_t)h->cfg.env_id0);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+int lmz_safe_goal_dl(lmz_env *h, DLManagedTensor *draws, DLManagedTensor *goals_out, DLManagedTensor *used_out,
+                     void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pd = nullptr, *pg = nullptr, *pu = nullptr;
+  int32_t nd = 0;
+  if (draws) {
+    if (draws->dl_tensor.ndim != 2) return fail(LMZ_ERR_INVALID, "draws: ndim %d, want 2", draws->dl_tensor.ndim);
+    nd = (int32_t)draws->dl_tensor.shape[1];
+    Want w{"draws", kDLInt, 64, 2, {n, nd, 0, 0}, false, 8};
+    if (int rc = check_dl(h, draws, w, &pd, nullptr)) return rc;
+  }
+  Want wg{"goals_out", kDLUInt, 8, 1, {n, 0, 0, 0}, false, 1};
+  if (int rc = check_dl(h, goals_out, wg, &pg, nullptr)) return rc;
+  if (used_out) {
+    Want w{"used_out", kDLInt, 32, 1, {n, 0, 0, 0}, false, 4};
+    if (int rc = check_dl(h, used_out, w, &pu, nullptr)) return rc;
+  }
+  return lmz_safe_goal(h, static_cast<const int64_t *>(pd), nd, static_cast<uint8_t *>(pg), static_cast<int32_t *>(pu), stream);
+}
 
 int lmz_stats(lmz_env *h, int64_t *out_host, int64_t *errors_host, void *stream) {
   if (int rc = check_handle(h)) return rc;

@@ -58,6 +58,13 @@ struct KParams {
   int l2_policy;                // L2_* policy of the obs stores (TMA path)
   unsigned long long *work;     // [2]: next tile to hand out, grabbers finished (self re-arming)
   uint32_t bulk_split;          // 0, or the largest single bulk copy in bytes
+  // ---- lmaze-v5 / v6 (planner / actor env, lmz_v5.cuh)
+  uint32_t *aux2;               // third packed state word
+  void *obs2;                   // local observation f32 [n][4][35][35], or null
+  float *reward2;               // originalReward (the actor's reward) [n]
+  uint8_t *done2;               // localDone [n]
+  uint8_t *loc_err;             // 1 where the reference's buildLocalObservation raises IndexError [n], or null
+  uint8_t *fgoal_out;           // hot cell of fovealGoal [n], or null
 };
 
 enum : int { L2_EVICT_FIRST = 1, L2_EVICT_NORMAL = 2, L2_EVICT_LAST = 3, L2_NONE = 4 };

@@ -4,6 +4,8 @@
     LmazeEnv_v2   <-> reference gym_lmaze/envs/lmaze_env_v2.py:17  ('lmaze-v2')
     LmazeEnv_v3   <-> reference gym_lmaze/envs/lmaze_env_v3.py:17  ('lmaze-v3')
     LmazeEnv_v4   <-> reference gym_lmaze/envs/lmaze_env_v4.py:17  ('lmaze-v4')
+    LmazeEnv_v5   <-> reference gym_lmaze/envs/lmaze_env_v5.py:17  ('lmaze-v5', planner / actor protocol)
+    LmazeEnv_v6   <-> reference gym_lmaze/envs/lmaze_env_v6.py:17  ('lmaze-v6', v5 + safeFovealGoal)
 
 Same returns and types as the reference: `reset()` -> numpy float32 observation, `step(a)` ->
 `(obs, reward, done, info)` with reward a Python float (exactly -0.0 / -1.0 / -0.01 / 100.0), done a
@@ -15,6 +17,7 @@ import numpy as np
 import torch
 
 from .lmaze_vec_cuda import LmazeVecCuda, INVALID_ACTION, _V3_WORDS
+from .lmaze_hier_cuda import LmazeHierCuda
 
 # f32 bit pattern -> the reference's Python float (lmaze_env.py:21-23,109)
 _REWARD = {0x80000000: -0.0, 0xBF800000: -1.0, 0xBC23D70A: -0.01, 0x42C80000: 100.0}
@@ -105,3 +108,73 @@ class LmazeEnv_v3(_SingleMaze):
             self._vec.reset(mode="test")
             return self._obs()
         return super().reset(spawn=spawn)
+
+
+class LmazeEnv_v5(object):
+    """Reference LmazeEnv_v5: reset() -> foveal obs; plannerStep(goal) -> local obs; step(a) -> the 8-tuple
+    (fovobs, locobs, globalReward, originalReward, globalDone, localDone, fovealGoal, local_action),
+    lmaze_env_v5.py:285-292.  The constructor ends with reset(), like the reference's (lmaze_env_v5.py:92)."""
+    metadata = {"render.modes": ["human"]}
+    _variant = "v5"
+
+    def __init__(self, device=None, seed=0, **kwargs):
+        self._vec = LmazeHierCuda(1, self._variant, device=device, seed=seed, autoreset=False, **kwargs)
+        self.VISUALIZE = False
+        self.step_limit, self.foveal_step_limit = 10, 50
+        self.reset()
+
+    def reset(self, spawn=None):
+        """spawn: optional (ball_x, ball_y, goal_x, goal_y, layout) pinning the reference's random draws."""
+        self._vec.reset(spawn=None if spawn is None else [list(spawn)])
+        return self._vec.obs[0].cpu().numpy()
+
+    def _loc(self):
+        if bool(self._vec.loc_err.item()):
+            # lmaze_env_v5.py:365-366: the actor is 3 cells right of / below the planner-time fovea
+            raise IndexError("index 5 is out of bounds for axis 1 with size 5")
+        return self._vec.loc_obs[0].cpu().numpy()
+
+    def plannerStep(self, goal):
+        goal = int(goal)                                   # :165
+        if not 0 <= goal <= 24:
+            raise IndexError("lmaze-v5 foveal goal %d outside the 5x5 window" % goal)
+        self._vec.plannerStep(torch.tensor([goal], dtype=torch.uint8))
+        return self._loc()
+
+    def step(self, goal):
+        code = int(goal)                                   # :190
+        wire = code if 0 <= code < 255 else INVALID_ACTION
+        v = self._vec
+        v.step(torch.tensor([wire], dtype=torch.uint8), goal_plane=False)
+        fov = v.obs[0].cpu().numpy()
+        gbits = int(v.reward.view(torch.int32).item()) & 0xFFFFFFFF
+        lbits = int(v.local_reward.view(torch.int32).item()) & 0xFFFFFFFF
+        return (fov, self._loc(), _REWARD[gbits], _REWARD[lbits], bool(v.done.item()), bool(v.local_done.item()),
+                v.goal_plane()[0].cpu().numpy(), code)
+
+    def render(self, mode="human", close=False):
+        self.VISUALIZE = (mode == "human")
+
+    def rendering(self, msg):
+        self.VISUALIZE = msg
+
+    def writing(self, msg):
+        self.SAVEFRAME = msg
+
+    def close(self):
+        self._vec.close()
+
+    @property
+    def state_vector(self):
+        return self._vec.get_state()[0].tolist()
+
+
+class LmazeEnv_v6(LmazeEnv_v5):
+    _variant = "v6"
+
+    def safeFovealGoal(self, draws=None):
+        """lmaze_env_v6.py:505-523.  draws: optional list of the np.random.randint(0, 25) values to consume."""
+        if draws is None:
+            return int(self._vec.safeFovealGoal().item())
+        goals, _ = self._vec.safeFovealGoal([list(draws)])
+        return int(goals.item())

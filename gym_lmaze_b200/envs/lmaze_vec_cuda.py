@@ -25,7 +25,8 @@ from ..spaces import make_spaces
 _VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
              "v2": _abi.LMZ_V2, 2: _abi.LMZ_V2, "lmaze-v2": _abi.LMZ_V2,
              "v4": _abi.LMZ_V4, 4: _abi.LMZ_V4, "lmaze-v4": _abi.LMZ_V4,
-             "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3}
+             "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3,
+             "v5": _abi.LMZ_V5, 5: _abi.LMZ_V5, "lmaze-v5": _abi.LMZ_V5}    # v5/v6: use LmazeHierCuda
 _RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128, "incremental": _abi.RENDER_INCREMENTAL}
 _OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT}
 # lmaze_env_v3.py:236-247 -- the strings v3's step() accepts; anything else is its unmatched branch
@@ -51,7 +52,9 @@ class LmazeVecCuda(object):
                  env_id0=0, random_ball=True, random_goal=True, with_obs=True, tune=None, obs_mode="full",
                  obs_window=None):
         if variant not in _VARIANTS:
-            raise ValueError("unknown variant %r (built: v0, v2, v3, v4)" % (variant,))
+            raise ValueError("unknown variant %r (built: v0, v2, v3, v4; v5/v6 through LmazeHierCuda)" % (variant,))
+        if _VARIANTS[variant] == _abi.LMZ_V5 and not hasattr(self, "plannerStep"):
+            raise ValueError("lmaze-v5/v6 is the planner/actor env: construct LmazeHierCuda")
         if render_mode not in _RENDER:
             raise ValueError("render_mode must be 'tma', 'st128' or 'incremental'")
         if obs_mode not in _OBS_MODE:

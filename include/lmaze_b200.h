@@ -50,7 +50,9 @@ typedef enum {
   LMZ_V0 = 0,   /* LmazeEnv     'lmaze-v0', 12x12, obs f32 (4,84,84)  -- lmaze_env.py:11-256    */
   LMZ_V2 = 2,   /* LmazeEnv_v2  'lmaze-v2', 5 mazes of 18x18, Discrete(25), obs f32 (5,35,35) -- lmaze_env_v2.py:17-405 */
   LMZ_V3 = 3,   /* LmazeEnv_v3  'lmaze-v3', 18x18, obs f32 (3,72,72)  -- lmaze_env_v3.py:17-402 */
-  LMZ_V4 = 4    /* LmazeEnv_v4  'lmaze-v4', v2 + float visit layer, obs f32 (7,35,35) -- lmaze_env_v4.py:17-482 */
+  LMZ_V4 = 4,   /* LmazeEnv_v4  'lmaze-v4', v2 + float visit layer, obs f32 (7,35,35) -- lmaze_env_v4.py:17-482 */
+  LMZ_V5 = 5    /* LmazeEnv_v5 / LmazeEnv_v6  'lmaze-v5', 'lmaze-v6': planner / actor env, foveal obs f32 (7,35,35)
+                   + local obs f32 (4,35,35) -- lmaze_env_v5.py:17-712; v6 adds safeFovealGoal, lmaze_env_v6.py:505-523 */
 } lmz_variant;
 
 /* How the fused kernel writes the observation tensor. */
@@ -195,17 +197,57 @@ int lmz_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedT
  * resume, and how parity tests start both sides from the same state).  For v2 columns
  * 5 and 6 are: layout (1..5), and prev_x | prev_y << 5 | last_action << 10 | action_valid << 15
  * (the position of the previous crop and the action plane of the current obs). */
+/* For v5/v6 the rows are int32 [N][LMZ_ST_COLS_HIER] (see lmz_state_cols). */
 int lmz_get_state(lmz_env *env, int32_t *out, void *stream);
 int lmz_set_state(lmz_env *env, const int32_t *in, void *stream);
 int lmz_get_state_dl(lmz_env *env, DLManagedTensor *out, void *stream);
 int lmz_set_state_dl(lmz_env *env, DLManagedTensor *in, void *stream);
 
-/* lmaze-v4 only: the float visit layer state[2] of every env (lmaze_env_v4.py:106-113,211-214),
+/* lmaze-v4 / v5 / v6: the float visit layer state[2] of every env (lmaze_env_v4.py:106-113,211-214; lmaze_env_v5.py:308-312),
  * f32 [N][18][18] on the device -- part of the checkpoint next to lmz_get_state. */
 int lmz_get_visit(lmz_env *env, float *out, void *stream);
 int lmz_set_visit(lmz_env *env, const float *in, void *stream);
 int lmz_get_visit_dl(lmz_env *env, DLManagedTensor *out, void *stream);
 int lmz_set_visit_dl(lmz_env *env, DLManagedTensor *in, void *stream);
+
+/* ---- lmaze-v5 / lmaze-v6: the planner / actor protocol ------------------------------------------
+ * reset()             -> lmz_reset: foveal obs into the tensor bound as `obs`      (lmaze_env_v5.py:102-153)
+ * plannerStep(goal)   -> lmz_planner_step: local obs into `loc_obs`                (:158-182)
+ * step(action)        -> lmz_step: the reference's 8-tuple (:285-292) lands in
+ *                          obs (foveal), loc_obs, reward (globalReward), local_reward (originalReward),
+ *                          done (globalDone), local_done (localDone), foveal_goal (hot cell of fovealGoal);
+ *                          the 8th element is the caller's own action.
+ * Actions 0..3 are (+1,0) (-1,0) (0,+1) (0,-1) on (row, col) (:205-217) -- NOT v0's map; other values do not move.
+ * With autoreset an env whose globalDone is raised is reset inside the same step: both observation rows
+ * then show the new episode (what reset() / buildLocalObservation() would return), the flags and rewards
+ * stay the terminal ones, and the caller's next lmz_planner_step mask is local_done | done.
+ * Where the reference's buildLocalObservation raises IndexError (the actor is 3 cells right of / below the
+ * planner-time fovea, :365-366) the local row is written as zeros, loc_err[i] = 1 and the error counter of
+ * lmz_stats is bumped; negative indices wrap exactly like numpy's.
+ * lmz_set_window, lmz_rollout and lmz_step_host are not available for this variant. */
+#define LMZ_ST_COLS_HIER 17   /* x, y, prev_x, prev_y, fovea_x1, fovea_y1, goal_x, goal_y, fgoal_x, fgoal_y, last_x, last_y,
+                                 fgoal_action, step_count, foveal_step_count, globalDone | localDone << 1 | layout << 4, episode */
+int lmz_state_cols(int32_t variant);                               /* LMZ_ST_COLS, or LMZ_ST_COLS_HIER for v5 */
+int lmz_local_obs_shape(int32_t variant, int64_t shape[3]);        /* (4,35,35), lmaze_env_v5.py:357-358 */
+/* loc_obs f32 [N,4,35,35] (16-byte aligned; may be NULL), local_reward f32 [N], local_done u8 [N],
+ * loc_err u8 [N] (may be NULL), foveal_goal u8 [N] (may be NULL). */
+int lmz_bind_local(lmz_env *env, float *loc_obs, float *local_reward, uint8_t *local_done, uint8_t *loc_err,
+                   uint8_t *foveal_goal);
+int lmz_bind_local_dl(lmz_env *env, DLManagedTensor *loc_obs, DLManagedTensor *local_reward,
+                      DLManagedTensor *local_done, DLManagedTensor *loc_err, DLManagedTensor *foveal_goal);
+/* plannerStep() for every env whose mask byte is non-zero (mask NULL = all): goals [N] in 0..24 of
+ * `goal_dtype` (lmz_action_dtype); out-of-range goals (IndexError in the reference) are clamped and counted. */
+int lmz_planner_step(lmz_env *env, const void *goals, int32_t goal_dtype, const uint8_t *mask, void *stream);
+int lmz_planner_step_dl(lmz_env *env, DLManagedTensor *goals, DLManagedTensor *mask, void *stream);
+/* lmaze-v6 safeFovealGoal() (lmaze_env_v6.py:505-523): goals_out u8 [N] = a cell 0..24 of the 5x5 window around
+ * the ball that is not a wall.  draws NULL => device RNG, exactly uniform over the non-wall cells (the
+ * distribution of the reference's rejection loop); else int64 [N][n_draws] are the values its
+ * np.random.randint(0, 25) calls would return: the first non-wall one wins, used_out i32 [N] (may be NULL)
+ * receives how many were consumed, and goals_out is 255 if none qualified. */
+int lmz_safe_goal(lmz_env *env, const int64_t *draws, int32_t n_draws, uint8_t *goals_out, int32_t *used_out,
+                  void *stream);
+int lmz_safe_goal_dl(lmz_env *env, DLManagedTensor *draws, DLManagedTensor *goals_out, DLManagedTensor *used_out,
+                     void *stream);
 
 /* Copies the device counters to out_host[LMZ_NUM_STATS] (synchronises `stream`).
  * *errors_host (may be NULL) receives the number of rejected injected spawns. */

@@ -130,6 +130,7 @@ void lmzo_vec_planner_v5(lmzo_env *envs, int64_t n, const int64_t *goals, const 
                          uint8_t *loc_err);
 void lmzo_vec_step_v5(lmzo_env *envs, int64_t n, const int64_t *actions, const uint8_t *mask, float *fov, float *loc,
                       float *greward, float *lreward, uint8_t *gdone, uint8_t *ldone, uint8_t *loc_err);
+void lmzo_vec_render_v5(const lmzo_env *envs, int64_t n, const uint8_t *mask, float *fov, float *loc, uint8_t *loc_err);
 /* int32 [N][16]: x, y, x1, y1, fx1, fy1, gx, gy, fgx, fgy, last_x, last_y, fgoal_action, step, foveal_step, flags */
 void lmzo_vec_export_v5(const lmzo_env *envs, int64_t n, int32_t *out);
 /* v6 safeFovealGoal (lmaze_env_v6.py:505-523): consumes draws[] (each in 0..24) until a non-wall cell of

@@ -91,6 +91,8 @@ def lib():
     L.lmzo_vec_planner_v5.restype = None
     L.lmzo_vec_step_v5.argtypes = [vp, i64, vp, u8p] + [vp] * 7
     L.lmzo_vec_step_v5.restype = None
+    L.lmzo_vec_render_v5.argtypes = [vp, i64, u8p, vp, vp, vp]
+    L.lmzo_vec_render_v5.restype = None
     L.lmzo_vec_export_v5.argtypes = [vp, i64, vp]
     L.lmzo_vec_export_v5.restype = None
     L.lmzo_safe_goal_v6.argtypes = [vp, vp, ctypes.c_int, ip]
@@ -287,6 +289,14 @@ class OracleHier(object):
         self.L.lmzo_vec_step_v5(_ptr(self._mem), self.n, _ptr(a), _ptr(self._mask(mask, self.n)), _ptr(fov), _ptr(loc),
                                 _ptr(gr), _ptr(lr), _ptr(gd), _ptr(ld), _ptr(err))
         return fov, loc, gr, lr, gd, ld, err
+
+    def render(self, mask=None, fov=None, loc=None):
+        """Both observations of the current state (rows where mask is false are left as passed in / zero)."""
+        fov = np.zeros((self.n, 7, 35, 35), dtype=np.float32) if fov is None else fov
+        loc = np.zeros((self.n, 4, 35, 35), dtype=np.float32) if loc is None else loc
+        err = np.zeros(self.n, dtype=np.uint8)
+        self.L.lmzo_vec_render_v5(_ptr(self._mem), self.n, _ptr(self._mask(mask, self.n)), _ptr(fov), _ptr(loc), _ptr(err))
+        return fov, loc, err
 
     def export(self):
         out = np.zeros((self.n, 16), dtype=np.int32)

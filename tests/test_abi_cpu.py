@@ -45,7 +45,10 @@ def test_static_queries_and_layouts(abi, golden_dir):
     shape = (ctypes.c_int64 * 3)()
     assert L.lmz_obs_shape(abi.LMZ_V0, ctypes.byref(shape)) == 0 and tuple(shape) == (4, 84, 84)
     assert L.lmz_obs_shape(abi.LMZ_V3, ctypes.byref(shape)) == 0 and tuple(shape) == (3, 72, 72)
-    assert L.lmz_obs_shape(5, ctypes.byref(shape)) < 0 and b"unknown variant" in L.lmz_last_error()
+    assert L.lmz_obs_shape(abi.LMZ_V5, ctypes.byref(shape)) == 0 and tuple(shape) == (7, 35, 35)
+    assert L.lmz_local_obs_shape(abi.LMZ_V5, ctypes.byref(shape)) == 0 and tuple(shape) == (4, 35, 35)
+    assert L.lmz_state_cols(abi.LMZ_V5) == 17 and L.lmz_state_cols(abi.LMZ_V0) == 8 and L.lmz_num_actions(abi.LMZ_V5) == 4
+    assert L.lmz_obs_shape(7, ctypes.byref(shape)) < 0 and b"unknown variant" in L.lmz_last_error()
     z = np.load(os.path.join(golden_dir, "layouts.npz"))
     for name, variant, G in (("v0", abi.LMZ_V0, 12), ("v3", abi.LMZ_V3, 18)):
         assert L.lmz_grid_size(variant) == G
@@ -64,7 +67,7 @@ def test_config_validation_and_no_cpu_fallback(abi):
     h = ctypes.c_void_p()
     bad = abi.LmzConfig.from_buffer_copy(cfg); bad.struct_size = 8
     assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -1 and b"struct_size" in L.lmz_last_error()
-    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.variant = 5
+    bad = abi.LmzConfig.from_buffer_copy(cfg); bad.variant = 7
     assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -4
     bad = abi.LmzConfig.from_buffer_copy(cfg); bad.num_envs = 0
     assert L.lmz_create(ctypes.byref(bad), ctypes.byref(h)) == -1

@@ -1,0 +1,242 @@
+"""GPU tier, lmaze-v5 / lmaze-v6 (planner / actor env): the CUDA path through the C ABI against
+(a) the golden traces recorded from the unmodified reference and (b) the CPU oracle on the same
+seeded inputs -- every returned value per call, bit for bit (both observation tensors, both rewards'
+bit patterns, both done flags, the IndexError flag, the packed state and the float visit layer).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lmz():
+    import gym_lmaze_b200 as g
+    from gym_lmaze_b200 import _abi
+    _abi.load()
+    assert torch.cuda.is_available()
+    return g
+
+
+def f64(bits):
+    return np.int64(bits).view(np.float64)
+
+
+def u32(t):
+    if torch.is_tensor(t):
+        t = t.detach().cpu().numpy()
+    return np.ascontiguousarray(t).view(np.uint32)
+
+
+def fov_obs(bits, visit):
+    b = np.unpackbits(bits)[:125].reshape(5, 5, 5).astype(np.float32)
+    small = np.stack([b[0], b[1], visit[0], b[2], b[3], b[4], visit[1]])
+    return np.repeat(np.repeat(small, 7, 1), 7, 2)
+
+
+def loc_obs(bits):
+    small = np.unpackbits(bits)[:100].reshape(4, 5, 5).astype(np.float32)
+    return np.repeat(np.repeat(small, 7, 1), 7, 2)
+
+
+# ---------------------------------------------------------------- golden traces (reference outputs)
+@pytest.mark.parametrize("variant", ["v5", "v6"])
+def test_hier_golden_traces(lmz, golden_dir, variant):
+    """All four recorded envs run side by side in one batch of 4; each event drives only its own env
+    (reset / plannerStep are masked; a step advances every env, so the others are restored afterwards)."""
+    z = np.load(os.path.join(golden_dir, variant + "_traces.npz"))
+    n_events = 0
+    for e in range(int(z["n_envs"])):
+        env = lmz.LmazeHierCuda(1, variant, autoreset=False)
+        ev = z["e%d_events" % e]
+        for k, row in enumerate(ev):
+            kind, arg, grb, orb, gd, ld, bx, by = (int(v) for v in row[:8])
+            sp = [int(v) for v in row[8:13]]
+            if kind == 0:
+                fov = env.reset(spawn=[sp])
+                assert np.array_equal(u32(fov[0]), u32(fov_obs(z["e%d_fov_bits" % e][k], z["e%d_fov_visit" % e][k]))), (e, k)
+            elif kind == 1:
+                loc = env.plannerStep([arg])
+                assert not bool(env.loc_err.item())
+                assert np.array_equal(u32(loc[0]), u32(loc_obs(z["e%d_loc_bits" % e][k]))), (e, k)
+            else:
+                fov, loc, gr, lr, gdo, ldo, fg, act = env.step([arg])
+                assert not bool(env.loc_err.item())
+                assert u32(gr)[0] == np.float32(f64(grb)).view(np.uint32), (e, k)
+                assert u32(lr)[0] == np.float32(f64(orb)).view(np.uint32), (e, k)
+                assert (int(gdo.item()), int(ldo.item())) == (gd, ld), (e, k)
+                assert np.array_equal(u32(fov[0]), u32(fov_obs(z["e%d_fov_bits" % e][k], z["e%d_fov_visit" % e][k]))), (e, k)
+                assert np.array_equal(u32(loc[0]), u32(loc_obs(z["e%d_loc_bits" % e][k]))), (e, k)
+                assert fg.shape == (1, 1, 5, 5) and float(fg.sum()) == 1.0 and int(act.item()) == arg
+            st = env.get_state()[0].tolist()
+            assert (st[0], st[1]) == (bx, by), (e, k)
+            if k % 16 == 0 or kind == 0:
+                assert float(env.get_visit()[0].double().sum()) == z["e%d_visit_sum" % e][k], (e, k)
+            n_events += 1
+        assert env.stats()["steps"] == int((ev[:, 0] == 2).sum())
+        env.close()
+    assert n_events > 2500
+
+
+def test_v6_safe_goal_golden(lmz, golden_dir, oracle_mod):
+    """safeFovealGoal (lmaze_env_v6.py:505-523) with the reference's own np.random draws injected."""
+    z = np.load(os.path.join(golden_dir, "v6_traces.npz"))
+    rows = [str(r) for r in z["safe_layout"]]
+    k = [i for i in range(1, 6) if oracle_mod.layout_v2(i) == rows][0]
+    res = z["safe_results"]
+    n = len(res)
+    env = lmz.LmazeHierCuda(n, "v6", autoreset=False)
+    env.reset()
+    st = env.get_state()
+    st[:, 0] = torch.as_tensor(res[:, 0]); st[:, 1] = torch.as_tensor(res[:, 1])
+    st[:, 15] = k << 4
+    env.set_state(st)
+    draws = np.zeros((n, 40), np.int64)
+    pos = 0
+    for i, (bx, by, want, used) in enumerate(res):
+        chunk = z["safe_draws"][pos:pos + 40]
+        draws[i, :len(chunk)] = chunk
+        pos += int(used)
+    goals, used = env.safeFovealGoal(draws)
+    assert np.array_equal(goals.cpu().numpy().astype(np.int64), res[:, 2])
+    assert np.array_equal(used.cpu().numpy().astype(np.int64), res[:, 3])
+    # device RNG: always a non-wall cell of the window, and every non-wall cell comes up
+    env2 = lmz.LmazeHierCuda(8192, "v6", autoreset=False, seed=5)
+    env2.reset()
+    st = env2.get_state()
+    st[:, 0], st[:, 1], st[:, 15] = int(res[0, 0]), int(res[0, 1]), k << 4
+    env2.set_state(st)
+    g = env2.safeFovealGoal().cpu().numpy().astype(np.int64)
+    bx, by = int(res[0, 0]), int(res[0, 1])
+    free = np.array([rows[bx - 2 + a // 5][by - 2 + a % 5] != "W" for a in range(25)])
+    counts = np.bincount(g, minlength=25)
+    assert counts[~free].sum() == 0 and (counts[free] > 0).all()
+    expect = 8192 / free.sum()
+    assert (np.abs(counts[free] - expect) < 6 * np.sqrt(expect)).all()
+    env.close(); env2.close()
+
+
+# ---------------------------------------------------------------- batched parity vs the oracle
+def _drive(lmz, oracle_mod, n, iters, seed, autoreset):
+    env = lmz.LmazeHierCuda(n, "v5", seed=seed, autoreset=autoreset, env_id0=1000)
+    ora = oracle_mod.OracleHier(n, seed=seed, env_id0=1000)
+    rng = np.random.RandomState(seed)
+    fov = env.reset()
+    fov_ref = ora.reset()
+    assert np.array_equal(u32(fov), u32(fov_ref))
+    need_plan = np.ones(n, np.uint8)
+    n_err = n_gd = n_ld = 0
+    for it in range(iters):
+        goals = rng.randint(0, 25, size=n)
+        if need_plan.any():
+            loc = env.plannerStep(goals, mask=need_plan)
+            loc_ref, err_ref = ora.planner_step(goals, mask=need_plan)
+            m = need_plan.astype(bool)
+            assert np.array_equal(u32(loc)[m], u32(loc_ref)[m]), it
+            assert np.array_equal(env.loc_err.cpu().numpy()[m], err_ref[m].astype(bool)), it
+        acts = rng.randint(0, 4, size=n)
+        acts[rng.rand(n) < 0.05] = 7                       # unmatched action: no move (lmaze_env_v5.py:203-217)
+        fov, loc, gr, lr, gd, ld, fg, _ = env.step(torch.as_tensor(acts), goal_plane=False)
+        fov_ref, loc_ref, gr_ref, lr_ref, gd_ref, ld_ref, err_ref = ora.step(acts)
+        assert np.array_equal(u32(gr), u32(gr_ref)) and np.array_equal(u32(lr), u32(lr_ref)), it
+        assert np.array_equal(gd.cpu().numpy(), gd_ref.astype(bool)), it
+        assert np.array_equal(ld.cpu().numpy(), ld_ref.astype(bool)), it
+        gdm = gd_ref.astype(bool)
+        if autoreset and gdm.any():
+            # the framework's same-step reset: both rows show the new episode (Philox spawn, same spec both sides)
+            ora.reset(mask=gdm.astype(np.uint8), want_obs=False)
+            ora.render(mask=gdm.astype(np.uint8), fov=fov_ref, loc=loc_ref)
+            err_ref[gdm] = 0
+        assert np.array_equal(env.loc_err.cpu().numpy(), err_ref.astype(bool)), it
+        assert np.array_equal(u32(fov), u32(fov_ref)), it
+        assert np.array_equal(u32(loc), u32(loc_ref)), it            # IndexError rows are all zero on both sides
+        n_err += int(err_ref.sum()); n_gd += int(gdm.sum()); n_ld += int(ld_ref.sum())
+        if not autoreset and gdm.any():
+            fov = env.reset(mask=gdm)
+            fov_ref2 = ora.reset(mask=gdm.astype(np.uint8))
+            assert np.array_equal(u32(fov)[gdm], u32(fov_ref2)[gdm]), it
+        need_plan = (ld_ref | gd_ref).astype(np.uint8)
+        if it % 10 == 9 or it == iters - 1:
+            st = env.get_state().cpu().numpy()
+            ref = ora.export()
+            assert np.array_equal(st[:, :13], ref[:, :13]), it
+            assert np.array_equal(np.minimum(st[:, 13:15], 255), np.minimum(ref[:, 13:15], 255)), it
+            assert np.array_equal(st[:, 15], ref[:, 15]), it
+            assert np.array_equal(st[:, 16].astype(np.uint32), ora.episode), it
+            assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), it
+            assert np.array_equal(env.foveal_goal.cpu().numpy().astype(np.int32), ref[:, 12]), it
+    stats = env.stats(check_errors=False)
+    assert stats["steps"] == n * iters and stats["episodes"] == n_gd
+    env.close()
+    return n_err, n_gd, n_ld
+
+
+@pytest.mark.parametrize("autoreset", [False, True])
+def test_hier_batched_parity(lmz, oracle_mod, autoreset):
+    n_err, n_gd, n_ld = _drive(lmz, oracle_mod, 4099, 140, 11 + int(autoreset), autoreset)
+    assert n_err > 50 and n_gd > 500 and n_ld > 20000      # the IndexError rows, resets and planner cycles all occurred
+
+
+def test_hier_state_roundtrip_and_render(lmz, oracle_mod):
+    n = 1000
+    env = lmz.LmazeHierCuda(n, "v5", seed=3, autoreset=False)
+    ora = oracle_mod.OracleHier(n, seed=3)
+    env.reset(); ora.reset()
+    rng = np.random.RandomState(0)
+    for it in range(25):
+        g = rng.randint(0, 25, size=n)
+        m = np.ones(n, np.uint8) if it == 0 else (rng.rand(n) < 0.3).astype(np.uint8)
+        env.plannerStep(g, mask=m); ora.planner_step(g, mask=m)
+        a = rng.randint(0, 4, size=n)
+        env.step(a, goal_plane=False); ora.step(a)
+    st, vis = env.get_state(), env.get_visit()
+    fov_ref, loc_ref, err_ref = ora.render()
+    # a second handle restored from the checkpoint renders the same two tensors
+    env2 = lmz.LmazeHierCuda(n, "v5", seed=3, autoreset=False)
+    env2.set_state(st); env2.set_visit(vis)
+    env2.render_obs()
+    assert np.array_equal(u32(env2.obs), u32(fov_ref)) and np.array_equal(u32(env2.loc_obs), u32(loc_ref))
+    assert np.array_equal(env2.loc_err.cpu().numpy(), err_ref.astype(bool))
+    assert torch.equal(env2.get_state(), st)
+    # ... and continues identically
+    g = rng.randint(0, 25, size=n); a = rng.randint(0, 4, size=n)
+    for e_ in (env, env2):
+        e_.plannerStep(g); e_.step(a, goal_plane=False)
+    assert torch.equal(env.obs, env2.obs) and torch.equal(env.loc_obs, env2.loc_obs)
+    assert torch.equal(env.get_visit(), env2.get_visit()) and torch.equal(env.get_state(), env2.get_state())
+    env.close(); env2.close()
+
+
+def test_hier_compat_classes(lmz, golden_dir):
+    """LmazeEnv_v5 / LmazeEnv_v6 with the reference's exact call surface and return types."""
+    z = np.load(os.path.join(golden_dir, "v6_traces.npz"))
+    env = lmz.make("lmaze-v6")
+    assert type(env).__name__ == "LmazeEnv_v6"
+    ev = z["e0_events"]
+    for k, row in enumerate(ev[:120]):
+        kind, arg, grb, orb, gd, ld = (int(v) for v in row[:6])
+        if kind == 0:
+            fov = env.reset(spawn=[int(v) for v in row[8:13]])
+            assert isinstance(fov, np.ndarray) and fov.shape == (7, 35, 35) and fov.dtype == np.float32
+        elif kind == 1:
+            loc = env.plannerStep(arg)
+            assert loc.shape == (4, 35, 35) and np.array_equal(loc, loc_obs(z["e0_loc_bits"][k]))
+        else:
+            out = env.step(arg)
+            assert len(out) == 8
+            assert isinstance(out[2], float) and np.float64(out[2]).view(np.int64) == grb
+            assert isinstance(out[3], float) and np.float64(out[3]).view(np.int64) == orb
+            assert out[4] is bool(gd) and out[5] is bool(ld) and out[6].shape == (1, 5, 5) and out[7] == arg
+            assert np.array_equal(u32(out[0]), u32(fov_obs(z["e0_fov_bits"][k], z["e0_fov_visit"][k])))
+    assert 0 <= env.safeFovealGoal() <= 24
+    with pytest.raises(IndexError):
+        env.plannerStep(25)
+    env.close()
+    vec = lmz.make("lmaze-vec-v5", num_envs=64)
+    assert type(vec).__name__ == "LmazeHierCuda" and vec.reset().shape == (64, 7, 35, 35)
+    with pytest.raises(ValueError):
+        lmz.LmazeVecCuda(4, "v5")
+    vec.close()
