@@ -9,14 +9,14 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "../../include/lmaze_b200.h"
 #include "lmz_kernels.cuh"
-#include "lmz_v2.cuh"
-#include "lmz_v5.cuh"
+#include "lmz_fov.cuh"
 
 namespace {
 
@@ -126,21 +126,34 @@ void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand
   }
 }
 
+// One table entry per float4 of a run of x7-upsampled 5x5 planes (lmz_fov.cuh): the four floats take at most two
+// different cell values -- the first k from value A, the rest from value B.  entry = A | B << 10 | k << 20, A and B
+// indexing [env in group][slot][cell] value planes.  `slot_of(channel)` maps an obs channel to its value plane.
+template <class V, class SlotOf>
+void build_f4_lut(uint32_t *lut, uint32_t floats_per_env, uint32_t n_entries, SlotOf slot_of) {
+  auto code = [&](uint32_t g) -> uint32_t {
+    const uint32_t env = g / floats_per_env, r = g % floats_per_env;
+    const uint32_t c = r / (V::S * V::S), row = (r / V::S) % V::S, col = r % V::S;
+    return env * V::VALS + (uint32_t)slot_of((int)c) * 25u + (row / V::E) * V::F + col / V::E;   // lmaze_env_v2.py:197-203
+  };
+  for (uint32_t q = 0; q < n_entries; ++q) {
+    const uint32_t c[4] = {code(4 * q), code(4 * q + 1), code(4 * q + 2), code(4 * q + 3)};
+    uint32_t k = 1;
+    while (k < 4 && c[k] == c[0]) ++k;
+    const uint32_t b = k < 4 ? c[k] : c[0];
+    for (uint32_t j = k; j < 4; ++j)
+      if (c[j] != b) { fprintf(stderr, "lmaze_b200: float4 table: more than two values in one float4\n"); abort(); }
+    lut[q] = c[0] | (b << 10) | (k << 20);
+  }
+}
+
 template <class V>
 void build_blob_fov(std::vector<unsigned char> &blob) {
   blob.assign(V::BLOB_BYTES, 0);
-  // (slot, cell) of every float of an env's (C,35,35) image: the x7 upsample of lmaze_env_v2.py:197-203.
-  // slot = which per-env plane feeds the channel: bit planes 0 free, 1 goal, 2 action, 3 prev free,
-  // 4 prev goal; float planes 5 visit, 6 visit at the previous window (v4 channel order:
-  // crop(free, goal, visit), action, retStatelast(free, goal, visit) -- lmaze_env_v4.py:37-40,236-239).
-  static const int slot_v2[5] = {0, 1, 2, 3, 4};
-  static const int slot_v4[7] = {0, 1, 5, 2, 3, 4, 6};
-  const int *slot = (V::C == 7) ? slot_v4 : slot_v2;
-  for (int c = 0; c < V::C; ++c)
-    for (int row = 0; row < V::S; ++row)
-      for (int col = 0; col < V::S; ++col)
-        blob[V::LUT_OFF + (c * V::S + row) * V::S + col] =
-            (unsigned char)((slot[c] << 5) | ((row / V::E) * V::F + col / V::E));
+  // the obs channels ARE the first C value planes (v2: free, goal, action, prev free, prev goal; v4/v5:
+  // crop(free, goal, visit), action / fovealGoal, retStatelast(free, goal, visit)); a group of 4 envs = OBS_FLOATS float4s
+  build_f4_lut<V>(reinterpret_cast<uint32_t *>(blob.data() + V::LUT_OFF), V::OBS_FLOATS, V::OBS_FLOATS,
+                  [](int c) { return c; });
   uint32_t *rowbits = reinterpret_cast<uint32_t *>(blob.data() + V::ROWBITS_OFF);
   uint16_t *gcand = reinterpret_cast<uint16_t *>(blob.data() + V::GCAND_OFF);
   uint16_t *bcand = reinterpret_cast<uint16_t *>(blob.data() + V::BCAND_OFF);
@@ -169,13 +182,10 @@ void build_blob_fov(std::vector<unsigned char> &blob) {
 void build_blob_v5(std::vector<unsigned char> &blob) {
   using V = lmz::V5;
   build_blob_fov<V>(blob);
-  // local obs channels: free crop (bit plane 0), ball rel. fovea_x1 (5), previous ball (6), fovealGoal (2)
-  static const int plane[4] = {0, 5, 6, 2};
-  for (int c = 0; c < V::CL; ++c)
-    for (int row = 0; row < V::S; ++row)
-      for (int col = 0; col < V::S; ++col)
-        blob[V::LOCLUT_OFF + (c * V::S + row) * V::S + col] =
-            (unsigned char)((plane[c] << 5) | ((row / V::E) * V::F + col / V::E));
+  // local obs channels (lmaze_env_v5.py:360-368): free crop (value plane 0), ball rel. fovea_x1 (7), previous ball (8),
+  // fovealGoal (3); one env row = 1,225 float4s exactly
+  build_f4_lut<V>(reinterpret_cast<uint32_t *>(blob.data() + V::LOCLUT_OFF), V::LOC_FLOATS, V::LOC_FLOATS / 4,
+                  [](int c) { static const int plane[4] = {0, 7, 8, 3}; return plane[c]; });
   uint16_t *xcell = reinterpret_cast<uint16_t *>(blob.data() + V::XCELL_OFF);
   for (int L = 0; L < V::NLAYOUT; ++L) {
     char cells[18 * 18];
@@ -352,7 +362,8 @@ int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
   if (configured_dev != h->cfg.device) {
-    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, W::BLOB_BYTES));
+    LMZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM_BYTES));
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, W::SMEM_BYTES));
     if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal env kernel does not fit on an SM");
     configured_dev = h->cfg.device;
   }
@@ -360,7 +371,7 @@ int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
   if (grid > units) grid = units;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, THREADS, W::BLOB_BYTES, s>>>(p);
+  kern<<<(unsigned)grid, THREADS, W::SMEM_BYTES, s>>>(p);
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
@@ -368,45 +379,17 @@ int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 
 template <class W>
 int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  // CTA size (tools/fov_sweep.py): v2 renders best with one 1024-thread CTA per SM (7.2 TB/s); v4 wants two
-  // 512-thread CTAs per SM so that one CTA's producer warps overlap the other's render (5.9 TB/s)
+  if (W::HAS_LOC && !h->local_bound)
+    return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
+  // CTA size (tools/fov_sweep.py, tools/hier_bench.py)
   const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::NVIS > 0 ? 512 : 1024);
   if (t == 256) return launch_fov_t<W, 256>(h, p, s);
   if (t == 1024) return launch_fov_t<W, 1024>(h, p, s);
   return launch_fov_t<W, 512>(h, p, s);
 }
 
-template <int THREADS>
-int launch_v5_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  using W = lmz::V5;
-  auto kern = lmz::lmz_env_v5_kernel<W, THREADS>;
-  static thread_local int configured_dev = -1;
-  static thread_local int ctas_per_sm = 1;
-  if (configured_dev != h->cfg.device) {
-    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, W::BLOB_BYTES));
-    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "planner/actor env kernel does not fit on an SM");
-    configured_dev = h->cfg.device;
-  }
-  const int64_t units = p.tile_end - p.tile_begin;
-  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
-  if (grid > units) grid = units;
-  if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, THREADS, W::BLOB_BYTES, s>>>(p);
-  LMZ_CUDA(cudaGetLastError());
-  h->launches += 1;
-  return LMZ_OK;
-}
-
-int launch_v5(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (!h->local_bound) return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
-  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : 512;
-  if (t == 256) return launch_v5_t<256>(h, p, s);
-  if (t == 1024) return launch_v5_t<1024>(h, p, s);
-  return launch_v5_t<512>(h, p, s);
-}
-
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (h->cfg.variant == LMZ_V5) return launch_v5(h, p, s);
+  if (h->cfg.variant == LMZ_V5) return launch_fov<lmz::V5>(h, p, s);
   if (h->cfg.variant == LMZ_V2) return launch_fov<lmz::V2>(h, p, s);
   if (h->cfg.variant == LMZ_V4) return launch_fov<lmz::V4>(h, p, s);
   if (h->cfg.variant == LMZ_V0) return launch_env_v<lmz::V0>(h, p, s);

@@ -1,0 +1,219 @@
+// lmz_fov.cuh -- the fused reset / step / render kernel of the FOVEAL variants: lmaze-v2, lmaze-v4
+// (lmz_v2.cuh) and the planner / actor env lmaze-v5 / v6 (lmz_v5.cuh, which adds plannerStep and a second,
+// "local" observation tensor).
+//
+// An observation here is C planes of 5x5 values, each upsampled x7 to 35x35 floats
+// (lmaze_env_v2.py:197-203, lmaze_env_v4.py:241-247, lmaze_env_v5.py:337-343,372-378): 6,125 / 8,575
+// floats per env, NOT a multiple of 4, so an env row is not 16-byte aligned -- but four consecutive rows
+// are.  The render therefore works on GROUPS of 4 envs: a group's image is OBS_FLOATS float4s, and because
+// every cell value repeats 7 times along a row, the four floats of one float4 take at most TWO different
+// cell values (a prefix of k floats from cell A, the rest from cell B).  One host-built table entry per
+// float4 -- A:10 | B:10 | k:3, A and B indexing the group's [4][NSLOT][25] value planes -- turns the whole
+// render into: 1 table load, 2 value loads, 3 selects, 1 streaming 128-bit store.  (The first version looked
+// every FLOAT up through a byte table and was issue-bound at 91 % issue-slot utilisation, 5.8 TB/s on v4.)
+//
+// CTA organisation: tiles of 32 envs are handed out by the global work counter.  Warp 0 runs the tile's 32
+// transitions (one env per lane, state in registers) and expands each env's 25-bit planes into float planes
+// in shared memory; for the variants with a float visit layer (v4, v5) warps 0-3 are dedicated PRODUCERS
+// that also make the coalesced read-modify-write pass over the tile's 32 x 324 visit floats and drop the
+// two 5x5 visit crops into the same planes -- one tile ahead of the other warps, which stream the previous
+// tile's rows out.  Everything is double buffered; one __syncthreads per tile.
+#pragma once
+#include "lmz_v2.cuh"
+#include "lmz_v5.cuh"
+
+#ifndef LMZ_VISIT_UN
+#define LMZ_VISIT_UN 8
+#endif
+#ifndef LMZ_VISIT_PROD
+#define LMZ_VISIT_PROD 128
+#endif
+
+namespace lmz {
+
+template <int ID, int C>
+__device__ __forceinline__ FovLane<5> fov_lane(const Fov<ID, C> *, const KParams &p, int64_t e,
+                                               const FovTables<Fov<ID, C>> &t, const unsigned char *) {
+  return v2_lane<Fov<ID, C>>(p, e, t);
+}
+__device__ __forceinline__ V5Lane fov_lane(const V5 *, const KParams &p, int64_t e, const FovTables<V5> &t,
+                                           const unsigned char *smem) {
+  return v5_lane<V5>(p, e, t, smem);
+}
+
+template <class W, int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_info[2][32];
+  __shared__ uint32_t s_flags[2][2];         // [buf][0 obs, 1 local obs]: bit l = env l of the tile is written
+  __shared__ long long s_tile[2];
+  constexpr int PROD = (W::NVIS > 0) ? (THREADS >= 512 ? LMZ_VISIT_PROD : 64) : 0;   // threads that never render
+  constexpr int CTHREADS = THREADS - PROD;
+  static_assert(CTHREADS >= 32, "need at least one rendering warp");
+  static_assert((uint32_t)CTHREADS < W::OBS_FLOATS, "index stepping assumes fewer threads than entries");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_blob<W>(smem, &bar, p.blob);
+  const FovTables<W> t(smem);
+  float *vals = reinterpret_cast<float *>(smem + W::BLOB_BYTES);          // [2][32][NSLOT][25]
+  const int64_t tiles = p.tile_end;
+  const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
+  WarpStats ws;
+
+  auto produce = [&](int buf) {              // warp 0 only
+    int64_t tl = 0;
+    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
+    tl = __shfl_sync(0xffffffffu, tl, 0);
+    const int64_t e = tl * 32 + lane;
+    const bool valid = tl < tiles && e < p.n;
+    FovLane<W::NBIT> v;
+    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
+    v.rfov = false; v.rloc = false;
+    if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, smem);
+    if (p.mode == MODE_STEP) ws.add(valid, v.o);
+    if (valid && (v.rfov || v.rloc)) {       // 25-bit planes -> float planes (lane stride VALS is odd: no bank conflicts)
+      float *mv = vals + (buf * 32 + lane) * W::VALS;
+#pragma unroll
+      for (int b = 0; b < W::NBIT; ++b) {
+        const uint32_t m = v.mask[b];
+        float *pl = mv + W::bit_slot(b) * 25;
+#pragma unroll
+        for (int c = 0; c < 25; ++c) pl[c] = ((m >> c) & 1u) ? 1.0f : 0.0f;
+      }
+    }
+    s_info[buf][lane] = valid ? v.info : 0u;
+    const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
+    const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
+    if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = tl; }
+  };
+  // visit layers of one tile's 32 envs: 32 x 324 consecutive floats, coalesced pass by the PROD producer
+  // threads: state[2] = (state[2] + visitMap) / 2 in float64, stored as float32
+  // (lmaze_env_v4.py:116-119,211-214; lmaze_env_v5.py:308-312)
+  auto visit_pass = [&](int buf) {
+    const int64_t tile = s_tile[buf];
+    if (tile >= tiles || !need_visit) return;
+    const int64_t e0 = tile * 32;
+    const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
+    float *vis = p.visit + e0 * (W::G * W::G);
+    float *tv = vals + buf * 32 * W::VALS;
+    constexpr uint32_t NP = PROD > 0 ? PROD : 1, PER = (32 * W::G * W::G + NP - 1) / NP, UN = LMZ_VISIT_UN;
+    for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
+      float vv[UN];
+      uint32_t live = 0;     // bit j: element j of this batch is loaded / updated
+#pragma unroll
+      for (uint32_t j = 0; j < UN; ++j) {                            // UN independent loads in flight per thread
+        const uint32_t idx = tid + (k0 + j) * NP;
+        vv[j] = 0.0f;
+        if (idx >= cells) continue;
+        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
+        const int x = cell / W::G, y = cell - x * W::G;
+        const uint32_t info = s_info[buf][env];
+        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+        const uint32_t op = (info >> 20) & 3u;
+        // a layer that is only looked at (v5 while the local episode runs) is read at the two windows only;
+        // one that is re-zeroed is not read at all
+        const bool out_cur = ((unsigned)(x - bx + 2) >= 5u) | ((unsigned)(y - by + 2) >= 5u);
+        const bool out_prev = ((unsigned)(x - px + 2) >= 5u) | ((unsigned)(y - py + 2) >= 5u);
+        if (op == 0 && out_cur && out_prev) continue;
+        live |= 1u << j;
+        if (op != 2) vv[j] = __ldcs(vis + idx);
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < UN; ++j) {
+        if (!((live >> j) & 1u)) continue;
+        const uint32_t idx = tid + (k0 + j) * NP;
+        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
+        const int x = cell / W::G, y = cell - x * W::G;
+        const uint32_t info = s_info[buf][env];
+        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+        const uint32_t op = (info >> 20) & 3u;
+        const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
+        const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
+        float v = vv[j];
+        if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
+        else if (op == 2) v = W::visit_reset(in_cur);
+        if (op) __stcs(vis + idx, v);
+        if (in_cur) tv[env * W::VALS + W::VIS_SLOT0 * 25 + dx * 5 + dy] = v;
+        if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) tv[env * W::VALS + W::VIS_SLOT1 * 25 + qx * 5 + qy] = v;
+      }
+    }
+  };
+  auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };
+  auto pick = [](uint32_t en, const float *gv) -> uint4 {           // one table entry -> the four floats of a float4
+    const uint32_t va = __float_as_uint(gv[en & 1023u]), vb = __float_as_uint(gv[(en >> 10) & 1023u]), k = en >> 20;
+    return make_uint4(va, k > 1 ? va : vb, k > 2 ? va : vb, k > 3 ? va : vb);
+  };
+
+  if (warp == 0) produce(0);
+  if (W::NVIS > 0 && tid < PROD) { producers_sync(); visit_pass(0); }
+  for (int buf = 0;; buf ^= 1) {
+    __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
+    const int64_t tile = s_tile[buf];
+    if (tile >= tiles) break;
+    if (W::NVIS > 0 && tid < PROD) {
+      if (warp == 0) produce(buf ^ 1);
+      producers_sync();
+      visit_pass(buf ^ 1);
+      continue;
+    }
+    if (W::NVIS == 0 && warp == 0) produce(buf ^ 1);
+    const int ctid = tid - PROD;
+    const float *tv = vals + buf * 32 * W::VALS;
+    const int64_t row0 = tile * 32 - p.win_lo;                     // obs row of the tile's first env
+    uint32_t flags = s_flags[buf][0];
+    if (flags) {
+      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + row0 * (int64_t)W::OBS_BYTES;
+      constexpr uint32_t TOTAL = 8 * W::OBS_FLOATS;                // float4s of the tile = 8 groups x OBS_FLOATS entries
+      uint32_t ent = ctid, grp = 0;
+      if (flags == 0xffffffffu && (row0 & 3) == 0) {
+        // fast path: the whole tile is rendered and 16-byte aligned
+#pragma unroll 4
+        for (uint32_t q = ctid; q < TOTAL; q += CTHREADS) {
+          st_stream_v4(dst + ((size_t)q << 4), pick(t.lut[ent], tv + grp * 4 * W::VALS));
+          ent += CTHREADS;
+          if (ent >= W::OBS_FLOATS) { ent -= W::OBS_FLOATS; ++grp; }
+        }
+      } else {
+        // partial tile (batch tail, reset mask, render-window edge): guarded 32-bit stores
+        for (uint32_t q = ctid; q < TOTAL; q += CTHREADS) {
+          const uint32_t en = t.lut[ent], a = en & 1023u, b = (en >> 10) & 1023u, k = en >> 20;
+          const float *gv = tv + grp * 4 * W::VALS;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t code = j < k ? a : b, env = grp * 4 + code / W::VALS;
+            if ((flags >> env) & 1u)
+              __stcs(reinterpret_cast<unsigned int *>(dst) + ((size_t)q * 4 + j), __float_as_uint(gv[code]));
+          }
+          ent += CTHREADS;
+          if (ent >= W::OBS_FLOATS) { ent -= W::OBS_FLOATS; ++grp; }
+        }
+      }
+    }
+    if (W::HAS_LOC) {
+      // local observation (lmaze_env_v5.py:356-380): every env row is 16-byte aligned (19,600 = 16 x 1,225)
+      flags = s_flags[buf][1];
+      if (flags) {
+        constexpr uint32_t PER = W::LOC_FLOATS / 4 > 0 ? W::LOC_FLOATS / 4 : 1;
+        const uint32_t *loclut = reinterpret_cast<const uint32_t *>(smem + W::LOCLUT_OFF);
+        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs2) + row0 * (int64_t)(W::LOC_FLOATS * 4);
+        uint32_t ent = ctid % PER, env = ctid / PER;
+#pragma unroll 4
+        for (uint32_t q = ctid; q < 32 * PER; q += CTHREADS) {
+          if ((flags >> env) & 1u) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);                  // IndexError in the reference: the row is all zero
+            if (!((s_info[buf][env] >> 22) & 1u)) v = pick(loclut[ent], tv + env * W::VALS);
+            st_stream_v4(dst + ((size_t)q << 4), v);
+          }
+          ent += CTHREADS;
+          while (ent >= PER) { ent -= PER; ++env; }
+        }
+      }
+    }
+  }
+  if (warp == 0) {
+    if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+    if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
+  }
+}
+
+}  // namespace lmz

@@ -6,12 +6,12 @@
 //     memory with the same single bulk async (TMA) load as the other variants' blob;
 //   * Discrete(25) "teleport the fovea" actions (:39,151-169), reward by the cell the fovea was
 //     pointed at (:175-180), done at reward 100 or stepCount > 50 (:222);
-//   * the observation is five 5x5 BIT planes -- free-cell crop and goal crop around the ball, the
+//   * the observation is five 5x5 planes -- free-cell crop and goal crop around the ball, the
 //     action one-hot, and the previous step's two crops (:185-193) -- each upsampled x7 to 35x35
 //     floats: 6,125 floats = 24,500 B per env.  24,500 is not a multiple of 16, so neither bulk
 //     copies nor per-env vector stores are possible; instead a TILE of 32 envs (784,000 B, which
-//     IS 16-byte aligned) is written as one flat run of float4 stores, every float looked up as
-//     bit `cell` of mask `c` of env `e` through a 6,125-entry (c,cell) table in shared memory.
+//     IS 16-byte aligned) is written as one flat run of float4 stores by the generic foveal kernel
+//     in lmz_fov.cuh, which this file feeds with the per-env transition (v2_lane).
 #pragma once
 #include "lmz_kernels.cuh"
 
@@ -25,21 +25,32 @@ struct Fov {
   static constexpr int NLAYOUT = 5, MAX_CAND = 80;
   static constexpr int NBIT = 5;                                       // bit planes: free, goal, action, prev free, prev goal
   static constexpr int NVIS = (C_ == 7) ? 2 : 0;                       // v4: float visit crop at the ball and at the previous window
+  static constexpr bool HAS_LOC = false;                               // no second observation tensor
+  static constexpr int NSLOT = C_;                                     // 5x5 value planes per env = obs channels
+  static constexpr int VALS = NSLOT * 25;
+  static constexpr int VIS_SLOT0 = 2, VIS_SLOT1 = 6;                   // v4 channel order: crop(free, goal, visit), action,
+                                                                       // retStatelast(free, goal, visit) -- lmaze_env_v4.py:37-40,236-239
+  __host__ __device__ static constexpr int bit_slot(int b) {           // channel fed by bit plane b
+    return C_ == 7 ? (b < 2 ? b : b + 1) : b;
+  }
+  __device__ static __forceinline__ float visit_reset(bool in_cur) { return in_cur ? 0.5f : 0.0f; }   // zeros, then :110-113
   static constexpr bool MAZE_FIRST = (ID_ == 4);                       // v4 re-rolls the maze BEFORE drawing goal/ball (:91-98)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                    // 6,125 (v2) / 8,575 (v4)
   static constexpr uint32_t OBS_BYTES = OBS_FLOATS * 4;                // 24,500 / 34,300
-  static constexpr uint32_t TILE_F4 = 32 * OBS_FLOATS / 4;             // float4 per 32-env tile (tile is 16-B aligned)
+  static constexpr uint32_t LOC_FLOATS = 0;
   static constexpr int STEP_LIMIT = 50;                                // lmaze_env_v2.py:43, lmaze_env_v4.py:48
   static constexpr uint32_t STEP_SAT = 63;
   // blob layout (bytes)
-  static constexpr uint32_t LUT_OFF = 0;                               // u8 [OBS_FLOATS]: (slot << 5) | cell
-  static constexpr uint32_t ROWBITS_OFF = align16(OBS_FLOATS);         // u32 [5][18]: bit y = cell (x,y) is B/S/X
+  static constexpr uint32_t LUT_OFF = 0;                               // u32 [OBS_FLOATS]: one entry per float4 of a 4-env group (lmz_fov.cuh)
+  static constexpr uint32_t LOCLUT_OFF = align16(OBS_FLOATS * 4);
+  static constexpr uint32_t ROWBITS_OFF = LOCLUT_OFF;                  // u32 [5][18]: bit y = cell (x,y) is B/S/X
   static constexpr uint32_t CLS_OFF = ROWBITS_OFF + align16(NLAYOUT * G * 4);     // u8 [5][324]
   static constexpr uint32_t GCAND_OFF = CLS_OFF + align16(NLAYOUT * G * G);       // u16 [5][80] cells not in {W,S}
   static constexpr uint32_t BCAND_OFF = GCAND_OFF + NLAYOUT * MAX_CAND * 2;       // u16 [5][80] cells not in {W,X}
   static constexpr uint32_t BRANK_OFF = BCAND_OFF + NLAYOUT * MAX_CAND * 2;       // i8 [5][324] index in BCAND or -1
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5]
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;   // + the double-buffered per-env value planes
 };
 using V2 = Fov<2, 5>;
 using V4 = Fov<4, 7>;
@@ -65,14 +76,14 @@ __host__ __device__ inline void v2_pack(const V2Regs &r, uint32_t &s, uint32_t &
 
 template <class W>
 struct FovTables {
-  const uint8_t *lut;
+  const uint32_t *lut;
   const uint32_t *rowbits;
   const uint8_t *cls;
   const uint16_t *gcand, *bcand;
   const int8_t *brank;
   const uint8_t *count;      // ng[0..4], nb[5..9]
   __device__ __forceinline__ explicit FovTables(const unsigned char *smem)
-      : lut(smem + W::LUT_OFF), rowbits(reinterpret_cast<const uint32_t *>(smem + W::ROWBITS_OFF)),
+      : lut(reinterpret_cast<const uint32_t *>(smem + W::LUT_OFF)), rowbits(reinterpret_cast<const uint32_t *>(smem + W::ROWBITS_OFF)),
         cls(smem + W::CLS_OFF), gcand(reinterpret_cast<const uint16_t *>(smem + W::GCAND_OFF)),
         bcand(reinterpret_cast<const uint16_t *>(smem + W::BCAND_OFF)),
         brank(reinterpret_cast<const int8_t *>(smem + W::BRANK_OFF)), count(smem + W::COUNT_OFF) {}
@@ -137,11 +148,15 @@ __device__ __forceinline__ void v2_respawn(V2Regs &r, const KParams &p, int64_t 
   episode += 1;
 }
 
-struct V2Lane {
+// What one env hands to the renderer: NB 25-bit planes, and where / how its visit layer is touched.
+template <int NB>
+struct FovLane {
   LaneOut o;
-  uint32_t mask[5];         // the five 25-bit planes: free, goal, action, previous free, previous goal
-  uint32_t info;            // x:5 | y:5 | px:5 | py:5 | visit op:2  (v4: 0 keep, 1 step update, 2 reset)
+  uint32_t mask[NB];
+  uint32_t info;            // x:5 | y:5 | px:5 | py:5 | visit op:2 (0 read only, 1 average, 2 reset) | local-obs error:1
+  bool rfov, rloc;          // which observation rows this call writes
 };
+using V2Lane = FovLane<5>;  // free, goal, action, previous free, previous goal
 
 template <class W>
 __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const FovTables<W> &t) {
@@ -196,149 +211,13 @@ __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const Fov
   o.st = s;
   if (p.mode != MODE_RENDER) { p.state[e] = s; p.goal_count[e] = aux; }
   o.render = o.render && p.obs != nullptr && e >= p.win_lo && e < p.win_lo + p.win_n;
+  out.rfov = o.render; out.rloc = false;
   out.mask[0] = v2_free_crop<W>(t, r.L, r.x, r.y);                                   // :185-186
   out.mask[1] = v2_goal_crop(r.x, r.y, r.gx, r.gy);
   out.mask[2] = r.a >= 0 ? (1u << r.a) : 0u;                                         // :136-137 / :87
   out.mask[3] = v2_free_crop<W>(t, r.L, r.px, r.py);                                 // retStatelast (:193)
   out.mask[4] = v2_goal_crop(r.px, r.py, r.gx, r.gy);
   return out;
-}
-
-// CTA-cooperative fused reset / step / render for the foveal variants (v2, v4).  Warp 0 grabs a 32-env
-// tile from the global work counter, runs the transitions (one env per lane) and parks the five 25-bit
-// planes of every env in shared memory; all threads then write the tile's contiguous bytes as float4
-// stores (double-buffered: warp 0 is already on the next tile).  v4 adds one cooperative pass per tile
-// over the envs' float visit layers: state[2] = (state[2] + visitMap) / 2 in float64, stored as float32
-// (lmaze_env_v4.py:116-119,211-214), capturing the 5x5 crops at the ball and at the previous window.
-template <class W, int THREADS>
-__global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t s_mask[2][32 * W::NBIT];
-  __shared__ uint32_t s_info[2][32];
-  __shared__ float s_vis[W::NVIS > 0 ? 2 * 32 * 50 : 1];   // [buf][env][0: at the ball, 1: at the previous window][25]
-  __shared__ uint32_t s_flags[2];            // bit l: env l of the tile is to be rendered
-  __shared__ long long s_tile[2];
-  // v2: warp 0 produces (transitions) and then renders with everybody else.
-  // v4: warps 0-3 are PRODUCERS -- warp 0 runs the next tile's transitions, then all four update that
-  //     tile's float visit layers -- while the remaining warps render the current tile, so the visit
-  //     pass (global read-modify-write latency) is hidden behind the obs stores.
-  constexpr int PROD = (W::NVIS > 0) ? (THREADS >= 512 ? 128 : 64) : 0;   // threads that never render
-  constexpr int CTHREADS = THREADS - PROD;
-  static_assert(CTHREADS >= 32, "need at least one rendering warp");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  stage_blob<W>(smem, &bar, p.blob);
-  const FovTables<W> t(smem);
-  const int64_t tiles = p.tile_end;
-  WarpStats ws;
-
-  auto produce = [&](int buf) {              // warp 0 only
-    int64_t tl = 0;
-    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
-    tl = __shfl_sync(0xffffffffu, tl, 0);
-    const int64_t e = tl * 32 + lane;
-    const bool valid = tl < tiles && e < p.n;
-    V2Lane v;
-    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
-#pragma unroll
-    for (int c = 0; c < W::NBIT; ++c) v.mask[c] = 0;
-    if (valid) v = v2_lane<W>(p, e, t);
-    if (p.mode == MODE_STEP) ws.add(valid, v.o);
-#pragma unroll
-    for (int c = 0; c < W::NBIT; ++c) s_mask[buf][lane * W::NBIT + c] = v.mask[c];
-    s_info[buf][lane] = valid ? v.info : 0u;
-    const unsigned fl = __ballot_sync(0xffffffffu, valid && v.o.render);
-    if (lane == 0) { s_flags[buf] = fl; s_tile[buf] = tl; }
-  };
-  // v4 visit layers of one tile's 32 envs: 32 x 324 consecutive floats, coalesced read-modify-write by
-  // the PROD producer threads: state[2] = (state[2] + visitMap) / 2 in float64 (lmaze_env_v4.py:211-214)
-  auto visit_pass = [&](int buf) {
-    const int64_t tile = s_tile[buf];
-    if (tile >= tiles) return;
-    const int64_t e0 = tile * 32;
-    const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
-    float *vis = p.visit + e0 * (W::G * W::G);
-    float *sv = s_vis + buf * (32 * 50);
-    constexpr uint32_t NP = PROD > 0 ? PROD : 1, PER = (32 * W::G * W::G + NP - 1) / NP, UN = 8;
-    for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
-      float vv[UN];
-#pragma unroll
-      for (uint32_t j = 0; j < UN; ++j) {                            // UN independent loads in flight per thread
-        const uint32_t idx = tid + (k0 + j) * NP;
-        vv[j] = (idx < cells) ? __ldcs(vis + idx) : 0.0f;
-      }
-#pragma unroll
-      for (uint32_t j = 0; j < UN; ++j) {
-        const uint32_t idx = tid + (k0 + j) * NP;
-        if (idx >= cells) continue;
-        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-        const int x = cell / W::G, y = cell - x * W::G;
-        const uint32_t info = s_info[buf][env];
-        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-        const uint32_t op = info >> 20;
-        const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-        const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-        float v = vv[j];
-        if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
-        else if (op == 2) v = in_cur ? 0.5f : 0.0f;                 // fresh zeros, then the same update (:106-113)
-        if (op) __stcs(vis + idx, v);
-        if (in_cur) sv[env * 50 + dx * 5 + dy] = v;
-        if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) sv[env * 50 + 25 + qx * 5 + qy] = v;
-      }
-    }
-  };
-  auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };
-
-  if (warp == 0) produce(0);
-  if (W::NVIS > 0 && tid < PROD) { producers_sync(); visit_pass(0); }
-  for (int buf = 0;; buf ^= 1) {
-    __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
-    const int64_t tile = s_tile[buf];
-    if (tile >= tiles) break;
-    if (W::NVIS > 0 && tid < PROD) {
-      if (warp == 0) produce(buf ^ 1);
-      producers_sync();
-      visit_pass(buf ^ 1);
-      continue;
-    }
-    if (W::NVIS == 0 && warp == 0) produce(buf ^ 1);
-    const uint32_t flags = s_flags[buf];
-    if (flags == 0) continue;
-    const int ctid = tid - PROD;
-    const uint32_t *mk = s_mask[buf];
-    const float *sv = s_vis + (W::NVIS > 0 ? buf * (32 * 50) : 0);
-    const int64_t row0 = tile * 32 - p.win_lo;                     // obs row of the tile's first env
-    float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)W::OBS_FLOATS;
-    auto value = [&](uint32_t env, uint32_t r) -> uint32_t {       // float bits of obs[env][r]
-      const uint32_t code = t.lut[r], slot = code >> 5, cell = code & 31u;
-      if (W::NVIS > 0 && slot >= (uint32_t)W::NBIT) return __float_as_uint(sv[env * 50 + (slot - W::NBIT) * 25 + cell]);
-      return ((mk[env * W::NBIT + slot] >> cell) & 1u) ? 0x3f800000u : 0u;
-    };
-    if (flags == 0xffffffffu && (row0 & 3) == 0) {
-      // fast path: the whole tile is rendered and 16-byte aligned -> TILE_F4 float4 stores
-      for (uint32_t q = ctid; q < W::TILE_F4; q += CTHREADS) {
-        uint32_t g = q * 4, env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
-        uint4 v;
-        uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          w[k] = value(env, r);
-          if (++r == W::OBS_FLOATS) { r = 0; ++env; }
-        }
-        st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), v);
-      }
-    } else {
-      // partial tile (batch tail, reset mask, render-window edge): guarded 32-bit stores
-      for (uint32_t g = ctid; g < 32 * W::OBS_FLOATS; g += CTHREADS) {
-        const uint32_t env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
-        if ((flags >> env) & 1u) __stcs(reinterpret_cast<unsigned int *>(dst) + g, value(env, r));
-      }
-    }
-  }
-  if (warp == 0) {
-    if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
-    if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
-  }
 }
 
 // get/set_state for v2.  cols: x, y, goal_x, goal_y, step_count, layout, aux, episode

@@ -14,6 +14,7 @@
 //     ball relative to the planner-time fovea WITH numpy's negative-index wrap-around, fovealGoal,
 //     :356-380).  Both are x7 upsampled and written as flat runs of float4 per 32-env tile, like v2/v4;
 //   * ~80 bits of per-env state in three packed words.
+// The kernel itself is the generic foveal kernel of lmz_fov.cuh; this file supplies the per-env logic.
 // Where the reference raises IndexError (ball 3 cells right of / below the planner-time fovea, :365-366)
 // the local obs row is written as all zeros, loc_err[e] = 1 and the error counter is bumped.
 #pragma once
@@ -29,19 +30,26 @@ struct V5 {
   static constexpr int NLAYOUT = 5, MAX_CAND = 80;
   static constexpr int NBIT = 7;      // bit planes: free, goal, fovealGoal, last free, last goal, ball rel, previous ball rel
   static constexpr int NVIS = 2;      // float planes: visit crop at the ball, visit crop at retStatelast's window
+  static constexpr bool HAS_LOC = true;
+  // 5x5 value planes per env: slots 0-6 are the foveal channels -- crop(free, goal, visit), fovealGoal,
+  // retStatelast(free, goal, visit) (:314-333) -- 7/8 the ball / previous ball relative to the planner-time fovea;
+  // the local obs (:356-380) is slots 0, 7, 8, 3
+  static constexpr int NSLOT = 9;
+  static constexpr int VALS = NSLOT * 25;
+  static constexpr int VIS_SLOT0 = 2, VIS_SLOT1 = 6;
+  __host__ __device__ static constexpr int bit_slot(int b) { return b < 2 ? b : (b < 5 ? b + 1 : b + 2); }
+  __device__ static __forceinline__ float visit_reset(bool) { return 0.0f; }   // self.state = zeros (:134), no averaging
   static constexpr bool MAZE_FIRST = true;                                   // reset(): setGrid() first (:104,115-116)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                          // 8,575 (foveal)
   static constexpr uint32_t OBS_BYTES = OBS_FLOATS * 4;                      // 34,300
   static constexpr uint32_t LOC_FLOATS = CL * S * S;                         // 4,900 (local)
   static constexpr uint32_t LOC_BYTES = LOC_FLOATS * 4;                      // 19,600
-  static constexpr uint32_t TILE_F4 = 32 * OBS_FLOATS / 4;                   // float4 per 32-env tile
-  static constexpr uint32_t LOC_TILE_F4 = 32 * LOC_FLOATS / 4;
   static constexpr int STEP_LIMIT = 10, FSTEP_LIMIT = 50;                    // :47-48
   static constexpr uint32_t STEP_SAT = 255;
   // blob layout (bytes)
-  static constexpr uint32_t LUT_OFF = 0;                                     // u8 [8575]: (slot << 5) | cell, foveal obs
-  static constexpr uint32_t LOCLUT_OFF = align16(OBS_FLOATS);                // u8 [4900]: (bit plane << 5) | cell, local obs
-  static constexpr uint32_t ROWBITS_OFF = LOCLUT_OFF + align16(LOC_FLOATS);  // u32 [5][18]
+  static constexpr uint32_t LUT_OFF = 0;                                     // u32 [8575]: float4 entries of a 4-env group, foveal obs
+  static constexpr uint32_t LOCLUT_OFF = align16(OBS_FLOATS * 4);                   // u32 [1225]: float4 entries of one env, local obs
+  static constexpr uint32_t ROWBITS_OFF = LOCLUT_OFF + align16(LOC_FLOATS); // u32 [5][18]
   static constexpr uint32_t CLS_OFF = ROWBITS_OFF + align16(NLAYOUT * G * 4);
   static constexpr uint32_t GCAND_OFF = CLS_OFF + align16(NLAYOUT * G * G);
   static constexpr uint32_t BCAND_OFF = GCAND_OFF + NLAYOUT * MAX_CAND * 2;
@@ -49,6 +57,7 @@ struct V5 {
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G); // u8 ng[5], nb[5]; u16 xcell[5] at +16
   static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;
 };
 
 struct V5Regs {
@@ -107,12 +116,7 @@ __device__ __forceinline__ bool v5_np_index(int &i) {
   return true;
 }
 
-struct V5Lane {
-  LaneOut o;
-  uint32_t mask[V5::NBIT];
-  uint32_t info;            // x:5 | y:5 | shown last x:5 | shown last y:5 | visit op:2 (0 read, 1 average, 2 zero) | loc_err:1
-  bool rfov, rloc;          // which observation rows this call writes
-};
+using V5Lane = FovLane<V5::NBIT>;   // info: x | y | shown retStatelast x | y | visit op (0 read, 1 average, 2 zero) | loc_err
 
 template <class W>
 __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const FovTables<W> &t, const unsigned char *smem) {
@@ -211,158 +215,6 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
   out.mask[5] = loc_ok ? (1u << (i0 * 5 + i1)) : 0u;                                 // :365
   out.mask[6] = loc_ok ? (1u << (j0 * 5 + j1)) : 0u;                                 // :366
   return out;
-}
-
-// Fused reset / plannerStep / step / render of the planner-actor env.  Same CTA organisation as the v4
-// kernel: warps 0-3 are producers (warp 0 runs the next tile's transitions, then all four make the pass
-// over that tile's float visit layers and capture the two 5x5 crops per env), the other warps write the
-// current tile's foveal rows and then its local rows as flat float4 runs.
-template <class W, int THREADS>
-__global__ void __launch_bounds__(THREADS) lmz_env_v5_kernel(const KParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t s_mask[2][32 * W::NBIT];
-  __shared__ uint32_t s_info[2][32];
-  __shared__ float s_vis[2 * 32 * 50];       // [buf][env][0: at the ball, 1: at the shown retStatelast window][25]
-  __shared__ uint32_t s_flags[2][2];         // [buf][0 foveal, 1 local]: bit l = env l of the tile is written
-  __shared__ long long s_tile[2];
-  constexpr int PROD = THREADS >= 512 ? 128 : 64;
-  constexpr int CTHREADS = THREADS - PROD;
-  static_assert(CTHREADS >= 32, "need at least one rendering warp");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  stage_blob<W>(smem, &bar, p.blob);
-  const FovTables<W> t(smem);
-  const uint8_t *loclut = smem + W::LOCLUT_OFF;
-  const int64_t tiles = p.tile_end;
-  const bool need_visit = (p.mode != MODE_PLANNER);
-  WarpStats ws;
-
-  auto produce = [&](int buf) {              // warp 0 only
-    int64_t tl = 0;
-    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
-    tl = __shfl_sync(0xffffffffu, tl, 0);
-    const int64_t e = tl * 32 + lane;
-    const bool valid = tl < tiles && e < p.n;
-    V5Lane v;
-    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
-    v.rfov = false; v.rloc = false;
-#pragma unroll
-    for (int c = 0; c < W::NBIT; ++c) v.mask[c] = 0;
-    if (valid) v = v5_lane<W>(p, e, t, smem);
-    if (p.mode == MODE_STEP) ws.add(valid, v.o);
-#pragma unroll
-    for (int c = 0; c < W::NBIT; ++c) s_mask[buf][lane * W::NBIT + c] = v.mask[c];
-    s_info[buf][lane] = valid ? v.info : 0u;
-    const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
-    const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
-    if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = tl; }
-  };
-  // visit layers of one tile's 32 envs: 32 x 324 consecutive floats, coalesced pass by the producer threads
-  auto visit_pass = [&](int buf) {
-    const int64_t tile = s_tile[buf];
-    if (tile >= tiles || !need_visit) return;
-    const int64_t e0 = tile * 32;
-    const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
-    float *vis = p.visit + e0 * (W::G * W::G);
-    float *sv = s_vis + buf * (32 * 50);
-    constexpr uint32_t PER = (32 * W::G * W::G + PROD - 1) / PROD, UN = 8;
-    for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
-      float vv[UN];
-#pragma unroll
-      for (uint32_t j = 0; j < UN; ++j) {
-        const uint32_t idx = tid + (k0 + j) * PROD;
-        vv[j] = (idx < cells) ? __ldcs(vis + idx) : 0.0f;
-      }
-#pragma unroll
-      for (uint32_t j = 0; j < UN; ++j) {
-        const uint32_t idx = tid + (k0 + j) * PROD;
-        if (idx >= cells) continue;
-        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-        const int x = cell / W::G, y = cell - x * W::G;
-        const uint32_t info = s_info[buf][env];
-        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-        const uint32_t op = (info >> 20) & 3u;
-        const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-        const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-        float v = vv[j];
-        if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);       // :308-312, float64 then float32
-        else if (op == 2) v = 0.0f;                                               // :134
-        if (op) __stcs(vis + idx, v);
-        if (in_cur) sv[env * 50 + dx * 5 + dy] = v;
-        if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) sv[env * 50 + 25 + qx * 5 + qy] = v;
-      }
-    }
-  };
-  auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory"); };
-
-  if (warp == 0) produce(0);
-  if (tid < PROD) { producers_sync(); visit_pass(0); }
-  for (int buf = 0;; buf ^= 1) {
-    __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
-    const int64_t tile = s_tile[buf];
-    if (tile >= tiles) break;
-    if (tid < PROD) {
-      if (warp == 0) produce(buf ^ 1);
-      producers_sync();
-      visit_pass(buf ^ 1);
-      continue;
-    }
-    const int ctid = tid - PROD;
-    const uint32_t *mk = s_mask[buf];
-    const uint32_t *inf = s_info[buf];
-    const float *sv = s_vis + buf * (32 * 50);
-    const int64_t row0 = tile * 32 - p.win_lo;
-    // ---- foveal rows (:314-348)
-    uint32_t flags = s_flags[buf][0];
-    if (flags) {
-      float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)W::OBS_FLOATS;
-      auto value = [&](uint32_t env, uint32_t r) -> uint32_t {
-        const uint32_t code = t.lut[r], slot = code >> 5, cell = code & 31u;
-        if (slot >= 5u) return __float_as_uint(sv[env * 50 + (slot - 5u) * 25 + cell]);
-        return ((mk[env * W::NBIT + slot] >> cell) & 1u) ? 0x3f800000u : 0u;
-      };
-      if (flags == 0xffffffffu && (row0 & 3) == 0) {
-        for (uint32_t q = ctid; q < W::TILE_F4; q += CTHREADS) {
-          uint32_t g = q * 4, env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
-          uint4 v;
-          uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            w[k] = value(env, r);
-            if (++r == W::OBS_FLOATS) { r = 0; ++env; }
-          }
-          st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), v);
-        }
-      } else {
-        for (uint32_t g = ctid; g < 32 * W::OBS_FLOATS; g += CTHREADS) {
-          const uint32_t env = g / W::OBS_FLOATS, r = g - env * W::OBS_FLOATS;
-          if ((flags >> env) & 1u) __stcs(reinterpret_cast<unsigned int *>(dst) + g, value(env, r));
-        }
-      }
-    }
-    // ---- local rows (:356-380): every env row is 16-byte aligned (19,600 = 16 x 1,225)
-    flags = s_flags[buf][1];
-    if (flags) {
-      float *dst = reinterpret_cast<float *>(p.obs2) + row0 * (int64_t)W::LOC_FLOATS;
-      auto value = [&](uint32_t env, uint32_t r) -> uint32_t {
-        const uint32_t code = loclut[r], plane = code >> 5, cell = code & 31u;
-        return ((mk[env * W::NBIT + plane] >> cell) & 1u) ? 0x3f800000u : 0u;
-      };
-      for (uint32_t q = ctid; q < W::LOC_TILE_F4; q += CTHREADS) {
-        const uint32_t env = q / (W::LOC_FLOATS / 4), r = (q - env * (W::LOC_FLOATS / 4)) * 4;
-        if (!((flags >> env) & 1u)) continue;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (!((inf[env] >> 22) & 1u)) {          // IndexError in the reference: the row stays all zero
-          v.x = value(env, r); v.y = value(env, r + 1); v.z = value(env, r + 2); v.w = value(env, r + 3);
-        }
-        st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), v);
-      }
-    }
-  }
-  if (warp == 0) {
-    if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
-    if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
-  }
 }
 
 // v6 safeFovealGoal() (lmaze_env_v6.py:505-523): a foveal goal whose window cell is not a wall.

@@ -8,8 +8,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import gym_lmaze_b200 as lmz
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 threads = [int(t) for t in sys.argv[2].split(",")] if len(sys.argv) > 2 else [512]
+split = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 for thr in threads:
-    env = lmz.LmazeHierCuda(N, "v5", seed=1, tune=(thr, 0, 0, 0))
+    env = lmz.LmazeHierCuda(N, "v5", seed=1, tune=(thr, 0, 0, split))
     env.reset()
     a = torch.randint(0, 4, (8, N), device="cuda", dtype=torch.uint8)
     g = torch.randint(0, 25, (8, N), device="cuda", dtype=torch.uint8)
