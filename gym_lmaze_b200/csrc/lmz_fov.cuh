@@ -14,17 +14,15 @@
 //
 // CTA organisation: tiles of 32 envs are handed out by the global work counter.  Warp 0 runs the tile's 32
 // transitions (one env per lane, state in registers) and expands each env's 25-bit planes into float planes
-// in shared memory; for the variants with a float visit layer (v4, v5) warps 0-3 are dedicated PRODUCERS
-// that also make the coalesced read-modify-write pass over the tile's 32 x 324 visit floats and drop the
-// two 5x5 visit crops into the same planes -- one tile ahead of the other warps, which stream the previous
-// tile's rows out.  Everything is double buffered; one __syncthreads per tile.
+// in shared memory; for the variants with a float visit layer (v4, v5) warps 0-3 are dedicated PRODUCERS:
+// the tile's 32 x 324 visit floats arrive by ONE bulk async (TMA) load issued the moment the tile is grabbed,
+// the producers update them out of shared memory (coalesced write-back) and drop the two 5x5 visit crops into
+// the same planes -- one tile ahead of the other warps, which stream the previous tile's rows out.
+// Everything is double buffered; one __syncthreads per tile.
 #pragma once
 #include "lmz_v2.cuh"
 #include "lmz_v5.cuh"
 
-#ifndef LMZ_VISIT_UN
-#define LMZ_VISIT_UN 8
-#endif
 #ifndef LMZ_VISIT_PROD
 #define LMZ_VISIT_PROD 128
 #endif
@@ -45,6 +43,7 @@ template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t vbar[2];
   __shared__ uint32_t s_info[2][32];
   __shared__ uint32_t s_flags[2][2];         // [buf][0 obs, 1 local obs]: bit l = env l of the tile is written
   __shared__ long long s_tile[2];
@@ -53,9 +52,12 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   static_assert(CTHREADS >= 32, "need at least one rendering warp");
   static_assert((uint32_t)CTHREADS < W::OBS_FLOATS, "index stepping assumes fewer threads than entries");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (W::NVIS > 0 && tid == 0) { mbar_init(&vbar[0], 1); mbar_init(&vbar[1], 1); }   // fenced + synced inside stage_blob
   stage_blob<W>(smem, &bar, p.blob);
   const FovTables<W> t(smem);
   float *vals = reinterpret_cast<float *>(smem + W::BLOB_BYTES);          // [2][32][NSLOT][25]
+  float *vbuf = vals + 2 * 32 * W::VALS;                                  // [2][32][324]: TMA landing zone of the visit layers
+  uint32_t vphase = 0;                                                    // bit b: parity the next wait on vbar[b] expects
   const int64_t tiles = p.tile_end;
   const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
   WarpStats ws;
@@ -64,6 +66,14 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     int64_t tl = 0;
     if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
     tl = __shfl_sync(0xffffffffu, tl, 0);
+    if (W::NVIS > 0 && need_visit && lane == 0 && tl < tiles) {
+      // the tile's 32 visit layers are 41,472 contiguous bytes: ONE bulk async (TMA) load, in flight while
+      // this warp runs the transitions
+      const int64_t e0 = tl * 32;
+      const uint32_t bytes = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G * 4));
+      mbar_expect_tx(&vbar[buf], bytes);
+      bulk_g2s(vbuf + buf * (32 * W::G * W::G), p.visit + e0 * (W::G * W::G), bytes, &vbar[buf]);
+    }
     const int64_t e = tl * 32 + lane;
     const bool valid = tl < tiles && e < p.n;
     FovLane<W::NBIT> v;
@@ -96,46 +106,25 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
     float *vis = p.visit + e0 * (W::G * W::G);
     float *tv = vals + buf * 32 * W::VALS;
-    constexpr uint32_t NP = PROD > 0 ? PROD : 1, PER = (32 * W::G * W::G + NP - 1) / NP, UN = LMZ_VISIT_UN;
-    for (uint32_t k0 = 0; k0 < PER; k0 += UN) {
-      float vv[UN];
-      uint32_t live = 0;     // bit j: element j of this batch is loaded / updated
-#pragma unroll
-      for (uint32_t j = 0; j < UN; ++j) {                            // UN independent loads in flight per thread
-        const uint32_t idx = tid + (k0 + j) * NP;
-        vv[j] = 0.0f;
-        if (idx >= cells) continue;
-        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-        const int x = cell / W::G, y = cell - x * W::G;
-        const uint32_t info = s_info[buf][env];
-        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-        const uint32_t op = (info >> 20) & 3u;
-        // a layer that is only looked at (v5 while the local episode runs) is read at the two windows only;
-        // one that is re-zeroed is not read at all
-        const bool out_cur = ((unsigned)(x - bx + 2) >= 5u) | ((unsigned)(y - by + 2) >= 5u);
-        const bool out_prev = ((unsigned)(x - px + 2) >= 5u) | ((unsigned)(y - py + 2) >= 5u);
-        if (op == 0 && out_cur && out_prev) continue;
-        live |= 1u << j;
-        if (op != 2) vv[j] = __ldcs(vis + idx);
-      }
-#pragma unroll
-      for (uint32_t j = 0; j < UN; ++j) {
-        if (!((live >> j) & 1u)) continue;
-        const uint32_t idx = tid + (k0 + j) * NP;
-        const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-        const int x = cell / W::G, y = cell - x * W::G;
-        const uint32_t info = s_info[buf][env];
-        const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-        const uint32_t op = (info >> 20) & 3u;
-        const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-        const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-        float v = vv[j];
-        if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
-        else if (op == 2) v = W::visit_reset(in_cur);
-        if (op) __stcs(vis + idx, v);
-        if (in_cur) tv[env * W::VALS + W::VIS_SLOT0 * 25 + dx * 5 + dy] = v;
-        if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) tv[env * W::VALS + W::VIS_SLOT1 * 25 + qx * 5 + qy] = v;
-      }
+    const float *vb = vbuf + buf * (32 * W::G * W::G);
+    mbar_wait(&vbar[buf], (vphase >> buf) & 1u);
+    vphase ^= 1u << buf;
+    constexpr uint32_t NP = PROD > 0 ? PROD : 1;
+#pragma unroll 4
+    for (uint32_t idx = tid; idx < cells; idx += NP) {
+      const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
+      const int x = cell / W::G, y = cell - x * W::G;
+      const uint32_t info = s_info[buf][env];
+      const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+      const uint32_t op = (info >> 20) & 3u;
+      const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
+      const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
+      float v = vb[idx];
+      if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
+      else if (op == 2) v = W::visit_reset(in_cur);
+      if (op) __stcs(vis + idx, v);
+      if (in_cur) tv[env * W::VALS + W::VIS_SLOT0 * 25 + dx * 5 + dy] = v;
+      if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) tv[env * W::VALS + W::VIS_SLOT1 * 25 + qx * 5 + qy] = v;
     }
   };
   auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };

@@ -50,7 +50,7 @@ struct Fov {
   static constexpr uint32_t BRANK_OFF = BCAND_OFF + NLAYOUT * MAX_CAND * 2;       // i8 [5][324] index in BCAND or -1
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5]
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
-  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;   // + the double-buffered per-env value planes
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * G * G * 4 : 0);   // + the double-buffered per-env value planes
 };
 using V2 = Fov<2, 5>;
 using V4 = Fov<4, 7>;
