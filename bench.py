@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
-    ap.add_argument("--variant", default="v0", choices=["v0", "v2", "v3", "v4"])
+    ap.add_argument("--variant", default="v0", choices=["v0", "v2", "v3", "v4", "v5"])
     ap.add_argument("--render-mode", default="tma", choices=["tma", "st128", "incremental"])
     ap.add_argument("--obs-mode", default="full", choices=["full", "compact"])
     ap.add_argument("--window", type=int, default=0,
@@ -124,8 +124,41 @@ def recorded_traffic(variant, render_mode):
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)
+def cpu_oracle_throughput_v5(n_envs, threads, budget_s, min_steps=2):
+    """lmaze-v5: plannerStep (where the local episode ended) + step + reset on globalDone, both observations
+    rendered, on `threads` host threads (one OracleHier slice per thread; ctypes releases the GIL)."""
+    import numpy as np
+    from oracle import oracle as O
+    per = max(1, n_envs // threads)
+    counts = [0] * threads
+
+    def worker(k):
+        rng = np.random.RandomState(k)
+        o = O.OracleHier(per, seed=1, env_id0=k * per)
+        o.reset(want_obs=False)
+        mask = np.ones(per, np.uint8)
+        t0 = time.perf_counter()
+        while counts[k] < min_steps or time.perf_counter() - t0 < budget_s:
+            o.planner_step(rng.randint(0, 25, size=per), mask=mask)
+            _, _, _, _, gd, ld, _ = o.step(rng.randint(0, 4, size=per))
+            if gd.any():
+                o.reset(mask=gd, want_obs=False)
+            mask = (gd | ld).astype(np.uint8)
+            counts[k] += 1
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return per * sum(counts) / dt, sum(counts) // threads, dt
+
+
 def cpu_oracle_throughput(variant, n_envs, threads, budget_s, min_steps=2):
     """Steps/s of the C oracle port (full step + auto-reset + f32 render) on `threads` host threads."""
+    if variant == "v5":
+        return cpu_oracle_throughput_v5(n_envs, threads, budget_s, min_steps)
     import numpy as np
     from oracle import oracle as O
     ov = {"v0": O.V0, "v2": O.V2, "v3": O.V3, "v4": O.V4}[variant]
@@ -167,6 +200,19 @@ def run_reference(args):
     O.build()
     threads = os.cpu_count() or 1
     sample_envs = 32768
+    if args.variant == "v5":
+        value, k, dt = cpu_oracle_throughput_v5(sample_envs, threads, 0.0, min_steps=args.warmup + args.steps)
+        sample = ("%d-env slice of the %d-env workload per step (plannerStep where due + step + both f32 obs renders), "
+                  "C oracle port, %d threads; %d steps incl. warm-up" % (sample_envs, args.envs, threads, k))
+        print(json.dumps({
+            "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, k) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, note="CPU arm: bounded sample per step"),
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
     ov = {"v0": O.V0, "v2": O.V2, "v3": O.V3, "v4": O.V4}[args.variant]
     import numpy as np
     vec = O.OracleVec(ov, sample_envs, seed=1, autoreset=True, threads=threads)
@@ -197,7 +243,7 @@ def run_reference(args):
 
 
 def workload_config(args, note=None):
-    G, E, C = {"v0": (12, 7, 4), "v3": (18, 4, 3), "v2": (5, 7, 5), "v4": (5, 7, 7)}[args.variant]   # v2/v4: 5x5 fovea
+    G, E, C = {"v0": (12, 7, 4), "v3": (18, 4, 3), "v2": (5, 7, 5), "v4": (5, 7, 7), "v5": (5, 7, 11)}[args.variant]   # v2/v4/v5: 5x5 fovea; v5: (7,35,35) + (4,35,35)
     if args.obs_mode == "compact":
         obs, per_env = "u8 (%d,%d,%d) compact (un-expanded layers; reference image = x%d replication)" % (C, G, G, E), C * G * G
     else:
@@ -206,7 +252,9 @@ def workload_config(args, note=None):
     which = ("BASELINE configs[2], HBM roofline run" if args.variant == "v0" and args.obs_mode == "full"
              else "BASELINE configs[3]-style: largest maze variant" if args.variant == "v3" and args.obs_mode == "full"
              else "SURVEY 8f next #1: multi-layout foveal env" if args.variant == "v2"
-             else "SURVEY 8f next #3: foveal env + float visit layer" if args.variant == "v4" else "compact-observation mode")
+             else "SURVEY 8f next #3: foveal env + float visit layer" if args.variant == "v4"
+             else "SURVEY 8f next #4: planner/actor env, a step = plannerStep(auto mask) + step, two obs tensors"
+             if args.variant == "v5" else "compact-observation mode")
     cfg = {
         "workload": "lmaze_env_%s %d envs/GPU, fused step+auto-reset+obs render (%s)" % (args.variant, args.envs, which),
         "variant": args.variant, "envs_per_gpu": args.envs, "obs": obs, "actions": "u8 ring [4,N] resident in HBM",
@@ -238,20 +286,31 @@ def run_ours(args):
     import gym_lmaze_b200 as lmz          # raises if the CUDA library is missing: no fallback
     N = args.envs
     W = args.window if 0 < args.window < N else N
-    env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, env_id0=rank * N, autoreset=True,
-                           render_mode=args.render_mode, obs_mode=args.obs_mode, obs_window=W)
+    hier = args.variant == "v5"
+    if hier:
+        env = lmz.LmazeHierCuda(N, "v5", device=dev, seed=2026, env_id0=rank * N, autoreset=True)
+    else:
+        env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, env_id0=rank * N, autoreset=True,
+                               render_mode=args.render_mode, obs_mode=args.obs_mode, obs_window=W)
     windows = list(range(0, N, W))
     if windows[-1] + W > N:
         windows[-1] = N - W
     obs_bytes = env.obs[0].numel() * env.obs.element_size()
     step_bytes = obs_bytes + 14 + (2 * 324 * 4 if args.variant == "v4" else 0)   # v4: visit layer read + write
+    if hier:
+        step_bytes = 0        # filled in after the timed region from the measured localDone / planner fractions
     if args.render_mode == "incremental":
         # persistent obs tensor: at most the old and the new ExE ball block are rewritten (upper bound)
         E = 7 if args.variant == "v0" else 4
         step_bytes = 2 * E * E * 4 + 14
 
-    def full_step(actions):
+    def full_step(i):
         """one step = transition of every env + every env's observation written once"""
+        actions = ring[i % R]
+        if hier:        # plannerStep for the envs waiting for their planner (device-side mask), then the actor step
+            env.plannerStep(goal_ring[i % R], mask="auto")
+            env.step(actions, goal_plane=False)
+            return
         if len(windows) > 1:
             env.set_window(windows[0])
         env.step(actions)
@@ -260,6 +319,7 @@ def run_ours(args):
     R = 4
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ring = torch.randint(0, env.num_actions, (R, N), generator=gen, device=dev, dtype=torch.uint8)
+    goal_ring = torch.randint(0, 25, (R, N), generator=gen, device=dev, dtype=torch.uint8) if hier else None
     env.reset()
 
     def barrier():
@@ -277,7 +337,7 @@ def run_ours(args):
 
     # ---- device-resident inputs: K launches of the fused kernel, CUDA events on the launch stream
     for i in range(args.warmup):
-        full_step(ring[i % R])
+        full_step(i)
     launches0 = env.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -286,7 +346,7 @@ def run_ours(args):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
     for i in range(args.steps):
-        full_step(ring[i % R])
+        full_step(i)
         evs[i + 1].record()
     barrier()
     total_ms = reduce_max(evs[0].elapsed_time(evs[-1]))
@@ -297,13 +357,32 @@ def run_ours(args):
     step_ms = total_ms / args.steps
     launches_per_step = max(1, gpu_launches // args.steps)
     kernel_ms = step_ms / launches_per_step      # default config: ONE launch per step, step time == kernel time
+    hier_note = None
+    if hier:
+        ld = float(env._ldone_u8.float().mean())            # share of env-steps whose local episode is over
+        st = env.get_state()
+        pf = float(((st[:, 15] & 2) != 0).logical_or(st[:, 14] == 0).float().mean())   # share waiting for the planner
+        # step launch: foveal + local obs, visit layer read (+ written back where localDone), 3 state words r/w,
+        # 2 rewards, 4 flag bytes, action; planner launch: 3 state words read, and for the waiting envs goal +
+        # state write + local obs
+        step_bytes = int(34300 + 19600 + 1296 * (1 + ld) + 24 + 8 + 4 + 1 + 12 + pf * (19600 + 12 + 1 + 2))
+        hier_note = {"local_done_fraction": ld, "planner_fraction": pf,
+                     "bytes": "34,300 foveal + 19,600 local obs + 1,296 visit read (+1,296 x localDone written) + state/"
+                              "rewards/flags/action 37 + planner launch: 12 + planner_fraction x (19,600 local obs + 15)"}
     achieved = N * step_bytes / (step_ms * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory)
     a_host = torch.randint(0, env.num_actions, (R, N), dtype=torch.uint8).pin_memory()
     r_host = torch.empty(N, dtype=torch.float32).pin_memory()
     d_host = torch.empty(N, dtype=torch.uint8).pin_memory()
+    if hier:
+        g_host = torch.randint(0, 25, (R, N), dtype=torch.uint8).pin_memory()
+        r2_host = torch.empty(N, dtype=torch.float32).pin_memory()
+        d2_host = torch.empty(N, dtype=torch.uint8).pin_memory()
     def full_step_host(i):
+        if hier:
+            env.step_host(g_host[i % R], a_host[i % R], r_host, r2_host, d_host, d2_host)
+            return
         if len(windows) > 1:
             env.set_window(windows[0])
         env.step_host(a_host[i % R], r_host, d_host)
@@ -331,7 +410,7 @@ def run_ours(args):
     if not args.no_extras and rank == 0 and world == 1:
         extras = side_measurements(env, args, torch, dev)
 
-    stats = env.stats_allreduce() if world > 1 else env.stats()
+    stats = env.stats_allreduce(check_errors=not hier) if world > 1 else env.stats(check_errors=not hier)   # v5: random actors hit the reference's IndexError rows
     if extras and args.variant in ("v0", "v3") and args.obs_mode == "full" and args.render_mode != "incremental":
         # (3) same workload, obs tensor kept PERSISTENT and patched in place (needs the 118 GB back first)
         env.close()
@@ -350,15 +429,18 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N, "d2h_bytes_per_step": 5 * N,
-                "ms_per_step": e2e_ms / args.steps, "api": "LmazeVecCuda.step_host -> lmz_step_host (C ABI)",
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 2 * N if hier else N,
+                "d2h_bytes_per_step": 10 * N if hier else 5 * N,
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "LmazeHierCuda.step_host -> lmz_hier_step_host (C ABI)" if hier
+                else "LmazeVecCuda.step_host -> lmz_step_host (C ABI)",
                 "obs": "device-resident (consumed on the GPU via DLPack); see extras.e2e_obs_to_host for the "
                        "full obs D2H variant", "reward_checksum": checksum},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.variant, args.render_mode)
                      if (args.obs_mode == "full" and W == N and N == 1 << 20) else None, "peak_source": peak_src,
-                     "kernel": "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4") else
+                     "kernel": "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4", "v5") else
                      "lmz_env_incr_kernel<%s>" % args.variant.upper() if args.render_mode == "incremental" else
                      "lmz_env_%s_kernel<%s>" % ("compact" if args.obs_mode == "compact" else
                                                 "tma" if args.render_mode == "tma" else "st", args.variant.upper()),
@@ -370,6 +452,8 @@ def run_ours(args):
                      "kernel_ms_median": per_step[len(per_step) // 2]},
         "episode_stats": stats,
     }
+    if hier_note:
+        line["roofline"]["v5"] = hier_note
     if extras:
         line["extras"] = extras
     if not args.no_cpu_baseline and world == 1:
@@ -383,7 +467,7 @@ def run_ours(args):
             "sample": "%d steps of a 16384-env slice of the workload (%.1f s), C oracle port, %d pthreads"
                       % (k_all, dt_all, P),
             "single_core": {"value": v_one, "sample": "%d steps x 2048 envs (%.1f s)" % (k_one, dt_one)},
-            "python_loop": {"value": python_loop_throughput(), "cores": 1,
+            "python_loop": None if hier else {"value": python_loop_throughput(), "cores": 1,
                             "sample": "40 steps of the interpreted per-pixel loop restatement (oracle/pyloop.py), "
                                       "the reference's implementation style; survey-time probe of the real "
                                       "reference: ~40 env-steps/s/core"},
@@ -441,7 +525,7 @@ def side_measurements(env, args, torch, dev):
                                           "MEASURED_PEAKS hbm_gbs is a read+write copy, so a pure-write kernel "
                                           "can exceed it"}
     del scratch
-    if args.variant in ("v2", "v4"):
+    if args.variant in ("v2", "v4", "v5"):
         return out
     # (1) BASELINE configs[4]-style: T=64 fused rollout, device-side Philox actions, no per-step obs
     T = 64

@@ -30,7 +30,8 @@ EXPORTS = (
     "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_get_visit", "lmz_set_visit", "lmz_get_visit_dl",
     "lmz_set_visit_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
     "lmz_state_cols", "lmz_local_obs_shape", "lmz_bind_local", "lmz_bind_local_dl", "lmz_planner_step",
-    "lmz_planner_step_dl", "lmz_safe_goal", "lmz_safe_goal_dl",
+    "lmz_planner_step_dl", "lmz_safe_goal", "lmz_safe_goal_dl", "lmz_planner_step_auto", "lmz_planner_step_auto_dl",
+    "lmz_hier_step_host",
 )
 
 
@@ -111,6 +112,9 @@ def load():
     L.lmz_bind_local_dl.argtypes = [vp] * 6
     L.lmz_planner_step.argtypes = [vp, vp, i32, vp, vp]
     L.lmz_planner_step_dl.argtypes = [vp, vp, vp, vp]
+    L.lmz_planner_step_auto.argtypes = [vp, vp, i32, vp]
+    L.lmz_planner_step_auto_dl.argtypes = [vp, vp, vp]
+    L.lmz_hier_step_host.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.lmz_safe_goal.argtypes = [vp, vp, i32, vp, vp, vp]
     L.lmz_safe_goal_dl.argtypes = [vp, vp, vp, vp, vp]
     L.lmz_stats.argtypes = [vp, ctypes.POINTER(i64 * NUM_STATS), ctypes.POINTER(i64), vp]

@@ -1024,6 +1024,55 @@ int lmz_planner_step(lmz_env *h, const void *goals, int32_t goal_dtype, const ui
   return launch_env(h, p, static_cast<cudaStream_t>(stream));
 }
 
+int lmz_planner_step_auto(lmz_env *h, const void *goals, int32_t goal_dtype, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_planner_step_auto: only lmaze-v5/v6 have a planner level");
+  if (int rc = check_bound(h)) return rc;
+  if (!goals) return fail(LMZ_ERR_INVALID, "goals is NULL");
+  if (goal_dtype < LMZ_ACT_U8 || goal_dtype > LMZ_ACT_I64) return fail(LMZ_ERR_INVALID, "unknown goal dtype %d", goal_dtype);
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_PLANNER; p.actions = goals; p.action_dtype = goal_dtype; p.auto_mask = 1;
+  return launch_env(h, p, static_cast<cudaStream_t>(stream));
+}
+
+int lmz_planner_step_auto_dl(lmz_env *h, DLManagedTensor *goals, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  void *pg = nullptr;
+  int ad = 0;
+  Want wg{"goals", 255, 0, 1, {h->cfg.num_envs, 0, 0, 0}, false, 1};
+  if (int rc = check_dl(h, goals, wg, &pg, &ad)) return rc;
+  return lmz_planner_step_auto(h, pg, ad, stream);
+}
+
+int lmz_hier_step_host(lmz_env *h, const void *goals_host, const void *actions_host, int32_t dtype,
+                       float *global_reward_host, float *local_reward_host, uint8_t *global_done_host,
+                       uint8_t *local_done_host, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_hier_step_host: only lmaze-v5/v6");
+  if (int rc = check_bound(h)) return rc;
+  if (!h->local_bound) return fail(LMZ_ERR_STATE, "local outputs not bound: call lmz_bind_local first");
+  if (!goals_host || !actions_host || !global_reward_host || !local_reward_host || !global_done_host || !local_done_host)
+    return fail(LMZ_ERR_INVALID, "host buffers must not be NULL");
+  if (dtype < LMZ_ACT_U8 || dtype > LMZ_ACT_I64) return fail(LMZ_ERR_INVALID, "unknown dtype %d", dtype);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)h->cfg.num_envs;
+  if (!h->act_stage) LMZ_CUDA(cudaMalloc(&h->act_stage, n * 16));       // goals | actions
+  const size_t esz = dtype == LMZ_ACT_U8 ? 1 : dtype == LMZ_ACT_I32 ? 4 : 8;
+  unsigned char *stage = static_cast<unsigned char *>(h->act_stage);
+  LMZ_CUDA(cudaMemcpyAsync(stage, goals_host, n * esz, cudaMemcpyHostToDevice, s));
+  LMZ_CUDA(cudaMemcpyAsync(stage + n * 8, actions_host, n * esz, cudaMemcpyHostToDevice, s));
+  if (int rc = lmz_planner_step_auto(h, stage, dtype, stream)) return rc;
+  if (int rc = lmz_step(h, stage + n * 8, dtype, nullptr, stream)) return rc;
+  LMZ_CUDA(cudaMemcpyAsync(global_reward_host, h->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaMemcpyAsync(local_reward_host, h->reward2, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaMemcpyAsync(global_done_host, h->done, n, cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaMemcpyAsync(local_done_host, h->done2, n, cudaMemcpyDeviceToHost, s));
+  LMZ_CUDA(cudaStreamSynchronize(s));
+  return LMZ_OK;
+}
+
 int lmz_planner_step_dl(lmz_env *h, DLManagedTensor *goals, DLManagedTensor *mask, void *stream) {
   if (int rc = check_handle(h)) return rc;
   const int64_t n = h->cfg.num_envs;

@@ -65,6 +65,7 @@ struct KParams {
   uint8_t *done2;               // localDone [n]
   uint8_t *loc_err;             // 1 where the reference's buildLocalObservation raises IndexError [n], or null
   uint8_t *fgoal_out;           // hot cell of fovealGoal [n], or null
+  int auto_mask;                // plannerStep: act on the envs that are waiting for their planner
 };
 
 enum : int { L2_EVICT_FIRST = 1, L2_EVICT_NORMAL = 2, L2_EVICT_LAST = 3, L2_NONE = 4 };

@@ -164,7 +164,9 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     out.rfov = out.rloc = true;
     write_state = true;
   } else if (p.mode == MODE_PLANNER) {
-    if (p.mask == nullptr || p.mask[e] != 0) {
+    // auto mask: the envs that are waiting for their planner -- local episode over, or no plannerStep since reset()
+    const bool take = p.auto_mask ? (r.ld != 0 || r.fstep == 0) : (p.mask == nullptr || p.mask[e] != 0);
+    if (take) {
       long long g = load_action(p.actions, p.action_dtype, e);
       if (g < 0 || g > 24) { atomicAdd(p.errors, 1u); g = g < 0 ? 0 : 24; }         // the reference raises IndexError (:168)
       r.step = 0; r.ld = 0;                                                          // :161-163

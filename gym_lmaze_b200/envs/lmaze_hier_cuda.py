@@ -46,8 +46,16 @@ class LmazeHierCuda(LmazeVecCuda):
 
     # ------------------------------------------------------------------ protocol
     def plannerStep(self, goals, mask=None):
-        """Reference plannerStep (lmaze_env_v5.py:158-182) for the envs where mask is true; returns the local obs."""
+        """Reference plannerStep (lmaze_env_v5.py:158-182) for the envs where mask is true; returns the local obs.
+        mask="auto": the envs that are waiting for their planner (localDone set, or no plannerStep since their
+        last reset) -- decided on the device, no host round trip."""
         goals = self._as_actions(goals)
+        if isinstance(mask, str):
+            if mask != "auto":
+                raise ValueError("mask must be a tensor, None or 'auto'")
+            pg, kg = _abi.dl(goals)
+            _abi.check(self._lib.lmz_planner_step_auto_dl(self._h, pg, self._stream()))
+            return self.loc_obs
         if mask is not None:
             mask = torch.as_tensor(mask).to(device=self.device).to(torch.uint8).contiguous()
         pg, kg = _abi.dl(goals)
@@ -109,7 +117,24 @@ class LmazeHierCuda(LmazeVecCuda):
         self._graphs = getattr(self, "_graphs", []) + [(graph, actions_buf, spawn_buf)]
         return graph.replay
 
+    def step_host(self, goals_host, actions_host, greward_host, lreward_host, gdone_host, ldone_host):
+        """End-to-end planner + actor step with HOST buffers (pinned CPU tensors): H2D goals and actions,
+        plannerStep(mask="auto") + step, D2H both rewards and both done flags, stream synchronised on return."""
+        n = self.num_envs
+        for t in (goals_host, actions_host, greward_host, lreward_host, gdone_host, ldone_host):
+            if t.device.type != "cpu" or not t.is_contiguous() or t.numel() != n:
+                raise ValueError("step_host takes contiguous CPU tensors of num_envs elements")
+        if goals_host.dtype != actions_host.dtype or actions_host.dtype not in (torch.uint8, torch.int32, torch.int64):
+            raise ValueError("goals_host / actions_host must share a dtype of uint8/int32/int64")
+        if greward_host.dtype != torch.float32 or lreward_host.dtype != torch.float32:
+            raise ValueError("reward buffers must be float32")
+        ad = (torch.uint8, torch.int32, torch.int64).index(actions_host.dtype)
+        _abi.check(self._lib.lmz_hier_step_host(
+            self._h, goals_host.data_ptr(), actions_host.data_ptr(), ad, greward_host.data_ptr(),
+            lreward_host.data_ptr(), gdone_host.data_ptr(), ldone_host.data_ptr(), self._stream()))
+        return greward_host, lreward_host, gdone_host, ldone_host
+
     def _unsupported(self, *a, **k):
         raise NotImplementedError("not available for the planner/actor env (lmaze-v5/v6)")
 
-    rollout = step_host = set_window = render_window = initState = _unsupported
+    rollout = set_window = render_window = initState = _unsupported

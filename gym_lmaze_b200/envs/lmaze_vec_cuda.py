@@ -335,10 +335,10 @@ class LmazeVecCuda(object):
     def stats_reset(self):
         _abi.check(self._lib.lmz_stats_reset(self._h, self._stream()))
 
-    def stats_allreduce(self, group=None):
+    def stats_allreduce(self, group=None, check_errors=True):
         """Sum of the integer episode counters over all ranks (never on the step path)."""
         import torch.distributed as dist
-        local = self.stats()
+        local = self.stats(check_errors=check_errors)
         return allreduce_stats(local, self.device, group) if dist.is_available() and dist.is_initialized() else local
 
     @property

@@ -239,6 +239,18 @@ int lmz_bind_local_dl(lmz_env *env, DLManagedTensor *loc_obs, DLManagedTensor *l
  * `goal_dtype` (lmz_action_dtype); out-of-range goals (IndexError in the reference) are clamped and counted. */
 int lmz_planner_step(lmz_env *env, const void *goals, int32_t goal_dtype, const uint8_t *mask, void *stream);
 int lmz_planner_step_dl(lmz_env *env, DLManagedTensor *goals, DLManagedTensor *mask, void *stream);
+/* The same with the mask derived on the device: plannerStep for every env that is WAITING for its planner --
+ * localDone is set, or no plannerStep happened since its last reset (which includes envs that auto-reset in the
+ * previous step).  This is the loop `if localDone: plannerStep(...)` of a hierarchical agent without a host
+ * round trip, and it makes the planner + step pair capturable in a CUDA graph. */
+int lmz_planner_step_auto(lmz_env *env, const void *goals, int32_t goal_dtype, void *stream);
+int lmz_planner_step_auto_dl(lmz_env *env, DLManagedTensor *goals, void *stream);
+/* Host-buffer form of one planner + actor step (the end-to-end call): copies goals and actions H2D, runs
+ * lmz_planner_step_auto and lmz_step, copies globalReward / originalReward / globalDone / localDone D2H and waits
+ * for the stream.  Observations stay in the bound device tensors. */
+int lmz_hier_step_host(lmz_env *env, const void *goals_host, const void *actions_host, int32_t dtype,
+                       float *global_reward_host, float *local_reward_host, uint8_t *global_done_host,
+                       uint8_t *local_done_host, void *stream);
 /* lmaze-v6 safeFovealGoal() (lmaze_env_v6.py:505-523): goals_out u8 [N] = a cell 0..24 of the 5x5 window around
  * the ball that is not a wall.  draws NULL => device RNG, exactly uniform over the non-wall cells (the
  * distribution of the reference's rejection loop); else int64 [N][n_draws] are the values its

@@ -239,3 +239,40 @@ def test_hier_compat_classes(lmz, golden_dir):
     with pytest.raises(ValueError):
         lmz.LmazeVecCuda(4, "v5")
     vec.close()
+
+
+def test_hier_auto_mask_and_host_step(lmz, oracle_mod):
+    """plannerStep(mask="auto") picks exactly the envs that wait for their planner (localDone set, or no
+    plannerStep since reset -- incl. envs that auto-reset in the previous step); step_host is the same pair
+    of launches through host buffers."""
+    n, seed = 3000, 21
+    env = lmz.LmazeHierCuda(n, "v5", seed=seed, autoreset=True)
+    ora = oracle_mod.OracleHier(n, seed=seed)
+    env.reset(); ora.reset()
+    rng = np.random.RandomState(3)
+    want_mask = np.ones(n, np.uint8)
+    pin = lambda t: t.pin_memory()
+    gr_h, lr_h = pin(torch.empty(n, dtype=torch.float32)), pin(torch.empty(n, dtype=torch.float32))
+    gd_h, ld_h = pin(torch.empty(n, dtype=torch.uint8)), pin(torch.empty(n, dtype=torch.uint8))
+    for it in range(80):
+        goals = rng.randint(0, 25, size=n); acts = rng.randint(0, 4, size=n)
+        if it % 2 == 0:
+            env.plannerStep(goals, mask="auto")
+            env.step(acts, goal_plane=False)
+            gr, lr, gd, ld = env.reward.cpu(), env.local_reward.cpu(), env._done_u8.cpu(), env._ldone_u8.cpu()
+        else:
+            env.step_host(pin(torch.as_tensor(goals, dtype=torch.uint8)), pin(torch.as_tensor(acts, dtype=torch.uint8)),
+                          gr_h, lr_h, gd_h, ld_h)
+            gr, lr, gd, ld = gr_h.clone(), lr_h.clone(), gd_h.clone(), ld_h.clone()
+        loc_p, _ = ora.planner_step(goals, mask=want_mask)
+        fov_ref, loc_ref, gr_ref, lr_ref, gd_ref, ld_ref, err_ref = ora.step(acts)
+        assert np.array_equal(u32(gr), u32(gr_ref)) and np.array_equal(u32(lr), u32(lr_ref)), it
+        assert np.array_equal(gd.numpy(), gd_ref) and np.array_equal(ld.numpy(), ld_ref), it
+        gdm = gd_ref.astype(bool)
+        if gdm.any():
+            ora.reset(mask=gdm.astype(np.uint8), want_obs=False)
+            ora.render(mask=gdm.astype(np.uint8), fov=fov_ref, loc=loc_ref)
+        assert np.array_equal(u32(env.obs), u32(fov_ref)) and np.array_equal(u32(env.loc_obs), u32(loc_ref)), it
+        want_mask = (gd_ref | ld_ref).astype(np.uint8)
+    assert np.array_equal(env.get_state().cpu().numpy()[:, :13], ora.export()[:, :13])
+    env.close()
