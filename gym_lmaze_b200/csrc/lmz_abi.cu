@@ -390,7 +390,33 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return launch_fov_t<W, 512>(h, p, s);
 }
 
+// plannerStep (lmaze-v5/v6): warp-granular kernel, several small CTAs per SM
+int launch_planner(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  using W = lmz::V5;
+  constexpr int THREADS = 128;
+  if (!h->local_bound) return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
+  auto kern = lmz::lmz_planner_kernel<W, THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::BLOB_BYTES));
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, W::BLOB_BYTES));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "planner kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  const int64_t units = p.tile_end - p.tile_begin;
+  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, W::BLOB_BYTES, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.variant == LMZ_V5 && p.mode == lmz::MODE_PLANNER) return launch_planner(h, p, s);
   if (h->cfg.variant == LMZ_V5) return launch_fov<lmz::V5>(h, p, s);
   if (h->cfg.variant == LMZ_V2) return launch_fov<lmz::V2>(h, p, s);
   if (h->cfg.variant == LMZ_V4) return launch_fov<lmz::V4>(h, p, s);

@@ -128,10 +128,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     }
   };
   auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };
-  auto pick = [](uint32_t en, const float *gv) -> uint4 {           // one table entry -> the four floats of a float4
-    const uint32_t va = __float_as_uint(gv[en & 1023u]), vb = __float_as_uint(gv[(en >> 10) & 1023u]), k = en >> 20;
-    return make_uint4(va, k > 1 ? va : vb, k > 2 ? va : vb, k > 3 ? va : vb);
-  };
+  auto pick = [](uint32_t en, const float *gv) -> uint4 { return f4_pick(en, gv); };
 
   if (warp == 0) produce(0);
   if (W::NVIS > 0 && tid < PROD) { producers_sync(); visit_pass(0); }
@@ -185,16 +182,27 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
         constexpr uint32_t PER = W::LOC_FLOATS / 4 > 0 ? W::LOC_FLOATS / 4 : 1;
         const uint32_t *loclut = reinterpret_cast<const uint32_t *>(smem + W::LOCLUT_OFF);
         unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs2) + row0 * (int64_t)(W::LOC_FLOATS * 4);
-        uint32_t ent = ctid % PER, env = ctid / PER;
+        if (flags == 0xffffffffu) {
+          uint32_t ent = ctid % PER, env = ctid / PER;
 #pragma unroll 4
-        for (uint32_t q = ctid; q < 32 * PER; q += CTHREADS) {
-          if ((flags >> env) & 1u) {
+          for (uint32_t q = ctid; q < 32 * PER; q += CTHREADS) {
             uint4 v = make_uint4(0u, 0u, 0u, 0u);                  // IndexError in the reference: the row is all zero
             if (!((s_info[buf][env] >> 22) & 1u)) v = pick(loclut[ent], tv + env * W::VALS);
             st_stream_v4(dst + ((size_t)q << 4), v);
+            ent += CTHREADS;
+            while (ent >= PER) { ent -= PER; ++env; }
           }
-          ent += CTHREADS;
-          while (ent >= PER) { ent -= PER; ++env; }
+        } else {
+          while (flags) {                                          // a few envs of the tile (masked plannerStep)
+            const uint32_t env = __ffs(flags) - 1;
+            flags &= flags - 1;
+            const bool err = (s_info[buf][env] >> 22) & 1u;
+            for (uint32_t q = ctid; q < PER; q += CTHREADS) {
+              uint4 v = make_uint4(0u, 0u, 0u, 0u);
+              if (!err) v = pick(loclut[q], tv + env * W::VALS);
+              st_stream_v4(dst + ((size_t)(env * PER + q) << 4), v);
+            }
+          }
         }
       }
     }

@@ -89,6 +89,13 @@ struct FovTables {
         brank(reinterpret_cast<const int8_t *>(smem + W::BRANK_OFF)), count(smem + W::COUNT_OFF) {}
 };
 
+// One float4 of an x7-upsampled image from its table entry (A:10 | B:10 | k:3, built by the host: the first k
+// floats show value plane entry A, the rest entry B) -- see lmz_fov.cuh.
+__device__ __forceinline__ uint4 f4_pick(uint32_t en, const float *gv) {
+  const uint32_t va = __float_as_uint(gv[en & 1023u]), vb = __float_as_uint(gv[(en >> 10) & 1023u]), k = en >> 20;
+  return make_uint4(va, k > 1 ? va : vb, k > 2 ? va : vb, k > 3 ? va : vb);
+}
+
 // 5x5 crop of the free-cell layer around (x,y) as 25 bits, bit i*5+j = cell (x-2+i, y-2+j)
 template <class W>
 __device__ __forceinline__ uint32_t v2_free_crop(const FovTables<W> &t, int L, int x, int y) {

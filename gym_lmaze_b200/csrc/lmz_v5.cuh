@@ -219,6 +219,63 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
   return out;
 }
 
+// plannerStep on its own (lmaze_env_v5.py:158-182).  Only the envs whose local episode is over take part and
+// only their local observation is re-rendered, so the work per tile is small and the CTA-cooperative render
+// kernel would spend its time on the one producer warp's per-tile latency chain.  Here every WARP is
+// independent: it grabs a tile from the work counter, runs the 32 planner updates (one env per lane) and then
+// writes the 19,600-byte local rows of the envs that took part, one env at a time, as float4 runs.
+template <class W, int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_planner_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_vals[THREADS / 32][W::VALS];          // one env's value planes per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  stage_blob<W>(smem, &bar, p.blob);
+  const FovTables<W> t(smem);
+  const uint32_t *loclut = reinterpret_cast<const uint32_t *>(smem + W::LOCLUT_OFF);
+  constexpr uint32_t PER = W::LOC_FLOATS / 4;
+  float *mv = s_vals[warp];
+  for (;;) {
+    int64_t tl = 0;
+    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
+    tl = __shfl_sync(0xffffffffu, tl, 0);
+    if (tl >= p.tile_end) break;
+    const int64_t e = tl * 32 + lane;
+    const bool valid = e < p.n;
+    V5Lane v;
+    v.rloc = false; v.info = 0;
+#pragma unroll
+    for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
+    if (valid) v = v5_lane<W>(p, e, t, smem);
+    unsigned flags = __ballot_sync(0xffffffffu, valid && v.rloc);
+    while (flags) {
+      const int src = __ffs(flags) - 1;
+      flags &= flags - 1;
+      // local obs planes (lmaze_env_v5.py:360-368): free crop (value plane 0), ball (7), previous ball (8), fovealGoal (3)
+      const uint32_t m0 = __shfl_sync(0xffffffffu, v.mask[0], src), m5 = __shfl_sync(0xffffffffu, v.mask[5], src);
+      const uint32_t m6 = __shfl_sync(0xffffffffu, v.mask[6], src), m2 = __shfl_sync(0xffffffffu, v.mask[2], src);
+      const bool err = (__shfl_sync(0xffffffffu, v.info, src) >> 22) & 1u;
+      __syncwarp();
+      if (lane < 25) {
+        mv[0 * 25 + lane] = ((m0 >> lane) & 1u) ? 1.0f : 0.0f;
+        mv[7 * 25 + lane] = ((m5 >> lane) & 1u) ? 1.0f : 0.0f;
+        mv[8 * 25 + lane] = ((m6 >> lane) & 1u) ? 1.0f : 0.0f;
+        mv[3 * 25 + lane] = ((m2 >> lane) & 1u) ? 1.0f : 0.0f;
+      }
+      __syncwarp();
+      unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs2) + (tl * 32 + src - p.win_lo) * (int64_t)W::LOC_BYTES;
+#pragma unroll 4
+      for (uint32_t q = lane; q < PER; q += 32) {
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);              // IndexError in the reference: the row is all zero
+        if (!err) val = f4_pick(loclut[q], mv);
+        st_stream_v4(dst + ((size_t)q << 4), val);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
+}
+
 // v6 safeFovealGoal() (lmaze_env_v6.py:505-523): a foveal goal whose window cell is not a wall.
 // draws != null: int64 [n][n_draws] values the reference's np.random.randint(0, 25) would have returned;
 // the first non-wall one wins (used[e] = how many were consumed; goal -1 if none qualified).
