@@ -175,6 +175,8 @@ void build_blob_fov(std::vector<unsigned char> &blob) {
     }
     blob[V::COUNT_OFF + L] = (unsigned char)ng;
     blob[V::COUNT_OFF + 5 + L] = (unsigned char)nb;
+    for (int i = 0; i < V::G * V::G; ++i)
+      if (cells[i] == 'X') reinterpret_cast<uint16_t *>(blob.data() + V::XCELL_OFF)[L] = (uint16_t)i;
   }
 }
 
@@ -186,13 +188,6 @@ void build_blob_v5(std::vector<unsigned char> &blob) {
   // fovealGoal (3); one env row = 1,225 float4s exactly
   build_f4_lut<V>(reinterpret_cast<uint32_t *>(blob.data() + V::LOCLUT_OFF), V::LOC_FLOATS, V::LOC_FLOATS / 4,
                   [](int c) { static const int plane[4] = {0, 7, 8, 3}; return plane[c]; });
-  uint16_t *xcell = reinterpret_cast<uint16_t *>(blob.data() + V::XCELL_OFF);
-  for (int L = 0; L < V::NLAYOUT; ++L) {
-    char cells[18 * 18];
-    v2_cells(L + 1, cells);
-    for (int i = 0; i < V::G * V::G; ++i)
-      if (cells[i] == 'X') xcell[L] = (uint16_t)i;
-  }
 }
 
 }  // namespace

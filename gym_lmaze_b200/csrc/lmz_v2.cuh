@@ -49,6 +49,7 @@ struct Fov {
   static constexpr uint32_t BCAND_OFF = GCAND_OFF + NLAYOUT * MAX_CAND * 2;       // u16 [5][80] cells not in {W,X}
   static constexpr uint32_t BRANK_OFF = BCAND_OFF + NLAYOUT * MAX_CAND * 2;       // i8 [5][324] index in BCAND or -1
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5]
+  static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;                           // u16 [5]: each maze's 'X' cell
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
   static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * G * G * 4 : 0);   // + the double-buffered per-env value planes
 };
@@ -82,11 +83,13 @@ struct FovTables {
   const uint16_t *gcand, *bcand;
   const int8_t *brank;
   const uint8_t *count;      // ng[0..4], nb[5..9]
+  const uint16_t *xcell;     // the 'X' cell of each maze
   __device__ __forceinline__ explicit FovTables(const unsigned char *smem)
       : lut(reinterpret_cast<const uint32_t *>(smem + W::LUT_OFF)), rowbits(reinterpret_cast<const uint32_t *>(smem + W::ROWBITS_OFF)),
         cls(smem + W::CLS_OFF), gcand(reinterpret_cast<const uint16_t *>(smem + W::GCAND_OFF)),
         bcand(reinterpret_cast<const uint16_t *>(smem + W::BCAND_OFF)),
-        brank(reinterpret_cast<const int8_t *>(smem + W::BRANK_OFF)), count(smem + W::COUNT_OFF) {}
+        brank(reinterpret_cast<const int8_t *>(smem + W::BRANK_OFF)), count(smem + W::COUNT_OFF),
+        xcell(reinterpret_cast<const uint16_t *>(smem + W::XCELL_OFF)) {}
 };
 
 // One float4 of an x7-upsampled image from its table entry (A:10 | B:10 | k:3, built by the host: the first k
@@ -116,17 +119,21 @@ template <class W>
 __device__ __forceinline__ void v2_respawn(V2Regs &r, const KParams &p, int64_t e, uint32_t &episode,
                                            const FovTables<W> &t) {
   int sx, sy, gx, gy, nl;
+  int Ld;                                         // the maze setGoal() / setBall() look at
   if (p.spawn) {
     const int4 s = p.spawn[e];
     sx = s.x; sy = s.y; gx = s.z; gy = s.w & 31; nl = s.w >> 5;
     bool ok = nl >= 1 && nl <= 5;
-    const int Lc = W::MAZE_FIRST ? (ok ? nl : 1) : r.L;           // the maze the rejection loops look at
-    const uint8_t *cls = t.cls + (Lc - 1) * W::G * W::G;
+    Ld = W::MAZE_FIRST ? (ok ? nl : 1) : r.L;
+    const uint8_t *cls = t.cls + (Ld - 1) * W::G * W::G;
+    if (!p.random_goal) { gx = t.xcell[Ld - 1] / W::G; gy = t.xcell[Ld - 1] % W::G; }   // the injected goal is ignored
+    if (!p.random_ball) { sx = 4; sy = 4; }
     if (ok) ok = gx >= 1 && gx <= W::G - 2 && gy >= 1 && gy <= W::G - 2 && sx >= 1 && sx <= W::G - 2 && sy >= 1 &&
                  sy <= W::G - 2;
     if (ok) {
       const int gc = cls[gx * W::G + gy], bc = cls[sx * W::G + sy];
-      ok = gc != CLS_W && gc != CLS_S && bc != CLS_W && bc != CLS_X && !(sx == gx && sy == gy);
+      if (p.random_goal) ok = gc != CLS_W && gc != CLS_S;
+      if (ok && p.random_ball) ok = bc != CLS_W && bc != CLS_X && !(sx == gx && sy == gy);
     }
     if (!ok) {                                    // rejected: count it, fall back to the S / X cells of maze 1
       atomicAdd(p.errors, 1u);
@@ -141,6 +148,7 @@ __device__ __forceinline__ void v2_respawn(V2Regs &r, const KParams &p, int64_t 
       if (episode == 0) r.L = 1 + (int)ws.uniform(5);              // the maze the constructor rolled (:75)
       L0 = r.L - 1;
     }
+    Ld = L0 + 1;
     const int g = t.gcand[L0 * W::MAX_CAND + ws.uniform(t.count[L0])];
     const int rank = t.brank[L0 * W::G * W::G + g];
     const uint32_t nb = t.count[5 + L0];
@@ -150,6 +158,10 @@ __device__ __forceinline__ void v2_respawn(V2Regs &r, const KParams &p, int64_t 
     const int b = t.bcand[L0 * W::MAX_CAND + k];
     gx = g / W::G; gy = g % W::G; sx = b / W::G; sy = b % W::G;
     if (!W::MAZE_FIRST) nl = 1 + (int)ws.uniform(5);
+    // RANDOM_GOAL / RANDOM_BALL False (lmaze_env_v2.py:278-299): the draws above are still consumed (the stream
+    // layout does not depend on the flags) and then replaced by the maze's 'X' / 'S' cell
+    if (!p.random_goal) { gx = t.xcell[Ld - 1] / W::G; gy = t.xcell[Ld - 1] % W::G; }
+    if (!p.random_ball) { sx = 4; sy = 4; }       // 'S' is (4,4) in all five mazes
   }
   r.L = nl; r.x = sx; r.y = sy; r.gx = gx; r.gy = gy; r.px = sx; r.py = sy; r.a = -1; r.step = 0;
   episode += 1;

@@ -96,13 +96,8 @@ __device__ __forceinline__ void v5_respawn(V5Regs &r, const KParams &p, int64_t 
                                            const FovTables<W> &t, const unsigned char *smem) {
   V2Regs v;
   v.L = r.L; v.x = r.x; v.y = r.y; v.gx = r.gx; v.gy = r.gy; v.px = v.py = 0; v.a = -1; v.step = 0;
-  v2_respawn<W>(v, p, e, episode, t);                     // MAZE_FIRST: maze, then goal, then ball (as v4)
+  v2_respawn<W>(v, p, e, episode, t);                     // MAZE_FIRST: maze, then goal, then ball (as v4); RANDOM_* flags
   r.L = v.L; r.x = v.x; r.y = v.y; r.gx = v.gx; r.gy = v.gy;
-  if (!p.random_goal) {                                   // setGoal() else-branch: the maze's 'X' cell (:483-485)
-    const int xc = reinterpret_cast<const uint16_t *>(smem + W::XCELL_OFF)[r.L - 1];
-    r.gx = xc / W::G; r.gy = xc % W::G;
-  }
-  if (!p.random_ball) { r.x = 4; r.y = 4; }               // setBall() else-branch: the 'S' cell, (4,4) in all five mazes
   r.x1 = r.fx1 = r.fgx = r.lx = r.x;                      // :139-148, and retStatelast = observation (:327-328)
   r.y1 = r.fy1 = r.fgy = r.ly = r.y;
   r.fga = 12;                                             // fovealGoal[0,2,2] = 1 (:131-132)

@@ -250,13 +250,15 @@ class OracleVec(object):
 class OracleHier(object):
     """N oracle envs of the planner/actor variant (lmaze-v5 / v6), batched like LmazeHierCuda."""
 
-    def __init__(self, n, seed=0, env_id0=0):
+    def __init__(self, n, seed=0, env_id0=0, random_ball=True, random_goal=True):
         self.L = lib()
         self.n, self.seed, self.env_id0 = int(n), int(seed), int(env_id0)
         self.env_bytes = self.L.lmzo_sizeof_env()
         self._mem = np.zeros(self.n * self.env_bytes, dtype=np.uint8)
         for i in range(self.n):
             self.L.lmzo_init(self._env(i), V5)
+            if not (random_ball and random_goal):
+                self.L.lmzo_env_set_flags(self._env(i), int(random_ball), int(random_goal))
         self.episode = np.zeros(self.n, dtype=np.uint32)
 
     def _env(self, i):

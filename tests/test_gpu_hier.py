@@ -276,3 +276,49 @@ def test_hier_auto_mask_and_host_step(lmz, oracle_mod):
         want_mask = (gd_ref | ld_ref).astype(np.uint8)
     assert np.array_equal(env.get_state().cpu().numpy()[:, :13], ora.export()[:, :13])
     env.close()
+
+
+@pytest.mark.parametrize("flags", [(False, True), (True, False), (False, False)])
+def test_foveal_random_flags(lmz, oracle_mod, flags):
+    """RANDOM_BALL / RANDOM_GOAL False (lmaze_env_v2.py:51-52,278-299; same in v4, v5): the ball starts on the
+    maze's 'S' cell, the goal sits on its 'X' cell -- device-RNG resets, v2 + v4 + v5 against the oracle."""
+    rb, rg = flags
+    n = 700
+    for variant, ov in (("v2", oracle_mod.V2), ("v4", oracle_mod.V4)):
+        env = lmz.LmazeVecCuda(n, variant, seed=8, autoreset=True, random_ball=rb, random_goal=rg)
+        ora = oracle_mod.OracleVec(ov, n, seed=8, autoreset=True, random_ball=rb, random_goal=rg)
+        assert np.array_equal(u32(env.reset()), u32(ora.reset()))
+        gen = torch.Generator().manual_seed(1)
+        for t in range(60):
+            a = torch.randint(0, 25, (n,), generator=gen)
+            obs, rew, done, _ = env.step(a)
+            o_ref, r_ref, d_ref = ora.step(a.numpy())
+            assert np.array_equal(u32(rew), u32(r_ref)) and np.array_equal(done.cpu().numpy(), d_ref.astype(bool)), (variant, t)
+            assert np.array_equal(u32(obs), u32(o_ref)), (variant, t)
+        st = env.get_state().cpu().numpy()
+        if not rb:
+            assert ((st[:, 4] > 0) | ((st[:, 0] == 4) & (st[:, 1] == 4))).all()     # fresh episodes start on 'S'
+        assert env.stats()["episodes"] > 0
+        env.close()
+    env = lmz.LmazeHierCuda(n, "v5", seed=8, autoreset=True, random_ball=rb, random_goal=rg)
+    ora = oracle_mod.OracleHier(n, seed=8, random_ball=rb, random_goal=rg)
+    assert np.array_equal(u32(env.reset()), u32(ora.reset()))
+    rng = np.random.RandomState(2)
+    mask = np.ones(n, np.uint8)
+    for t in range(60):
+        g = rng.randint(0, 25, size=n); a = rng.randint(0, 4, size=n)
+        env.plannerStep(g, mask=mask); ora.planner_step(g, mask=mask)
+        fov, loc, gr, lr, gd, ld, _, _ = env.step(a, goal_plane=False)
+        fov_ref, loc_ref, gr_ref, lr_ref, gd_ref, ld_ref, err_ref = ora.step(a)
+        gdm = gd_ref.astype(bool)
+        if gdm.any():
+            ora.reset(mask=gdm.astype(np.uint8), want_obs=False)
+            ora.render(mask=gdm.astype(np.uint8), fov=fov_ref, loc=loc_ref)
+        assert np.array_equal(u32(gr), u32(gr_ref)) and np.array_equal(u32(fov), u32(fov_ref)), t
+        assert np.array_equal(u32(loc), u32(loc_ref)), t
+        mask = (gd_ref | ld_ref).astype(np.uint8)
+    st = env.get_state().cpu().numpy()
+    if not rg:                                             # the goal is the maze's 'X' cell
+        xs = {k: [(x, r.index("X")) for x, r in enumerate(oracle_mod.layout_v2(k)) if "X" in r][0] for k in range(1, 6)}
+        assert all((st[i, 6], st[i, 7]) == xs[st[i, 15] >> 4] for i in range(n))
+    env.close()
