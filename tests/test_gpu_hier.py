@@ -322,3 +322,85 @@ def test_foveal_random_flags(lmz, oracle_mod, flags):
         xs = {k: [(x, r.index("X")) for x, r in enumerate(oracle_mod.layout_v2(k)) if "X" in r][0] for k in range(1, 6)}
         assert all((st[i, 6], st[i, 7]) == xs[st[i, 15] >> 4] for i in range(n))
     env.close()
+
+
+def test_hier_one_million_envs(lmz, oracle_mod):
+    """Full size (2^20 envs, 57 GB of observations): two blocks of envs at both ends of the batch are replayed
+    by the oracle from the same seeds (the device RNG is keyed by global env id), and size-independent
+    properties hold over the whole batch."""
+    N = 1 << 20
+    if torch.cuda.mem_get_info()[0] < N * 53900 + (6 << 30):
+        pytest.fail("B200 expected: need %d GiB free" % ((N * 53900 + (6 << 30)) >> 30))
+    seed, B = 4242, 384
+    env = lmz.LmazeHierCuda(N, "v5", seed=seed, autoreset=True)
+    blocks = [(0, oracle_mod.OracleHier(B, seed=seed, env_id0=0)), (N - B - 37, oracle_mod.OracleHier(B, seed=seed, env_id0=N - B - 37))]
+    fov = env.reset()
+    for lo, ora in blocks:
+        assert np.array_equal(u32(fov[lo:lo + B]), u32(ora.reset()))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    masks = [np.ones(B, np.uint8) for _ in blocks]
+    for t in range(12):
+        goals = torch.randint(0, 25, (N,), generator=gen, device="cuda", dtype=torch.uint8)
+        acts = torch.randint(0, 4, (N,), generator=gen, device="cuda", dtype=torch.uint8)
+        env.plannerStep(goals, mask="auto")
+        fov, loc, gr, lr, gd, ld, _, _ = env.step(acts, goal_plane=False)
+        for k, (lo, ora) in enumerate(blocks):
+            ora.planner_step(goals[lo:lo + B].cpu().numpy(), mask=masks[k])
+            fov_ref, loc_ref, gr_ref, lr_ref, gd_ref, ld_ref, err_ref = ora.step(acts[lo:lo + B].cpu().numpy())
+            gdm = gd_ref.astype(bool)
+            if gdm.any():
+                ora.reset(mask=gdm.astype(np.uint8), want_obs=False)
+                ora.render(mask=gdm.astype(np.uint8), fov=fov_ref, loc=loc_ref)
+            assert np.array_equal(u32(gr[lo:lo + B]), u32(gr_ref)) and np.array_equal(u32(lr[lo:lo + B]), u32(lr_ref)), (t, lo)
+            assert np.array_equal(u32(fov[lo:lo + B]), u32(fov_ref)) and np.array_equal(u32(loc[lo:lo + B]), u32(loc_ref)), (t, lo)
+            masks[k] = (gd_ref | ld_ref).astype(np.uint8)
+    # whole batch: rewards are among the reference's constants; every 35x35 plane is a x7 replication; the
+    # fovealGoal channel is one-hot; binary channels hold only 0 / 1
+    allowed_g = torch.tensor([0x42C80000, 0xBC23D70A, 0xBF800000], dtype=torch.int64, device="cuda")
+    assert torch.isin(gr.view(torch.int32).long() & 0xFFFFFFFF, allowed_g).all()
+    CH = 1 << 15
+    for lo in range(0, N, CH):
+        f, l = fov[lo:lo + CH], loc[lo:lo + CH]
+        small = f[:, :, ::7, ::7]
+        assert torch.equal(small.repeat_interleave(7, 2).repeat_interleave(7, 3), f)
+        assert torch.equal(l[:, :, ::7, ::7].repeat_interleave(7, 2).repeat_interleave(7, 3), l)
+        assert (small[:, 3].sum(dim=(1, 2)) == 1).all() and (small[:, 0, 2, 2] == 1).all()      # goal plane one-hot; the ball's own cell is free
+        binary = small[:, [0, 1, 3, 4, 5]]
+        assert ((binary == 0) | (binary == 1)).all() and ((l == 0) | (l == 1)).all()
+        ok = ~env.loc_err[lo:lo + CH]
+        assert (l[ok][:, 3, ::7, ::7].sum(dim=(1, 2)) == 1).all() and (l[~ok].sum(dim=(1, 2, 3)) == 0).all()
+    s = env.stats(check_errors=False)
+    assert s["steps"] == 12 * N and s["wall_bumps"] + s["moves"] == 12 * N
+    env.close()
+
+
+def test_hier_shard_invariance_and_graph_replay(lmz):
+    """Trajectories do not depend on how the batch is split over handles / GPUs, and a captured
+    plannerStep(auto) + step pair replays correctly."""
+    N, seed = 3000, 9
+    whole = lmz.LmazeHierCuda(N, "v5", seed=seed, env_id0=0)
+    lo, hi = lmz.shard_range(N, 1, 3)
+    part = lmz.LmazeHierCuda(hi - lo, "v5", seed=seed, env_id0=lo)
+    assert torch.equal(whole.reset()[lo:hi], part.reset())
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    g_buf = torch.zeros(hi - lo, dtype=torch.uint8, device="cuda")
+    a_buf = torch.zeros(hi - lo, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    part.plannerStep(g_buf, mask="auto"); part.step(a_buf, goal_plane=False)       # warm the launch paths ...
+    part.set_state(whole.get_state()[lo:hi].clone()); part.set_visit(whole.get_visit()[lo:hi].clone())   # ... and rewind
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        part.plannerStep(g_buf, mask="auto")
+        part.step(a_buf, goal_plane=False)
+    for t in range(40):
+        g = torch.randint(0, 25, (N,), generator=gen, device="cuda", dtype=torch.uint8)
+        a = torch.randint(0, 4, (N,), generator=gen, device="cuda", dtype=torch.uint8)
+        whole.plannerStep(g, mask="auto"); whole.step(a, goal_plane=False)
+        g_buf.copy_(g[lo:hi]); a_buf.copy_(a[lo:hi])
+        graph.replay()
+        assert torch.equal(whole.obs[lo:hi], part.obs) and torch.equal(whole.loc_obs[lo:hi], part.loc_obs), t
+        assert torch.equal(whole.reward[lo:hi].view(torch.int32), part.reward.view(torch.int32)), t
+    st_w, st_p = whole.get_state()[lo:hi], part.get_state()
+    assert torch.equal(st_w, st_p) and torch.equal(whole.get_visit()[lo:hi], part.get_visit())
+    whole.close(); part.close()
