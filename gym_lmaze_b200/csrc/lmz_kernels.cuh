@@ -19,6 +19,18 @@
 
 #include "lmz_variants.h"
 
+// tiles per grab of the small-observation kernels (tools/small_bench.py sweep: compact v0 8.6 -> 9.9 G env-steps/s and
+// transition-only 43 -> 116 G with 4; v3 / incremental are instruction-bound and flat)
+#ifndef LMZ_G_COMPACT_V0
+#define LMZ_G_COMPACT_V0 4
+#endif
+#ifndef LMZ_G_COMPACT_V3
+#define LMZ_G_COMPACT_V3 2
+#endif
+#ifndef LMZ_G_INCR
+#define LMZ_G_INCR 2
+#endif
+
 namespace lmz {
 
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
@@ -280,15 +292,17 @@ struct LaneOut {
   uint32_t eplen;     // stepCount of an episode that finished in this call
 };
 
+// `st_old` and `a` are the env's packed state and action, loaded by the caller (so that a kernel can have
+// the loads of several tiles in flight before it needs any of them).
 template <class V>
-__device__ __forceinline__ LaneOut env_lane(const KParams &p, int64_t e, const uint8_t *cls, const uint16_t *cand) {
+__device__ __forceinline__ LaneOut env_lane_pre(const KParams &p, int64_t e, uint32_t st_old, long long a,
+                                                const uint8_t *cls, const uint16_t *cand) {
   LaneOut o;
   o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
-  o.st_old = p.state[e];
+  o.st_old = st_old;
   EnvRegs r = V::unpack(o.st_old);
   bool reset_now = false;
   if (p.mode == MODE_STEP) {
-    const long long a = load_action(p.actions, p.action_dtype, e);
     uint32_t hits = 0;
     const StepOut so = transition<V>(r, a, cls, hits);
     if (V::ID == 0 && hits) p.goal_count[e] += hits;
@@ -311,6 +325,56 @@ __device__ __forceinline__ LaneOut env_lane(const KParams &p, int64_t e, const u
   }
   o.st = V::pack(r);
   if (p.mode != MODE_RENDER) p.state[e] = o.st;
+  return o;
+}
+
+template <class V>
+__device__ __forceinline__ LaneOut env_lane(const KParams &p, int64_t e, const uint8_t *cls, const uint16_t *cand) {
+  const uint32_t st_old = p.state[e];
+  const long long a = (p.mode == MODE_STEP) ? load_action(p.actions, p.action_dtype, e) : 0;
+  return env_lane_pre<V>(p, e, st_old, a, cls, cand);
+}
+
+// Latency-tolerant tile pipeline of the small-observation kernels (compact, incremental, transition-only).
+// Under a saturated write stream a global load or atomic takes several microseconds, and a warp that
+// grabs a tile, loads its 32 states and only then works is bound by that chain (ncu: long_scoreboard is
+// the top stall, ~17 us per tile per warp).  So every warp grabs GROUPS of G consecutive tiles with ONE
+// atomic, keeps the loads of a whole group in flight, and runs two groups ahead: the group being
+// rendered was loaded one iteration ago and grabbed two iterations ago.
+template <int G>
+struct TileGroup {
+  uint32_t st[G];
+  int act[G];           // action, clamped to 0..255 (anything outside 0..3 is the same no-op)
+};
+__device__ __forceinline__ int64_t grab_tiles(unsigned long long *work, int count) {
+  return (int64_t)atomicAdd(&work[0], (unsigned long long)count);
+}
+template <int G>
+__device__ __forceinline__ void preload_group(const KParams &p, int64_t tile0, int lane, int64_t tiles, TileGroup<G> &g) {
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+    const int64_t e = (tile0 + k) * 32 + lane;
+    g.st[k] = 0; g.act[k] = 255;
+    if (tile0 + k < tiles && e < p.n) {
+      g.st[k] = p.state[e];
+      if (p.mode == MODE_STEP) {
+        const long long a = load_action(p.actions, p.action_dtype, e);
+        g.act[k] = (a < 0 || a > 255) ? 255 : (int)a;
+      }
+    }
+  }
+}
+template <class V>
+__device__ __forceinline__ LaneOut tile_lane_pre(const KParams &p, int64_t tile, int lane, int64_t tiles, uint32_t st,
+                                                 int act, const uint8_t *cls, const uint16_t *cand, bool &valid) {
+  LaneOut o;
+  o.st = 0; o.st_old = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
+  const int64_t e = tile * 32 + lane;
+  valid = tile < tiles && e < p.n;
+  if (valid) {
+    o = env_lane_pre<V>(p, e, st, (long long)act, cls, cand);
+    o.render = o.render && p.obs != nullptr && e >= p.win_lo && e < p.win_lo + p.win_n;   // render window
+  }
   return o;
 }
 
@@ -550,44 +614,52 @@ __global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams 
   for (int k = 0; k < K; ++k) base[k] = (lane + 32 * k < (int)W) ? tmpl[lane + 32 * k] : 0u;
   const int64_t tiles = p.tile_end;
   WarpStats ws;
-  // persistent warps, tiles handed out dynamically; software pipelined like the TMA kernel: the next
-  // tile's loads / transitions are issued before the current tile's rows are stored
-  auto next_tile = [&]() {
+  // persistent warps; groups of G tiles handed out dynamically, two groups ahead (see TileGroup)
+  constexpr int G = (V::ID == 0) ? LMZ_G_COMPACT_V0 : LMZ_G_COMPACT_V3;
+  auto next_group = [&]() {
     int64_t t = 0;
-    if (lane == 0) t = p.tile_begin + grab_tile(p.work);
+    if (lane == 0) t = p.tile_begin + grab_tiles(p.work, G);
     return __shfl_sync(0xffffffffu, t, 0);
   };
-  int64_t tile = next_tile();
-  bool valid;
-  LaneOut o = tile_lane<V>(p, tile, lane, tiles, cls, cand, valid);
-  if (p.mode == MODE_STEP) ws.add(valid, o);
-  while (tile < tiles) {
-    const int64_t ntile = next_tile();
-    bool nvalid;
-    const LaneOut no = tile_lane<V>(p, ntile, lane, tiles, cls, cand, nvalid);
-    if (p.mode == MODE_STEP) ws.add(nvalid, no);
-    const unsigned rmask = __ballot_sync(0xffffffffu, valid && o.render);
-    if (rmask) {
+  int64_t t0 = next_group(), t1 = next_group();
+  TileGroup<G> pre;
+  preload_group<G>(p, t0, lane, tiles, pre);
+  while (t0 < tiles) {
+    const int64_t t2 = next_group();                 // needed two iterations from now
+    uint32_t st[G];
+    unsigned rmask[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {                    // transitions of the group loaded one iteration ago
+      bool valid;
+      const LaneOut o = tile_lane_pre<V>(p, t0 + k, lane, tiles, pre.st[k], pre.act[k], cls, cand, valid);
+      if (p.mode == MODE_STEP) ws.add(valid, o);
+      st[k] = o.st;
+      rmask[k] = __ballot_sync(0xffffffffu, valid && o.render);
+    }
+    preload_group<G>(p, t1, lane, tiles, pre);       // next group's loads fly while this group's rows are stored
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      if (!rmask[k]) continue;
       uint32_t hot[V::NHOT];
-      V::hot_bytes(V::unpack(o.st), hot);
-      uint32_t *dst = reinterpret_cast<uint32_t *>(p.obs) + (size_t)(tile * 32 - p.win_lo) * W;
-      for (unsigned m = rmask; m; m &= m - 1) {
+      V::hot_bytes(V::unpack(st[k]), hot);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(p.obs) + (size_t)((t0 + k) * 32 - p.win_lo) * W;
+      for (unsigned m = rmask[k]; m; m &= m - 1) {
         const int env = __ffs(m) - 1;
         uint32_t h[V::NHOT];
 #pragma unroll
         for (int q = 0; q < V::NHOT; ++q) h[q] = __shfl_sync(0xffffffffu, hot[q], env);
         uint32_t *row = dst + (size_t)env * W;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const uint32_t w = lane + 32 * k;
-          uint32_t v = base[k];
+        for (int kk = 0; kk < K; ++kk) {
+          const uint32_t w = lane + 32 * kk;
+          uint32_t v = base[kk];
 #pragma unroll
           for (int q = 0; q < V::NHOT; ++q) v |= ((h[q] >> 2) == w) ? (1u << (8 * (h[q] & 3))) : 0u;
           if (w < W) __stcs(row + w, v);
         }
       }
     }
-    tile = ntile; o = no; valid = nvalid;
+    t0 = t1; t1 = t2;
   }
   if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
   if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
@@ -628,58 +700,74 @@ __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) 
     else if (b == 0) { ch = 1; row = r.x * V::E; col = r.y * V::E; }
     else { ch = 2; row = r.gx * V::E; col = r.gy * V::E; }
   };
-  int64_t tile = next_tile();
-  bool valid;
-  LaneOut o = tile_lane<V>(p, tile, lane, tiles, cls, cand, valid);
-  ws.add(valid, o);
-  while (tile < tiles) {
-    const int64_t ntile = next_tile();
-    bool nvalid;
-    const LaneOut no = tile_lane<V>(p, ntile, lane, tiles, cls, cand, nvalid);
-    ws.add(nvalid, no);
-    // which envs of the tile have a block that moved?
-    bool moved = false;
-    if (valid && o.render) {
+  constexpr int G = LMZ_G_INCR;
+  auto next_group = [&]() {
+    int64_t t = 0;
+    if (lane == 0) t = p.tile_begin + grab_tiles(p.work, G);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
+  int64_t t0 = next_group(), t1 = next_group();
+  TileGroup<G> pre;
+  preload_group<G>(p, t0, lane, tiles, pre);
+  while (t0 < tiles) {
+    const int64_t t2 = next_group();
+    uint32_t st_new[G], st_old[G];
+    unsigned mmask[G];
 #pragma unroll
-      for (int b = 0; b < NBLK; ++b) {
-        int c0, r0, q0, c1, r1, q1;
-        block_of(o.st_old, b, c0, r0, q0); block_of(o.st, b, c1, r1, q1);
-        moved = moved || r0 != r1 || q0 != q1;
+    for (int k = 0; k < G; ++k) {
+      bool valid;
+      const LaneOut o = tile_lane_pre<V>(p, t0 + k, lane, tiles, pre.st[k], pre.act[k], cls, cand, valid);
+      ws.add(valid, o);
+      // which envs of the tile have a block that moved?
+      bool moved = false;
+      if (valid && o.render) {
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b) {
+          int c0, r0, q0, c1, r1, q1;
+          block_of(o.st_old, b, c0, r0, q0); block_of(o.st, b, c1, r1, q1);
+          moved = moved || r0 != r1 || q0 != q1;
+        }
       }
+      st_new[k] = o.st; st_old[k] = o.st_old;
+      mmask[k] = __ballot_sync(0xffffffffu, moved);
     }
-    for (unsigned m = __ballot_sync(0xffffffffu, moved); m; m &= m - 1) {
-      const int l = __ffs(m) - 1;
-      const uint32_t so = __shfl_sync(0xffffffffu, o.st_old, l), sn = __shfl_sync(0xffffffffu, o.st, l);
-      float *img = reinterpret_cast<float *>(p.obs) + (size_t)(tile * 32 + l - p.win_lo) * (V::OBS_BYTES / 4);
+    preload_group<G>(p, t1, lane, tiles, pre);
 #pragma unroll
-      for (int b = 0; b < NBLK; ++b) {
-        int ch, r0, q0, r1, q1;
-        block_of(so, b, ch, r0, q0); block_of(sn, b, ch, r1, q1);
-        if (r0 == r1 && q0 == q1) continue;
-        // The plane holds ONE block of ones, so every element's value follows from the new position.  Rewrite
-        // whole aligned 32-byte sectors around the old and the new block (values computed, not read): full-sector
-        // writes need no read-modify-write in L2/DRAM, and the two passes may overlap freely (same values).
-        float *plane = img + (size_t)ch * V::S * V::S;            // 32-byte aligned (plane = 28,224 / 20,736 B)
+    for (int k = 0; k < G; ++k) {
+      for (unsigned m = mmask[k]; m; m &= m - 1) {
+        const int l = __ffs(m) - 1;
+        const uint32_t so = __shfl_sync(0xffffffffu, st_old[k], l), sn = __shfl_sync(0xffffffffu, st_new[k], l);
+        float *img = reinterpret_cast<float *>(p.obs) + (size_t)((t0 + k) * 32 + l - p.win_lo) * (V::OBS_BYTES / 4);
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int brow = pass ? r1 : r0, bcol = pass ? q1 : q0;
+        for (int b = 0; b < NBLK; ++b) {
+          int ch, r0, q0, r1, q1;
+          block_of(so, b, ch, r0, q0); block_of(sn, b, ch, r1, q1);
+          if (r0 == r1 && q0 == q1) continue;
+          // The plane holds ONE block of ones, so every element's value follows from the new position.  Rewrite
+          // whole aligned 32-byte sectors around the old and the new block (values computed, not read): full-sector
+          // writes need no read-modify-write in L2/DRAM, and the two passes may overlap freely (same values).
+          float *plane = img + (size_t)ch * V::S * V::S;            // 32-byte aligned (plane = 28,224 / 20,736 B)
 #pragma unroll
-          for (int k0 = 0; k0 < V::E * 16; k0 += 32) {
-            const int k = k0 + lane, rr = k >> 4, j = k & 15;       // row of the block, float slot in its <= 64-byte span
-            if (rr < V::E) {
-              const int first = (brow + rr) * V::S + bcol;          // the row segment [first, first + E)
-              const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
-              const int e = lo + j;
-              if (e < hi) {
-                const int er = e / V::S, ec = e - er * V::S;
-                plane[e] = (er >= r1 && er < r1 + V::E && ec >= q1 && ec < q1 + V::E) ? 1.0f : 0.0f;
+          for (int pass = 0; pass < 2; ++pass) {
+            const int brow = pass ? r1 : r0, bcol = pass ? q1 : q0;
+#pragma unroll
+            for (int k0 = 0; k0 < V::E * 16; k0 += 32) {
+              const int kk = k0 + lane, rr = kk >> 4, j = kk & 15;    // row of the block, float slot in its <= 64-byte span
+              if (rr < V::E) {
+                const int first = (brow + rr) * V::S + bcol;          // the row segment [first, first + E)
+                const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
+                const int e = lo + j;
+                if (e < hi) {
+                  const int er = e / V::S, ec = e - er * V::S;
+                  plane[e] = (er >= r1 && er < r1 + V::E && ec >= q1 && ec < q1 + V::E) ? 1.0f : 0.0f;
+                }
               }
             }
           }
         }
       }
     }
-    tile = ntile; o = no; valid = nvalid;
+    t0 = t1; t1 = t2;
   }
   ws.flush(p.stats, lane);
   if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
