@@ -114,11 +114,13 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(variant, render_mode):
-    """dram bytes per launch from the committed `ncu --set full` capture, if any."""
+def recorded_traffic(variant, render_mode, n_envs):
+    """dram bytes per launch from the committed `ncu --set full` capture, if any (scaled to this batch size)."""
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return rec.get("%s_%s" % (variant, render_mode))
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s" % (variant, render_mode))
+        if isinstance(rec, dict):
+            return rec["bytes"] * n_envs / rec["envs"]
+        return rec
     except Exception:
         return None
 
@@ -438,8 +440,8 @@ def run_ours(args):
                        "full obs D2H variant", "reward_checksum": checksum},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(args.variant, args.render_mode)
-                     if (args.obs_mode == "full" and W == N and N == 1 << 20) else None, "peak_source": peak_src,
+                     "traffic": recorded_traffic(args.variant, args.render_mode, N)
+                     if (args.obs_mode == "full" and W == N) else None, "peak_source": peak_src,
                      "kernel": "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4", "v5") else
                      "lmz_env_incr_kernel<%s>" % args.variant.upper() if args.render_mode == "incremental" else
                      "lmz_env_%s_kernel<%s>" % ("compact" if args.obs_mode == "compact" else

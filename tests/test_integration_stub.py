@@ -16,6 +16,8 @@ def load_stub():
     code = code.replace('ctypes.CDLL("liblmaze_b200.so")', "ctypes.CDLL(%r)" % _abi.LIB_PATH)
     ns = {}
     exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    hier = re.search(r"```python\n(# gym_lmaze/envs/lmaze_env_v5_cuda\.py.*?)```", md, re.S).group(1)
+    exec(compile(hier, "INTEGRATION.md (v5)", "exec"), ns)
     return ns, _abi
 
 
@@ -41,4 +43,24 @@ def test_stub_runs_and_matches_the_package():
     ob, rb, db, _ = b.step(acts)
     assert torch.equal(oa, ob) and torch.equal(ra.view(torch.int32), rb.view(torch.int32)) and torch.equal(da, db)
     assert ia is acts
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_hier_stub_runs_and_matches_the_package():
+    import torch
+    import gym_lmaze_b200 as lmz
+    ns, _ = load_stub()
+    a = ns["LmazeHierEnvCuda"](300, device=0, seed=11)
+    b = lmz.LmazeHierCuda(300, "v5", device="cuda:0", seed=11)
+    assert torch.equal(a.reset(), b.reset())
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(30):
+        goals = torch.randint(0, 25, (300,), generator=gen, device="cuda", dtype=torch.uint8)
+        acts = torch.randint(0, 4, (300,), generator=gen, device="cuda", dtype=torch.uint8)
+        assert torch.equal(a.plannerStep(goals), b.plannerStep(goals, mask="auto"))
+        ta, tb = a.step(acts), b.step(acts)
+        for x, y in zip(ta[:7], tb[:7]):
+            assert torch.equal(x, y)
+        assert ta[7] is acts
     a.close(); b.close()
