@@ -377,9 +377,9 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (W::HAS_LOC && !h->local_bound)
     return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
   // CTA size (tools/fov_sweep.py, tools/hier_bench.py): one CTA per SM in every case (the visit variants need
-  // 167 / 185 KB of shared memory); v4, whose producers also write every layer back, is best with 384 rendering
-  // threads -- more of them queue ahead of the producers' loads and stores in the SM's memory pipeline
-  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 4 ? 512 : 1024);
+  // 167 / 185 KB of shared memory); v4 / v5, whose producer warps also stream the visit layers in and out, are
+  // best with 384 rendering threads -- more of them queue ahead of the producers in the SM's memory pipeline
+  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::NVIS > 0 ? 512 : 1024);
   if (t == 256) return launch_fov_t<W, 256>(h, p, s);
   if (t == 1024) return launch_fov_t<W, 1024>(h, p, s);
   return launch_fov_t<W, 512>(h, p, s);

@@ -31,12 +31,12 @@ namespace lmz {
 
 template <int ID, int C>
 __device__ __forceinline__ FovLane<5> fov_lane(const Fov<ID, C> *, const KParams &p, int64_t e,
-                                               const FovTables<Fov<ID, C>> &t, const unsigned char *) {
-  return v2_lane<Fov<ID, C>>(p, e, t);
+                                               const FovTables<Fov<ID, C>> &t, const unsigned char *, const FovPre &pre) {
+  return v2_lane<Fov<ID, C>>(p, e, t, pre);
 }
 __device__ __forceinline__ V5Lane fov_lane(const V5 *, const KParams &p, int64_t e, const FovTables<V5> &t,
-                                           const unsigned char *smem) {
-  return v5_lane<V5>(p, e, t, smem);
+                                           const unsigned char *smem, const FovPre &pre) {
+  return v5_lane<V5>(p, e, t, smem, pre);
 }
 
 template <class W, int THREADS>
@@ -62,24 +62,40 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
   WarpStats ws;
 
-  auto produce = [&](int buf) {              // warp 0 only
-    int64_t tl = 0;
-    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
-    tl = __shfl_sync(0xffffffffu, tl, 0);
+  // Warp 0 runs ONE TILE AHEAD of its own loads: when it turns to a tile, the tile's index was grabbed and its
+  // state words / actions (and, for the visit variants, the bulk load of its 32 visit layers) were issued a
+  // whole tile time earlier, so no DRAM or atomic round trip -- several microseconds each under a saturated
+  // write stream -- sits between two tiles of the producer.
+  int64_t tl_next = 0;                       // warp 0: the tile produce() turns to next
+  FovPre pre_next;                           // ... and its preloaded words (this lane's env)
+  pre_next.w0 = pre_next.w1 = pre_next.w2 = 0u; pre_next.act = 0;
+  auto prefetch = [&](int64_t tl, int vb) {  // warp 0: start everything tile `tl` will need
     if (W::NVIS > 0 && need_visit && lane == 0 && tl < tiles) {
-      // the tile's 32 visit layers are 41,472 contiguous bytes: ONE bulk async (TMA) load, in flight while
-      // this warp runs the transitions
+      // the tile's 32 visit layers are 41,472 contiguous bytes: ONE bulk async (TMA) load
       const int64_t e0 = tl * 32;
       const uint32_t bytes = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G * 4));
-      mbar_expect_tx(&vbar[buf], bytes);
-      bulk_g2s(vbuf + buf * (32 * W::G * W::G), p.visit + e0 * (W::G * W::G), bytes, &vbar[buf]);
+      mbar_expect_tx(&vbar[vb], bytes);
+      bulk_g2s(vbuf + vb * (32 * W::G * W::G), p.visit + e0 * (W::G * W::G), bytes, &vbar[vb]);
     }
+    const int64_t e = tl * 32 + lane;
+    if (tl < tiles && e < p.n) pre_next = fov_preload<W>(p, e);
+    tl_next = tl;
+  };
+  auto grab = [&]() {
+    int64_t tl = 0;
+    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
+    return __shfl_sync(0xffffffffu, tl, 0);
+  };
+  auto produce = [&](int buf) {              // warp 0 only
+    const int64_t tl = tl_next;
+    const FovPre pre = pre_next;
+    const int64_t tl_after = grab();         // in flight while this tile's transitions run
     const int64_t e = tl * 32 + lane;
     const bool valid = tl < tiles && e < p.n;
     FovLane<W::NBIT> v;
     v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
     v.rfov = false; v.rloc = false;
-    if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, smem);
+    if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, smem, pre);
     if (p.mode == MODE_STEP) ws.add(valid, v.o);
     if (valid && (v.rfov || v.rloc)) {       // 25-bit planes -> float planes (lane stride VALS is odd: no bank conflicts)
       float *mv = vals + (buf * 32 + lane) * W::VALS;
@@ -95,6 +111,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
     const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
     if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = tl; }
+    prefetch(tl_after, buf ^ 1);             // vbuf[buf ^ 1] is free: its tile's visit pass ended before the last barrier
   };
   // visit layers of one tile's 32 envs: 32 x 324 consecutive floats, coalesced pass by the PROD producer
   // threads: state[2] = (state[2] + visitMap) / 2 in float64, stored as float32
@@ -130,7 +147,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };
   auto pick = [](uint32_t en, const float *gv) -> uint4 { return f4_pick(en, gv); };
 
-  if (warp == 0) produce(0);
+  if (warp == 0) { prefetch(grab(), 0); produce(0); }
   if (W::NVIS > 0 && tid < PROD) { producers_sync(); visit_pass(0); }
   for (int buf = 0;; buf ^= 1) {
     __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again

@@ -177,18 +177,32 @@ struct FovLane {
 };
 using V2Lane = FovLane<5>;  // free, goal, action, previous free, previous goal
 
+// An env's packed state words and its action / goal, loaded ahead of time by the kernel (lmz_fov.cuh keeps
+// the loads of the NEXT tile in flight while it works on the current one).
+struct FovPre {
+  uint32_t w0, w1, w2;
+  long long act;
+};
 template <class W>
-__device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const FovTables<W> &t) {
+__device__ __forceinline__ FovPre fov_preload(const KParams &p, int64_t e) {
+  FovPre q;
+  q.w0 = p.state[e]; q.w1 = p.goal_count[e]; q.w2 = W::HAS_LOC ? p.aux2[e] : 0u;
+  q.act = (p.mode == MODE_STEP || p.mode == 3 /* MODE_PLANNER */) ? load_action(p.actions, p.action_dtype, e) : 0;
+  return q;
+}
+
+template <class W>
+__device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const FovTables<W> &t, const FovPre &pre) {
   V2Lane out;
   LaneOut &o = out.o;
   o.st_old = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
-  V2Regs r = v2_unpack(p.state[e], p.goal_count[e]);
+  V2Regs r = v2_unpack(pre.w0, pre.w1);
   bool reset_now = false;
   int reward_code = RC_NEG_ZERO;
   uint32_t visit_op = 0;
   if (p.mode == MODE_STEP) {
     visit_op = 1;
-    long long a64 = load_action(p.actions, p.action_dtype, e);
+    long long a64 = pre.act;
     if (a64 < 0 || a64 > 24) { atomicAdd(p.errors, 1u); a64 = a64 < 0 ? 0 : 24; }   // reference raises IndexError
     const int a = (int)a64;
     r.step = r.step < W::STEP_SAT ? r.step + 1 : W::STEP_SAT;                      // :148

@@ -114,17 +114,18 @@ __device__ __forceinline__ bool v5_np_index(int &i) {
 using V5Lane = FovLane<V5::NBIT>;   // info: x | y | shown retStatelast x | y | visit op (0 read, 1 average, 2 zero) | loc_err
 
 template <class W>
-__device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const FovTables<W> &t, const unsigned char *smem) {
+__device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const FovTables<W> &t, const unsigned char *smem,
+                                         const FovPre &pre) {
   V5Lane out;
   LaneOut &o = out.o;
   o.st_old = 0; o.render = false; o.done = false; o.cls = -1; o.eplen = 0;
   out.rfov = false; out.rloc = false;
-  V5Regs r = v5_unpack(p.state[e], p.goal_count[e], p.aux2[e]);
+  V5Regs r = v5_unpack(pre.w0, pre.w1, pre.w2);
   bool reset_now = false, write_state = false;
   uint32_t visit_op = 0;
   int slx = r.lx, sly = r.ly;                       // the retStatelast window the FOVEAL obs of this call shows
   if (p.mode == MODE_STEP) {
-    const long long a = load_action(p.actions, p.action_dtype, e);
+    const long long a = pre.act;
     r.x1 = r.x; r.y1 = r.y;                                                          // :192-193
     r.step = r.step < W::STEP_SAT ? r.step + 1 : W::STEP_SAT;                        // :196
     int dx = 0, dy = 0;                                                              // :203-217
@@ -162,7 +163,7 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     // auto mask: the envs that are waiting for their planner -- local episode over, or no plannerStep since reset()
     const bool take = p.auto_mask ? (r.ld != 0 || r.fstep == 0) : (p.mask == nullptr || p.mask[e] != 0);
     if (take) {
-      long long g = load_action(p.actions, p.action_dtype, e);
+      long long g = pre.act;
       if (g < 0 || g > 24) { atomicAdd(p.errors, 1u); g = g < 0 ? 0 : 24; }         // the reference raises IndexError (:168)
       r.step = 0; r.ld = 0;                                                          // :161-163
       r.fga = (int)g;                                                                // :165-168
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(THREADS) lmz_planner_kernel(const KParams p) {
     v.rloc = false; v.info = 0;
 #pragma unroll
     for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
-    if (valid) v = v5_lane<W>(p, e, t, smem);
+    if (valid) v = v5_lane<W>(p, e, t, smem, fov_preload<W>(p, e));
     unsigned flags = __ballot_sync(0xffffffffu, valid && v.rloc);
     while (flags) {
       const int src = __ffs(flags) - 1;
