@@ -363,7 +363,9 @@ int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     configured_dev = h->cfg.device;
   }
   const int64_t units = p.tile_end - p.tile_begin;
-  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  int per_sm = h->cfg.tune[2] > 0 ? h->cfg.tune[2] : 1;          // default: ONE persistent CTA per SM
+  if (per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+  int64_t grid = (int64_t)h->num_sms * per_sm;
   if (grid > units) grid = units;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, THREADS, W::SMEM_BYTES, s>>>(p);
@@ -376,12 +378,20 @@ template <class W>
 int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (W::HAS_LOC && !h->local_bound)
     return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
-  // CTA size (tools/fov_sweep.py, tools/hier_bench.py): one CTA per SM in every case (the visit variants need
-  // 167 / 185 KB of shared memory); v4 / v5, whose producer warps also stream the visit layers in and out, are
-  // best with 384 rendering threads -- more of them queue ahead of the producers in the SM's memory pipeline
-  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::NVIS > 0 ? 512 : 1024);
-  if (t == 256) return launch_fov_t<W, 256>(h, p, s);
-  if (t == 1024) return launch_fov_t<W, 1024>(h, p, s);
+  // CTA size and CTAs per SM (tools/fov_sweep2.py).  FEWER storing warps reach a HIGHER write bandwidth on a B200:
+  // v2 with ONE 128-thread CTA per SM (1 producer warp + 3 rendering warps) streams 7.47 TB/s, the pure-write
+  // ceiling, against 7.0 TB/s with 1024 threads and 6.3 TB/s with two 128-thread CTAs per SM; v4 is best with 224
+  // threads (4 producer warps for the visit layers + 3 rendering warps, 6.5 TB/s); v5, which writes two tensors
+  // per env and needs more instructions per byte, is flat from 288 threads up (6.3 TB/s).
+  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 2 ? 128 : W::ID == 4 ? 224 : 512);
+  constexpr int LO = W::NVIS > 0 ? 160 : 64;            // visit variants: 128 producer threads + at least one rendering warp
+  switch (t) {
+#define LMZ_FOV_CASE(T) case T: return launch_fov_t<W, (T >= LO ? T : 512)>(h, p, s);
+    LMZ_FOV_CASE(64) LMZ_FOV_CASE(96) LMZ_FOV_CASE(128) LMZ_FOV_CASE(160) LMZ_FOV_CASE(192) LMZ_FOV_CASE(224)
+    LMZ_FOV_CASE(256) LMZ_FOV_CASE(320) LMZ_FOV_CASE(384) LMZ_FOV_CASE(1024)
+#undef LMZ_FOV_CASE
+    default: break;
+  }
   return launch_fov_t<W, 512>(h, p, s);
 }
 
@@ -623,10 +633,10 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     return fail(LMZ_ERR_INVALID, "unknown obs_mode %d", cfg->obs_mode);
   {
     const int t = cfg->tune[0];
-    if (t != 0 && t != 32 && t != 64 && t != 128 && t != 256 && t != 512 && t != 1024)
-      return fail(LMZ_ERR_INVALID, "tune[0] (threads per CTA) must be 0, 32, 64, 128, 256, 512 or 1024");
+    if (t < 0 || t > 1024 || (t & 31))
+      return fail(LMZ_ERR_INVALID, "tune[0] (threads per CTA) must be 0 or a multiple of 32 up to 1024");
     if (cfg->tune[1] < 0 || cfg->tune[1] > 4) return fail(LMZ_ERR_INVALID, "tune[1] (L2 policy) must be 0..4");
-    if (cfg->tune[2] != 0) return fail(LMZ_ERR_INVALID, "tune[2] is reserved and must be 0");
+    if (cfg->tune[2] < 0 || cfg->tune[2] > 32) return fail(LMZ_ERR_INVALID, "tune[2] (CTAs per SM cap) must be 0..32");
     if (cfg->tune[3] < 0 || (cfg->tune[3] & 15)) return fail(LMZ_ERR_INVALID, "tune[3] (bulk split) must be a multiple of 16");
   }
   int ndev = 0;

@@ -26,6 +26,9 @@
 #ifndef LMZ_VISIT_PROD
 #define LMZ_VISIT_PROD 128
 #endif
+#ifndef LMZ_V2_PROD
+#define LMZ_V2_PROD 32    // v2: one dedicated producer warp (0: warp 0 produces, then renders with the others)
+#endif
 
 namespace lmz {
 
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   __shared__ uint32_t s_info[2][32];
   __shared__ uint32_t s_flags[2][2];         // [buf][0 obs, 1 local obs]: bit l = env l of the tile is written
   __shared__ long long s_tile[2];
-  constexpr int PROD = (W::NVIS > 0) ? (THREADS >= 512 ? LMZ_VISIT_PROD : 64) : 0;   // threads that never render
+  constexpr int PROD = (W::NVIS > 0) ? LMZ_VISIT_PROD : LMZ_V2_PROD;   // threads that never render
   constexpr int CTHREADS = THREADS - PROD;
   static_assert(CTHREADS >= 32, "need at least one rendering warp");
   static_assert((uint32_t)CTHREADS < W::OBS_FLOATS, "index stepping assumes fewer threads than entries");
@@ -153,13 +156,12 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
     const int64_t tile = s_tile[buf];
     if (tile >= tiles) break;
-    if (W::NVIS > 0 && tid < PROD) {
+    if (PROD > 0 && tid < PROD) {
       if (warp == 0) produce(buf ^ 1);
-      producers_sync();
-      visit_pass(buf ^ 1);
+      if (W::NVIS > 0) { producers_sync(); visit_pass(buf ^ 1); }
       continue;
     }
-    if (W::NVIS == 0 && warp == 0) produce(buf ^ 1);
+    if (PROD == 0 && warp == 0) produce(buf ^ 1);
     const int ctid = tid - PROD;
     const float *tv = vals + buf * 32 * W::VALS;
     const int64_t row0 = tile * 32 - p.win_lo;                     // obs row of the tile's first env

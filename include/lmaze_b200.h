@@ -91,9 +91,10 @@ typedef struct lmz_config {
   int32_t  random_goal;   /* RANDOM_GOAL  (lmaze_env_v3.py:104); ignored by v0 */
   int32_t  render_mode;   /* lmz_render_mode */
   int32_t  tune[4];       /* launch tuning for the TMA render path, 0 = library default:
-                             [0] threads per CTA (TMA path: 32/64/128/256 issuing warps x32; ST128 path: 256/512/1024)
+                             [0] threads per CTA (TMA path: 32/64/128/256 issuing warps x32; ST128 path: 256/512/1024;
+                                 foveal kernels: 64..384 in steps of 32, 512, 1024)
                              [1] L2 policy of the obs stores: 1 evict_first, 2 evict_normal, 3 evict_last, 4 none
-                             [2] reserved (0): tiles of 32 envs are handed to SMs dynamically
+                             [2] foveal kernels: resident CTAs per SM (0 = library default, one)
                              [3] split bulk copies into pieces of at most this many bytes (multiple of 16) */
   int32_t  obs_mode;      /* lmz_obs_mode */
   int32_t  reserved[2];   /* must be zero */
