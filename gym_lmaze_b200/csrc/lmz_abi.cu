@@ -294,7 +294,12 @@ int launch_compact(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     configured_dev = h->cfg.device;
   }
   const int64_t units = p.tile_end - p.tile_begin;
-  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  // resident CTAs per SM (tools/small_bench.py): with observations to write, TWO 4-warp CTAs per SM stream more
+  // (10.9 vs 9.9 G env-steps/s on v0) than the 8 that fit -- fewer storing warps, higher write bandwidth; the
+  // transition-only launch (14 B per env, latency-bound) wants them all
+  int per_sm = h->cfg.tune[2] > 0 ? h->cfg.tune[2] : (p.obs != nullptr ? 2 : ctas_per_sm);
+  if (per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+  int64_t grid = (int64_t)h->num_sms * per_sm;
   const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
@@ -317,7 +322,9 @@ int launch_incremental(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     configured_dev = h->cfg.device;
   }
   const int64_t units = p.tile_end - p.tile_begin;
-  int64_t grid = (int64_t)h->num_sms * ctas_per_sm;
+  int per_sm = h->cfg.tune[2] > 0 ? h->cfg.tune[2] : (V::ID == 0 ? 4 : 6);      // tools/small_bench.py: +10 % over full occupancy
+  if (per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+  int64_t grid = (int64_t)h->num_sms * per_sm;
   const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;

@@ -18,8 +18,11 @@ def run(tag, n, variant, **kw):
     ms = e0.elapsed_time(e1) / 40
     print("%-16s n=%d  %.4f ms  %.2f G env-steps/s" % (tag, n, ms, n / ms / 1e6), flush=True)
     env.close()
-run("compact v0", 1 << 24, "v0", obs_mode="compact")
-run("compact v3", 1 << 23, "v3", obs_mode="compact")
-run("incr v0", 1 << 20, "v0", render_mode="incremental")
-run("incr v3", 1 << 20, "v3", render_mode="incremental")
-run("transition v0", 1 << 24, "v0", with_obs=False)
+for cap in ([int(c) for c in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0]):
+    t = (0, 0, cap, 0)
+    print("CTAs per SM cap", cap)
+    run("compact v0", 1 << 24, "v0", obs_mode="compact", tune=t)
+    run("compact v3", 1 << 23, "v3", obs_mode="compact", tune=t)
+    run("incr v0", 1 << 20, "v0", render_mode="incremental", tune=t)
+    run("incr v3", 1 << 20, "v3", render_mode="incremental", tune=t)
+    run("transition v0", 1 << 24, "v0", with_obs=False, tune=t)
