@@ -389,17 +389,17 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   // v2 with ONE 128-thread CTA per SM (1 producer warp + 3 rendering warps) streams 7.47 TB/s, the pure-write
   // ceiling, against 7.0 TB/s with 1024 threads and 6.3 TB/s with two 128-thread CTAs per SM; v4 is best with 224
   // threads (4 producer warps for the visit layers + 3 rendering warps, 6.5 TB/s); v5, which writes two tensors
-  // per env and needs more instructions per byte, is flat from 288 threads up (6.3 TB/s).
+  // per env and needs more instructions per byte, is flat from 256 threads up (6.3 TB/s).
   const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 2 ? 128 : W::ID == 4 ? 224 : 512);
-  constexpr int LO = W::NVIS > 0 ? 160 : 64;            // visit variants: 128 producer threads + at least one rendering warp
   switch (t) {
-#define LMZ_FOV_CASE(T) case T: return launch_fov_t<W, (T >= LO ? T : 512)>(h, p, s);
-    LMZ_FOV_CASE(64) LMZ_FOV_CASE(96) LMZ_FOV_CASE(128) LMZ_FOV_CASE(160) LMZ_FOV_CASE(192) LMZ_FOV_CASE(224)
-    LMZ_FOV_CASE(256) LMZ_FOV_CASE(320) LMZ_FOV_CASE(384) LMZ_FOV_CASE(1024)
-#undef LMZ_FOV_CASE
+    case 128: if (W::NVIS == 0) return launch_fov_t<W, (W::NVIS == 0 ? 128 : 512)>(h, p, s); break;   // v2 only: the visit
+    case 224: return launch_fov_t<W, 224>(h, p, s);                                  // variants keep 128 producer threads
+    case 256: return launch_fov_t<W, 256>(h, p, s);
+    case 512: return launch_fov_t<W, 512>(h, p, s);
+    case 1024: return launch_fov_t<W, 1024>(h, p, s);
     default: break;
   }
-  return launch_fov_t<W, 512>(h, p, s);
+  return fail(LMZ_ERR_INVALID, "foveal kernels are built for tune[0] = 128 (v2 only), 224, 256, 512 or 1024 threads (got %d)", t);
 }
 
 // plannerStep (lmaze-v5/v6): warp-granular kernel, several small CTAs per SM

@@ -92,7 +92,7 @@ typedef struct lmz_config {
   int32_t  render_mode;   /* lmz_render_mode */
   int32_t  tune[4];       /* launch tuning for the TMA render path, 0 = library default:
                              [0] threads per CTA (TMA path: 32/64/128/256 issuing warps x32; ST128 path: 256/512/1024;
-                                 foveal kernels: 64..384 in steps of 32, 512, 1024)
+                                 foveal kernels: 128 (v2), 224, 256, 512, 1024)
                              [1] L2 policy of the obs stores: 1 evict_first, 2 evict_normal, 3 evict_last, 4 none
                              [2] foveal / compact / incremental kernels: resident CTAs per SM (0 = library default)
                              [3] split bulk copies into pieces of at most this many bytes (multiple of 16) */

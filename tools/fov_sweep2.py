@@ -27,7 +27,7 @@ def run(variant, N, nbytes, thr, cap):
     ms = e0.elapsed_time(e1) / 12
     print("%s threads=%4d ctas/sm<=%d: %.3f ms  %.1f M env-steps/s  %.0f GB/s" % (variant, thr, cap, ms, N / ms / 1e3, N * nbytes / ms / 1e6), flush=True)
     env.close(); del env
-cfgs = [(int(c.split("x")[0]), int(c.split("x")[1])) for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else "256x1,512x1,1024x1".split(","))]
+cfgs = [(int(c.split("x")[0]), int(c.split("x")[1])) for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else "224x1,256x1,512x1,1024x1".split(","))]
 sizes = {"v2": (1 << 22, 24514), "v4": (1 << 21, 36906), "v5": (1 << 20, 56400)}
 for variant in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["v2", "v4", "v5"]):
     for thr, cap in cfgs:
