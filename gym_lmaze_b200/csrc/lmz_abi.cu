@@ -389,7 +389,7 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   // v2 with ONE 128-thread CTA per SM (1 producer warp + 3 rendering warps) streams 7.47 TB/s, the pure-write
   // ceiling, against 7.0 TB/s with 1024 threads and 6.3 TB/s with two 128-thread CTAs per SM; v4 is best with 224
   // threads (4 producer warps for the visit layers + 3 rendering warps, 6.5 TB/s); v5, which writes two tensors
-  // per env and needs more instructions per byte, is flat from 256 threads up (6.3 TB/s).
+  // per env and needs more instructions per byte, needs 320 threads or more and is flat from there (6.3 TB/s).
   const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 2 ? 128 : W::ID == 4 ? 224 : 512);
   switch (t) {
     case 128: if (W::NVIS == 0) return launch_fov_t<W, (W::NVIS == 0 ? 128 : 512)>(h, p, s); break;   // v2 only: the visit
