@@ -246,7 +246,9 @@ def run_reference(args):
 
 def workload_config(args, note=None):
     G, E, C = {"v0": (12, 7, 4), "v3": (18, 4, 3), "v2": (5, 7, 5), "v4": (5, 7, 7), "v5": (5, 7, 11)}[args.variant]   # v2/v4/v5: 5x5 fovea; v5: (7,35,35) + (4,35,35)
-    if args.obs_mode == "compact":
+    if args.obs_mode == "compact" and args.variant in ("v2", "v4", "v5"):
+        obs, per_env = "f32 (%d,5,5) compact (the 5x5 crops; reference image = x7 replication)" % C, C * 25 * 4
+    elif args.obs_mode == "compact":
         obs, per_env = "u8 (%d,%d,%d) compact (un-expanded layers; reference image = x%d replication)" % (C, G, G, E), C * G * G
     else:
         obs, per_env = "f32 (%d,%d,%d) full render" % (C, G * E, G * E), C * G * E * G * E * 4
@@ -290,7 +292,7 @@ def run_ours(args):
     W = args.window if 0 < args.window < N else N
     hier = args.variant == "v5"
     if hier:
-        env = lmz.LmazeHierCuda(N, "v5", device=dev, seed=2026, env_id0=rank * N, autoreset=True)
+        env = lmz.LmazeHierCuda(N, "v5", device=dev, seed=2026, env_id0=rank * N, autoreset=True, obs_mode=args.obs_mode)
     else:
         env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, env_id0=rank * N, autoreset=True,
                                render_mode=args.render_mode, obs_mode=args.obs_mode, obs_window=W)
@@ -367,7 +369,8 @@ def run_ours(args):
         # step launch: foveal + local obs, visit layer read (+ written back where localDone), 3 state words r/w,
         # 2 rewards, 4 flag bytes, action; planner launch: 3 state words read, and for the waiting envs goal +
         # state write + local obs
-        step_bytes = int(34300 + 19600 + 1296 * (1 + ld) + 24 + 8 + 4 + 1 + 12 + pf * (19600 + 12 + 1 + 2))
+        fov_b, loc_b = (34300, 19600) if args.obs_mode == "full" else (700, 400)
+        step_bytes = int(fov_b + loc_b + 1296 * (1 + ld) + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
         hier_note = {"local_done_fraction": ld, "planner_fraction": pf,
                      "bytes": "34,300 foveal + 19,600 local obs + 1,296 visit read (+1,296 x localDone written) + state/"
                               "rewards/flags/action 37 + planner launch: 12 + planner_fraction x (19,600 local obs + 15)"}
@@ -442,7 +445,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.variant, args.render_mode, N)
                      if (args.obs_mode == "full" and W == N) else None, "peak_source": peak_src,
-                     "kernel": "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4", "v5") else
+                     "kernel": "lmz_fov_small_kernel<%s>" % args.variant.upper()
+                     if (args.variant in ("v2", "v4", "v5") and args.obs_mode == "compact") else
+                     "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4", "v5") else
                      "lmz_env_incr_kernel<%s>" % args.variant.upper() if args.render_mode == "incremental" else
                      "lmz_env_%s_kernel<%s>" % ("compact" if args.obs_mode == "compact" else
                                                 "tma" if args.render_mode == "tma" else "st", args.variant.upper()),

@@ -402,6 +402,41 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return fail(LMZ_ERR_INVALID, "foveal kernels are built for tune[0] = 128 (v2 only), 224, 256, 512 or 1024 threads (got %d)", t);
 }
 
+// compact observations / nothing to render (foveal variants): warp-granular kernel, several small CTAs per SM
+template <class W>
+int launch_fov_small(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  constexpr int THREADS = 128;
+  if (W::HAS_LOC && !h->local_bound)
+    return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
+  auto kern = lmz::lmz_fov_small_kernel<W, THREADS>;
+  constexpr int SMEM = (int)(W::BLOB_BYTES - W::ROWBITS_OFF);
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, SMEM));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal compact kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  const int64_t units = p.tile_end - p.tile_begin;
+  int per_sm = h->cfg.tune[2] > 0 ? h->cfg.tune[2] : ctas_per_sm;
+  if (per_sm > ctas_per_sm) per_sm = ctas_per_sm;
+  int64_t grid = (int64_t)h->num_sms * per_sm;
+  const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, THREADS, SMEM, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+template <class W>
+int launch_fov_any(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  const bool nothing_to_render = p.obs == nullptr && (!W::HAS_LOC || p.obs2 == nullptr);
+  if (h->cfg.obs_mode == LMZ_OBS_COMPACT || nothing_to_render) return launch_fov_small<W>(h, p, s);
+  return launch_fov<W>(h, p, s);
+}
+
 // plannerStep (lmaze-v5/v6): warp-granular kernel, several small CTAs per SM
 int launch_planner(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   using W = lmz::V5;
@@ -428,10 +463,11 @@ int launch_planner(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 }
 
 int launch_env(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (h->cfg.variant == LMZ_V5 && p.mode == lmz::MODE_PLANNER) return launch_planner(h, p, s);
-  if (h->cfg.variant == LMZ_V5) return launch_fov<lmz::V5>(h, p, s);
-  if (h->cfg.variant == LMZ_V2) return launch_fov<lmz::V2>(h, p, s);
-  if (h->cfg.variant == LMZ_V4) return launch_fov<lmz::V4>(h, p, s);
+  if (h->cfg.variant == LMZ_V5 && p.mode == lmz::MODE_PLANNER && h->cfg.obs_mode == LMZ_OBS_FULL && p.obs2 != nullptr)
+    return launch_planner(h, p, s);
+  if (h->cfg.variant == LMZ_V5) return launch_fov_any<lmz::V5>(h, p, s);
+  if (h->cfg.variant == LMZ_V2) return launch_fov_any<lmz::V2>(h, p, s);
+  if (h->cfg.variant == LMZ_V4) return launch_fov_any<lmz::V4>(h, p, s);
   if (h->cfg.variant == LMZ_V0) return launch_env_v<lmz::V0>(h, p, s);
   return launch_env_v<lmz::V3>(h, p, s);
 }
@@ -586,8 +622,9 @@ int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *e
   if (!shape) return fail(LMZ_ERR_INVALID, "shape is NULL");
   if (int rc = lmz_obs_shape(variant, shape)) return rc;
   if (obs_mode == LMZ_OBS_COMPACT) {
-    shape[1] = shape[2] = lmz_grid_size(variant);
-    if (elem_bytes) *elem_bytes = 1;
+    const bool fov = variant == LMZ_V2 || variant == LMZ_V4 || variant == LMZ_V5;
+    shape[1] = shape[2] = fov ? 5 : lmz_grid_size(variant);        // foveal variants: the 5x5 crops, as float32
+    if (elem_bytes) *elem_bytes = fov ? 4 : 1;
   } else if (obs_mode == LMZ_OBS_FULL) {
     if (elem_bytes) *elem_bytes = 4;
   } else {
@@ -625,8 +662,6 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
                 "5 = lmaze-v5/v6)", cfg->variant);
   const bool hier = cfg->variant == LMZ_V5;
   const bool foveal = cfg->variant == LMZ_V2 || cfg->variant == LMZ_V4;
-  if ((foveal || hier) && cfg->obs_mode != LMZ_OBS_FULL)
-    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v2/v4/v5 have no compact observation mode yet");
   if (cfg->num_envs < 1) return fail(LMZ_ERR_INVALID, "num_envs must be >= 1 (got %lld)", (long long)cfg->num_envs);
   if (cfg->env_id0 < 0) return fail(LMZ_ERR_INVALID, "env_id0 must be >= 0");
   if (cfg->render_mode != LMZ_RENDER_TMA && cfg->render_mode != LMZ_RENDER_ST128 &&
@@ -672,17 +707,17 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     build_blob<lmz::V0>(V0_CELLS, blob, h->n_cand, h->s_cell, h->x_cell);
   } else if (cfg->variant == LMZ_V2) {
     h->G = lmz::V2::G; h->C = lmz::V2::C; h->S = lmz::V2::S; h->obs_bytes_per_env = lmz::V2::OBS_BYTES;
-    h->compact_bytes_per_env = 0;
+    h->compact_bytes_per_env = lmz::V2::C * 25 * 4;
     build_blob_fov<lmz::V2>(blob);
     h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
   } else if (cfg->variant == LMZ_V4) {
     h->G = lmz::V4::G; h->C = lmz::V4::C; h->S = lmz::V4::S; h->obs_bytes_per_env = lmz::V4::OBS_BYTES;
-    h->compact_bytes_per_env = 0;
+    h->compact_bytes_per_env = lmz::V4::C * 25 * 4;
     build_blob_fov<lmz::V4>(blob);
     h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
   } else if (cfg->variant == LMZ_V5) {
     h->G = lmz::V5::G; h->C = lmz::V5::C; h->S = lmz::V5::S; h->obs_bytes_per_env = lmz::V5::OBS_BYTES;
-    h->compact_bytes_per_env = 0;
+    h->compact_bytes_per_env = lmz::V5::C * 25 * 4;
     build_blob_v5(blob);
     h->s_cell = 4 * 18 + 4; h->x_cell = 8 * 18 + 8;
   } else {
@@ -778,6 +813,10 @@ int lmz_bind(lmz_env *h, void *obs, float *reward, uint8_t *done) {
 
 static int check_obs_dl(lmz_env *h, DLManagedTensor *obs, int64_t rows, void **po) {
   if (h->cfg.obs_mode == LMZ_OBS_COMPACT) {
+    if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4 || h->cfg.variant == LMZ_V5) {
+      Want w{"obs", kDLFloat, 32, 4, {rows, h->C, 5, 5}, false, 16};
+      return check_dl(h, obs, w, po, nullptr);
+    }
     Want w{"obs", kDLUInt, 8, 4, {rows, h->C, h->G, h->G}, false, 16};
     return check_dl(h, obs, w, po, nullptr);
   }
@@ -1031,7 +1070,8 @@ int lmz_bind_local_dl(lmz_env *h, DLManagedTensor *loc_obs, DLManagedTensor *loc
   const int64_t n = h->cfg.num_envs;
   void *po = nullptr, *pr = nullptr, *pd = nullptr, *pe = nullptr, *pg = nullptr;
   if (loc_obs) {
-    Want w{"loc_obs", kDLFloat, 32, 4, {n, lmz::V5::CL, lmz::V5::S, lmz::V5::S}, false, 16};
+    const int64_t side = h->cfg.obs_mode == LMZ_OBS_COMPACT ? 5 : lmz::V5::S;
+    Want w{"loc_obs", kDLFloat, 32, 4, {n, lmz::V5::CL, side, side}, false, 16};
     if (int rc = check_dl(h, loc_obs, w, &po, nullptr)) return rc;
   }
   Want wr{"local_reward", kDLFloat, 32, 1, {n, 0, 0, 0}, false, 4};

@@ -32,6 +32,16 @@
 
 namespace lmz {
 
+// state[2] = (state[2] + visitMap) / 2, which the reference evaluates in float64 and stores as float32
+// (lmaze_env_v4.py:116-119,211-214; lmaze_env_v5.py:308-312).  For 0 <= v <= 1 the float32 expression below is
+// bit-identical to float32((float64(v) + m) * 0.5): v/2 is a single correctly rounded operation either way, and
+// v + 1 is either exact in float64 (v >= 2^-29) -- then both paths round the same exact value at the same bit --
+// or so close to 1 that both give exactly 1.0 before the halving.  (Checked bit for bit by the v4 / v5 parity
+// tests over the whole layer.)  It keeps FP64 and the f32<->f64 conversions off the producers' path.
+__device__ __forceinline__ float visit_average(float v, bool in_window) {
+  return in_window ? __fmul_rn(__fadd_rn(v, 1.0f), 0.5f) : __fmul_rn(v, 0.5f);
+}
+
 template <int ID, int C>
 __device__ __forceinline__ FovLane<5> fov_lane(const Fov<ID, C> *, const KParams &p, int64_t e,
                                                const FovTables<Fov<ID, C>> &t, const unsigned char *, const FovPre &pre) {
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
       const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
       const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
       float v = vb[idx];
-      if (op == 1) v = (float)(((double)v + (in_cur ? 1.0 : 0.0)) * 0.5);
+      if (op == 1) v = visit_average(v, in_cur);
       else if (op == 2) v = W::visit_reset(in_cur);
       if (op) __stcs(vis + idx, v);
       if (in_cur) tv[env * W::VALS + W::VIS_SLOT0 * 25 + dx * 5 + dy] = v;
@@ -230,6 +240,135 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
     if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
   }
+}
+
+// ---- compact observations / transition-only launches of the foveal variants -----------------------------------
+// obs_mode = LMZ_OBS_COMPACT: the observation is written as f32 [C][5][5] -- the reference's `retState` BEFORE its
+// x7 upsample (lmaze_env_v2.py:185-203, lmaze_env_v4.py:236-247, lmaze_env_v5.py:333-343,372-378) -- 500 / 700 /
+// 700 + 400 bytes per env instead of 24,500 / 34,300 / 53,900; the reference image is exactly
+// repeat_interleave(compact, 7) on both axes.  The same kernel serves launches with no observation bound.  The work
+// per tile is small, so the organisation is warp-granular like lmz_env_compact_kernel: every warp grabs its own
+// tiles (the next tile's index and state words requested one tile ahead), runs the 32 transitions, makes the
+// coalesced pass over the tile's visit layers itself (v4 / v5) and stores the tile's planes as one flat run of
+// coalesced 32-bit words.
+template <class W, int THREADS>
+__global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int WARPS = THREADS / 32;
+  constexpr uint32_t STAGE_OFF = W::ROWBITS_OFF;                 // the render tables are not needed here
+  __shared__ uint32_t s_mask[WARPS][32 * W::NSLOT];          // 25-bit planes indexed by value-plane slot
+  __shared__ uint32_t s_info[WARPS][32];
+  __shared__ float s_crop[W::NVIS > 0 ? WARPS : 1][W::NVIS > 0 ? 32 * 50 : 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, W::BLOB_BYTES - STAGE_OFF);
+    bulk_g2s(smem, p.blob + STAGE_OFF, W::BLOB_BYTES - STAGE_OFF, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const unsigned char *sb = smem - STAGE_OFF;                    // sb + X_OFF addresses staged table X
+  const FovTables<W> t(sb);
+  const int64_t tiles = p.tile_end;
+  const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
+  uint32_t *mk = s_mask[warp];
+  WarpStats ws;
+  auto grab = [&]() {
+    int64_t tl = 0;
+    if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
+    return __shfl_sync(0xffffffffu, tl, 0);
+  };
+  auto preload = [&](int64_t tl, FovPre &q) {
+    const int64_t e = tl * 32 + lane;
+    q.w0 = q.w1 = q.w2 = 0u; q.act = 0;
+    if (tl < tiles && e < p.n) q = fov_preload<W>(p, e);
+  };
+  int64_t tile = grab(), ntile = grab();
+  FovPre pre;
+  preload(tile, pre);
+  while (tile < tiles) {
+    const int64_t nntile = grab();                               // needed two tiles from now
+    const int64_t e = tile * 32 + lane;
+    const bool valid = e < p.n;
+    FovLane<W::NBIT> v;
+    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
+    v.rfov = false; v.rloc = false;
+#pragma unroll
+    for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
+    if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre);
+    if (p.mode == MODE_STEP) ws.add(valid, v.o);
+    preload(ntile, pre);                                         // next tile's words fly while this tile is written
+    const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
+    const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < W::NBIT; ++b) mk[lane * W::NSLOT + W::bit_slot(b)] = v.mask[b];
+    s_info[warp][lane] = valid ? v.info : 0u;
+    __syncwarp();
+    if (W::NVIS > 0 && need_visit) {
+      // the tile's 32 visit layers: coalesced read-modify-write by the warp, crops captured on the way
+      const int64_t e0 = tile * 32;
+      const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
+      float *vis = p.visit + e0 * (W::G * W::G);
+      float *cr = s_crop[W::NVIS > 0 ? warp : 0];
+      constexpr uint32_t UN = 12;                                // 324 = 27 x 12 loads per lane, 12 in flight
+      for (uint32_t k0 = 0; k0 < (uint32_t)(W::G * W::G); k0 += UN) {
+        float vv[UN];
+#pragma unroll
+        for (uint32_t j = 0; j < UN; ++j) {
+          const uint32_t idx = (k0 + j) * 32 + lane;
+          vv[j] = (idx < cells && ((s_info[warp][idx / (W::G * W::G)] >> 20) & 3u) != 2u) ? __ldcs(vis + idx) : 0.0f;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < UN; ++j) {
+          const uint32_t idx = (k0 + j) * 32 + lane;
+          if (idx >= cells) continue;
+          const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
+          const int x = cell / W::G, y = cell - x * W::G;
+          const uint32_t info = s_info[warp][env];
+          const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+          const uint32_t op = (info >> 20) & 3u;
+          const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
+          const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
+          float val = vv[j];
+          if (op == 1) val = visit_average(val, in_cur);
+          else if (op == 2) val = W::visit_reset(in_cur);
+          if (op) __stcs(vis + idx, val);
+          if (in_cur) cr[env * 50 + dx * 5 + dy] = val;
+          if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) cr[env * 50 + 25 + qx * 5 + qy] = val;
+        }
+      }
+      __syncwarp();
+    }
+    // value of plane `slot`, cell `cell` of env `env` of this tile
+    auto value = [&](uint32_t env, uint32_t slot, uint32_t cell) -> float {
+      if (W::NVIS > 0 && (slot == (uint32_t)W::VIS_SLOT0 || slot == (uint32_t)W::VIS_SLOT1))
+        return s_crop[W::NVIS > 0 ? warp : 0][env * 50 + (slot == (uint32_t)W::VIS_SLOT1 ? 25 : 0) + cell];
+      return ((mk[env * W::NSLOT + slot] >> cell) & 1u) ? 1.0f : 0.0f;
+    };
+    if (ff) {
+      constexpr uint32_t PER = W::C * 25;                        // floats per env: the obs channels are slots 0..C-1
+      float *dst = reinterpret_cast<float *>(p.obs) + (tile * 32 - p.win_lo) * (int64_t)PER;
+      for (uint32_t idx = lane; idx < 32 * PER; idx += 32) {
+        const uint32_t env = idx / PER, r = idx - env * PER;
+        if ((ff >> env) & 1u) __stcs(dst + idx, value(env, r / 25, r % 25));
+      }
+    }
+    if (W::HAS_LOC && fl) {
+      constexpr uint32_t PER = 4 * 25;                           // local obs planes: slots 0, 7, 8, 3 (lmaze_env_v5.py:360-368)
+      float *dst = reinterpret_cast<float *>(p.obs2) + (tile * 32 - p.win_lo) * (int64_t)PER;
+      for (uint32_t idx = lane; idx < 32 * PER; idx += 32) {
+        const uint32_t env = idx / PER, r = idx - env * PER, c = r / 25;
+        const uint32_t slot = c == 0 ? 0u : c == 1 ? 7u : c == 2 ? 8u : 3u;
+        const bool err = (s_info[warp][env] >> 22) & 1u;         // IndexError in the reference: the row is all zero
+        if ((fl >> env) & 1u) __stcs(dst + idx, err ? 0.0f : value(env, slot, r % 25));
+      }
+    }
+    tile = ntile; ntile = nntile;
+  }
+  if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
+  if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
 }
 
 }  // namespace lmz

@@ -21,15 +21,17 @@ from .lmaze_vec_cuda import LmazeVecCuda
 
 class LmazeHierCuda(LmazeVecCuda):
     def __init__(self, num_envs=1, variant="v5", device=None, seed=0, autoreset=True, env_id0=0, random_ball=True,
-                 random_goal=True, tune=None):
+                 random_goal=True, tune=None, obs_mode="full"):
         if variant not in ("v5", "v6", 5, 6, "lmaze-v5", "lmaze-v6"):
             raise ValueError("LmazeHierCuda is the planner/actor env: variant must be 'v5' or 'v6'")
         self.variant_name = "v6" if variant in ("v6", 6, "lmaze-v6") else "v5"
         super().__init__(num_envs, "v5", device=device, seed=seed, autoreset=autoreset, env_id0=env_id0,
-                         random_ball=random_ball, random_goal=random_goal, tune=tune)
+                         random_ball=random_ball, random_goal=random_goal, tune=tune, obs_mode=obs_mode)
         shape = (ctypes.c_int64 * 3)()
         _abi.check(self._lib.lmz_local_obs_shape(self.variant, ctypes.byref(shape)))
-        self.local_obs_shape = tuple(shape)
+        self.full_local_obs_shape = tuple(shape)
+        # obs_mode="compact": both observations are the 5x5 crops before the x7 upsample (f32 [N,7,5,5] / [N,4,5,5])
+        self.local_obs_shape = tuple(shape) if obs_mode == "full" else (shape[0], 5, 5)
         n, dev = self.num_envs, self.device
         self.loc_obs = torch.zeros((n,) + self.local_obs_shape, dtype=torch.float32, device=dev)
         self.local_reward = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -64,6 +66,13 @@ class LmazeHierCuda(LmazeVecCuda):
         return self.loc_obs
 
     planner_step = plannerStep
+
+    def expand_local(self, loc=None):
+        """Compact local obs f32 [n,4,5,5] -> the reference's [n,4,35,35] image (exact x7 replication)."""
+        loc = self.loc_obs if loc is None else loc
+        if loc.shape[-1] == self.full_local_obs_shape[-1]:
+            return loc
+        return loc.repeat_interleave(7, dim=2).repeat_interleave(7, dim=3)
 
     def goal_plane(self):
         """fovealGoal as the reference returns it: f32 [N, 1, 5, 5] one-hot (lmaze_env_v5.py:165-168)."""

@@ -79,9 +79,11 @@ class LmazeVecCuda(object):
         self.obs_mode = obs_mode
         _abi.check(self._lib.lmz_obs_desc(self.variant, _OBS_MODE[obs_mode], ctypes.byref(shape), None))
         self.obs_shape = tuple(shape)                    # shape of one row of `self.obs` in this obs_mode
-        self.obs_dtype = torch.float32 if obs_mode == "full" else torch.uint8
+        foveal = self.variant in (_abi.LMZ_V2, _abi.LMZ_V4, _abi.LMZ_V5)
+        # compact observations: u8 [C,G,G] layers for the full-view variants, f32 [C,5,5] crops for the foveal ones
+        self.obs_dtype = torch.float32 if (obs_mode == "full" or foveal) else torch.uint8
         self.grid_size = self._lib.lmz_grid_size(self.variant)
-        self.expansion = self.full_obs_shape[1] // self.grid_size
+        self.expansion = self.full_obs_shape[1] // (5 if foveal else self.grid_size)      # the reference's expansionRatio
         self.num_actions = self._lib.lmz_num_actions(self.variant)      # Discrete(4) / Discrete(25)
         self.num_layouts = self._lib.lmz_num_layouts(self.variant)
         self.single_action_space, self.single_observation_space = make_spaces(self.num_actions, self.full_obs_shape)
@@ -144,10 +146,10 @@ class LmazeVecCuda(object):
         return self.render_obs()
 
     def expand(self, obs=None):
-        """Compact u8 [n,C,G,G] -> the reference's f32 [n,C,G*E,G*E] image (torch plumbing;
+        """Compact u8 [n,C,G,G] (foveal variants: f32 [n,C,5,5]) -> the reference's f32 [n,C,G*E,G*E] image (torch plumbing;
         exact, because the reference upsample is a pure xE replication, lmaze_env.py:219-234)."""
         obs = self.obs if obs is None else obs
-        if obs.dtype != torch.uint8:
+        if obs.shape[-1] == self.full_obs_shape[-1]:
             return obs
         e = self.expansion
         return obs.to(torch.float32).repeat_interleave(e, dim=2).repeat_interleave(e, dim=3)

@@ -70,7 +70,9 @@ typedef enum {
 typedef enum {
   LMZ_OBS_FULL = 0,       /* f32 [N,C,G*E,G*E]: the reference's upsampled image (lmaze_env.py:217-234), bit-exact */
   LMZ_OBS_COMPACT = 1     /* u8  [N,C,G,G]: the same layers BEFORE the xE upsample (lmaze_env.py:208-215);
-                             the reference image is exactly repeat_interleave(compact, E) on both axes */
+                             the reference image is exactly repeat_interleave(compact, E) on both axes.
+                             Foveal variants (v2, v4, v5): f32 [N,C,5,5] -- the 5x5 crops before the x7 upsample
+                             (lmaze_env_v2.py:185-203); v5's local obs is then f32 [N,4,5,5] */
 } lmz_obs_mode;
 
 /* Element type of an action buffer. */

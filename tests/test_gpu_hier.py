@@ -404,3 +404,56 @@ def test_hier_shard_invariance_and_graph_replay(lmz):
     st_w, st_p = whole.get_state()[lo:hi], part.get_state()
     assert torch.equal(st_w, st_p) and torch.equal(whole.get_visit()[lo:hi], part.get_visit())
     whole.close(); part.close()
+
+
+def test_foveal_compact_and_transition_only(lmz, oracle_mod):
+    """obs_mode='compact' on the foveal variants: the f32 5x5 crops, whose x7 replication is exactly the reference
+    image (every step, incl. v4's float visit planes and v5's two tensors); and the launch with no observation
+    bound keeps the same trajectories."""
+    n = 2500
+    for variant, ov in (("v2", oracle_mod.V2), ("v4", oracle_mod.V4)):
+        env = lmz.LmazeVecCuda(n, variant, seed=6, obs_mode="compact")
+        bare = lmz.LmazeVecCuda(n, variant, seed=6, with_obs=False)
+        ora = oracle_mod.OracleVec(ov, n, seed=6, autoreset=True)
+        assert env.obs.shape == (n, env.full_obs_shape[0], 5, 5) and env.obs.dtype == torch.float32
+        assert np.array_equal(u32(env.expand(env.reset())), u32(ora.reset()))
+        bare.reset()
+        gen = torch.Generator().manual_seed(4)
+        for t in range(70):
+            a = torch.randint(0, 25, (n,), generator=gen)
+            obs, rew, done, _ = env.step(a)
+            _, rew_b, done_b, _ = bare.step(a)
+            o_ref, r_ref, d_ref = ora.step(a.numpy())
+            assert np.array_equal(u32(rew), u32(r_ref)) and np.array_equal(done.cpu().numpy(), d_ref.astype(bool)), (variant, t)
+            assert np.array_equal(u32(env.expand(obs)), u32(o_ref)), (variant, t)
+            assert torch.equal(rew_b.view(torch.int32), rew.view(torch.int32)) and torch.equal(done_b, done), (variant, t)
+        assert torch.equal(env.get_state(), bare.get_state())
+        if variant == "v4":
+            assert torch.equal(env.get_visit(), bare.get_visit())
+            assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit()))
+        assert [env.stats()[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist()
+        env.close(); bare.close()
+    env = lmz.LmazeHierCuda(n, "v5", seed=6, obs_mode="compact")
+    ora = oracle_mod.OracleHier(n, seed=6)
+    assert env.obs.shape == (n, 7, 5, 5) and env.loc_obs.shape == (n, 4, 5, 5)
+    assert np.array_equal(u32(env.expand(env.reset())), u32(ora.reset()))
+    rng = np.random.RandomState(7)
+    mask = np.ones(n, np.uint8)
+    for t in range(70):
+        g = rng.randint(0, 25, size=n); a = rng.randint(0, 4, size=n)
+        loc = env.plannerStep(g, mask="auto" if t % 2 else mask)
+        loc_ref, _ = ora.planner_step(g, mask=mask)
+        m = mask.astype(bool)
+        assert np.array_equal(u32(env.expand_local(loc))[m], u32(loc_ref)[m]), t
+        fov, loc, gr, lr, gd, ld, _, _ = env.step(a, goal_plane=False)
+        fov_ref, loc_ref, gr_ref, lr_ref, gd_ref, ld_ref, err_ref = ora.step(a)
+        gdm = gd_ref.astype(bool)
+        if gdm.any():
+            ora.reset(mask=gdm.astype(np.uint8), want_obs=False)
+            ora.render(mask=gdm.astype(np.uint8), fov=fov_ref, loc=loc_ref)
+        assert np.array_equal(u32(gr), u32(gr_ref)) and np.array_equal(u32(lr), u32(lr_ref)), t
+        assert np.array_equal(u32(env.expand(fov)), u32(fov_ref)), t
+        assert np.array_equal(u32(env.expand_local(loc)), u32(loc_ref)), t
+        mask = (gd_ref | ld_ref).astype(np.uint8)
+    assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit()))
+    env.close()
