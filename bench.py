@@ -554,6 +554,38 @@ def side_measurements(env, args, torch, dev):
                                   "[T,N] written", "bytes_per_env_step": 5.25,
                           "achieved_gbs": N * T * 5.25 / (ms * 1e-3) / 1e9}
     del rew, don
+    # (1b) BASELINE configs[1]-size batch (4,096 envs): the step is launch-bound (~65 us of GPU work), so what the host
+    # side costs per call matters -- plain Python step() vs a CUDA-graph replay of the same fused launch
+    try:
+        import gym_lmaze_b200 as lmz
+        n1 = 4096
+        env1 = lmz.LmazeVecCuda(n1, args.variant, device=dev, seed=1, render_mode=args.render_mode)
+        env1.reset()
+        a1 = torch.randint(0, 4, (n1,), device=dev, dtype=torch.uint8)
+        for _ in range(20):
+            env1.step(a1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            env1.step(a1)
+        torch.cuda.synchronize(dev)
+        dt_py = (time.perf_counter() - t0) / 2000
+        replay = env1.capture_step(a1)
+        for _ in range(20):
+            replay()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            replay()
+        torch.cuda.synchronize(dev)
+        dt_g = (time.perf_counter() - t0) / 2000
+        out["small_batch_4096"] = {"envs": n1, "python_step_us": dt_py * 1e6, "python_step_env_steps_per_s": n1 / dt_py,
+                                   "graph_replay_us": dt_g * 1e6, "graph_replay_env_steps_per_s": n1 / dt_g,
+                                   "mode": "BASELINE configs[1] batch size, full f32 render; wall clock over 2000 back-to-back "
+                                           "calls (LmazeVecCuda.step through ctypes + DLPack vs capture_step graph replay)"}
+        env1.close()
+    except Exception as exc:  # pragma: no cover
+        out["small_batch_4096"] = {"error": repr(exc)}
     # (2) e2e including the full observation D2H, on a bounded slice (PCIe-bound by construction)
     try:
         import gym_lmaze_b200 as lmz
