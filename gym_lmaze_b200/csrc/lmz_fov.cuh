@@ -347,22 +347,34 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
         return s_crop[W::NVIS > 0 ? warp : 0][env * 50 + (slot == (uint32_t)W::VIS_SLOT1 ? 25 : 0) + cell];
       return ((mk[env * W::NSLOT + slot] >> cell) & 1u) ? 1.0f : 0.0f;
     };
+    // Lane l owns floats l, l+32, l+64, ... of EVERY env row, so which plane / cell a lane reads is fixed for the
+    // whole kernel (no per-float index arithmetic) and a warp store covers 32 consecutive floats of one env.
     if (ff) {
       constexpr uint32_t PER = W::C * 25;                        // floats per env: the obs channels are slots 0..C-1
+      constexpr int KK = (PER + 31) / 32;
       float *dst = reinterpret_cast<float *>(p.obs) + (tile * 32 - p.win_lo) * (int64_t)PER;
-      for (uint32_t idx = lane; idx < 32 * PER; idx += 32) {
-        const uint32_t env = idx / PER, r = idx - env * PER;
-        if ((ff >> env) & 1u) __stcs(dst + idx, value(env, r / 25, r % 25));
+      for (unsigned m = ff; m; m &= m - 1) {
+        const uint32_t env = __ffs(m) - 1;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+          const uint32_t pos = lane + 32 * k;
+          if (pos < PER) __stcs(dst + env * PER + pos, value(env, pos / 25, pos % 25));
+        }
       }
     }
     if (W::HAS_LOC && fl) {
       constexpr uint32_t PER = 4 * 25;                           // local obs planes: slots 0, 7, 8, 3 (lmaze_env_v5.py:360-368)
+      constexpr int KK = (PER + 31) / 32;
       float *dst = reinterpret_cast<float *>(p.obs2) + (tile * 32 - p.win_lo) * (int64_t)PER;
-      for (uint32_t idx = lane; idx < 32 * PER; idx += 32) {
-        const uint32_t env = idx / PER, r = idx - env * PER, c = r / 25;
-        const uint32_t slot = c == 0 ? 0u : c == 1 ? 7u : c == 2 ? 8u : 3u;
+      for (unsigned m = fl; m; m &= m - 1) {
+        const uint32_t env = __ffs(m) - 1;
         const bool err = (s_info[warp][env] >> 22) & 1u;         // IndexError in the reference: the row is all zero
-        if ((fl >> env) & 1u) __stcs(dst + idx, err ? 0.0f : value(env, slot, r % 25));
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+          const uint32_t pos = lane + 32 * k, c = pos / 25;
+          const uint32_t slot = c == 0 ? 0u : c == 1 ? 7u : c == 2 ? 8u : 3u;
+          if (pos < PER) __stcs(dst + env * PER + pos, err ? 0.0f : value(env, slot, pos % 25));
+        }
       }
     }
     tile = ntile; ntile = nntile;
