@@ -12,13 +12,15 @@
 // render into: 1 table load, 2 value loads, 3 selects, 1 streaming 128-bit store.  (The first version looked
 // every FLOAT up through a byte table and was issue-bound at 91 % issue-slot utilisation, 5.8 TB/s on v4.)
 //
-// CTA organisation: tiles of 32 envs are handed out by the global work counter.  Warp 0 runs the tile's 32
-// transitions (one env per lane, state in registers) and expands each env's 25-bit planes into float planes
-// in shared memory; for the variants with a float visit layer (v4, v5) warps 0-3 are dedicated PRODUCERS:
-// the tile's 32 x 324 visit floats arrive by ONE bulk async (TMA) load issued the moment the tile is grabbed,
-// the producers update them out of shared memory (coalesced write-back) and drop the two 5x5 visit crops into
-// the same planes -- one tile ahead of the other warps, which stream the previous tile's rows out.
-// Everything is double buffered; one __syncthreads per tile.
+// CTA organisation: ONE small persistent CTA per SM; tiles of 32 envs are handed out by the global work counter.
+// Warp 0 is a dedicated producer: it runs the tile's 32 transitions (one env per lane, state in registers) and
+// expands each env's 25-bit planes into float planes in shared memory, one tile ahead of the rendering warps and
+// one tile ahead of its OWN loads (next tile's index, state words, actions).  For the variants with a float visit
+// layer (v4, v5) warps 0-3 are producers: the tile's 32 x 324 visit floats arrive by ONE bulk async (TMA) load,
+// the producers update them out of shared memory (coalesced write-back) and drop the two 5x5 visit crops into the
+// same planes.  Everything is double buffered; one __syncthreads per tile.  FEWER rendering warps reach a HIGHER
+// write bandwidth (tools/fov_sweep2.py): v2 runs 1 + 3 warps per SM (7.47 TB/s, the pure-write ceiling; 7.0 TB/s
+// with 32 warps), v4 4 + 3, v5 4 + 12.
 #pragma once
 #include "lmz_v2.cuh"
 #include "lmz_v5.cuh"
