@@ -96,7 +96,7 @@ typedef struct lmz_config {
                              [0] threads per CTA (TMA path: 32/64/128/256 issuing warps x32; ST128 path: 256/512/1024;
                                  foveal kernels: 128 (v2), 224, 256, 512, 1024)
                              [1] L2 policy of the obs stores: 1 evict_first, 2 evict_normal, 3 evict_last, 4 none
-                             [2] foveal / compact / incremental kernels: resident CTAs per SM (0 = library default)
+                             [2] resident CTAs per SM (0 = library default)
                              [3] split bulk copies into pieces of at most this many bytes (multiple of 16) */
   int32_t  obs_mode;      /* lmz_obs_mode */
   int32_t  reserved[2];   /* must be zero */
