@@ -127,8 +127,8 @@ void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand
 }
 
 // One table entry per float4 of a run of x7-upsampled 5x5 planes (lmz_fov.cuh): the four floats take at most two
-// different cell values -- the first k from value A, the rest from value B.  entry = A | B << 10 | k << 20, A and B
-// indexing [env in group][slot][cell] value planes.  `slot_of(channel)` maps an obs channel to its value plane.
+// different cell values -- the first k from value A, the rest from value B.  entry = A | B << 11 | k << 22, A and B
+// indexing [env in group][slot][cell] value planes (< 2048 entries).  `slot_of(channel)` maps an obs channel to its value plane.
 template <class V, class SlotOf>
 void build_f4_lut(uint32_t *lut, uint32_t floats_per_env, uint32_t n_entries, SlotOf slot_of) {
   auto code = [&](uint32_t g) -> uint32_t {
@@ -143,7 +143,7 @@ void build_f4_lut(uint32_t *lut, uint32_t floats_per_env, uint32_t n_entries, Sl
     const uint32_t b = k < 4 ? c[k] : c[0];
     for (uint32_t j = k; j < 4; ++j)
       if (c[j] != b) { fprintf(stderr, "lmaze_b200: float4 table: more than two values in one float4\n"); abort(); }
-    lut[q] = c[0] | (b << 10) | (k << 20);
+    lut[q] = c[0] | (b << 11) | (k << 22);
   }
 }
 
@@ -184,10 +184,10 @@ void build_blob_fov(std::vector<unsigned char> &blob) {
 void build_blob_v5(std::vector<unsigned char> &blob) {
   using V = lmz::V5;
   build_blob_fov<V>(blob);
-  // local obs channels (lmaze_env_v5.py:360-368): free crop (value plane 0), ball rel. fovea_x1 (7), previous ball (8),
-  // fovealGoal (3); one env row = 1,225 float4s exactly
+  // local obs channels (lmaze_env_v5.py:360-368): free crop (value plane 9), ball rel. fovea_x1 (7), previous ball (8),
+  // fovealGoal (10) -- the local copies are all zero on an IndexError row; one env row = 1,225 float4s exactly
   build_f4_lut<V>(reinterpret_cast<uint32_t *>(blob.data() + V::LOCLUT_OFF), V::LOC_FLOATS, V::LOC_FLOATS / 4,
-                  [](int c) { static const int plane[4] = {0, 7, 8, 3}; return plane[c]; });
+                  [](int c) { static const int plane[4] = {9, 7, 8, 10}; return plane[c]; });
 }
 
 }  // namespace
@@ -391,9 +391,9 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   // CTA size and CTAs per SM (tools/fov_sweep2.py).  FEWER storing warps reach a HIGHER write bandwidth on a B200:
   // v2 with ONE 128-thread CTA per SM (1 producer warp + 3 rendering warps) streams 7.47 TB/s, the pure-write
   // ceiling, against 7.0 TB/s with 1024 threads and 6.3 TB/s with two 128-thread CTAs per SM; v4 is best with 224
-  // threads (4 producer warps for the visit layers + 3 rendering warps, 6.5 TB/s); v5, which writes two tensors
-  // per env and needs more instructions per byte, needs 320 threads or more and is flat from there (6.3 TB/s).
-  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 2 ? 128 : W::ID == 4 ? 224 : 512);
+  // threads (4 producer warps for the visit layers + 3 rendering warps, 6.5 TB/s), v5 (two tensors per env) with
+  // 256 (4 + 4 warps, 6.4 TB/s; 6.0 TB/s with 512 threads).
+  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 2 ? 128 : W::ID == 4 ? 224 : 256);
   switch (t) {
     case 128: if (W::NVIS == 0) return launch_fov_t<W, (W::NVIS == 0 ? 128 : 512)>(h, p, s); break;   // v2 only: the visit
     case 224: return launch_fov_t<W, 224>(h, p, s);                                  // variants keep 128 producer threads

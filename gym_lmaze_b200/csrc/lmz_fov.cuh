@@ -8,7 +8,7 @@
 // are.  The render therefore works on GROUPS of 4 envs: a group's image is OBS_FLOATS float4s, and because
 // every cell value repeats 7 times along a row, the four floats of one float4 take at most TWO different
 // cell values (a prefix of k floats from cell A, the rest from cell B).  One host-built table entry per
-// float4 -- A:10 | B:10 | k:3, A and B indexing the group's [4][NSLOT][25] value planes -- turns the whole
+// float4 -- A:11 | B:11 | k:3, A and B indexing the group's [4][NSLOT][25] value planes -- turns the whole
 // render into: 1 table load, 2 value loads, 3 selects, 1 streaming 128-bit store.  (The first version looked
 // every FLOAT up through a byte table and was issue-bound at 91 % issue-slot utilisation, 5.8 TB/s on v4.)
 //
@@ -20,7 +20,7 @@
 // the producers update them out of shared memory (coalesced write-back) and drop the two 5x5 visit crops into the
 // same planes.  Everything is double buffered; one __syncthreads per tile.  FEWER rendering warps reach a HIGHER
 // write bandwidth (tools/fov_sweep2.py): v2 runs 1 + 3 warps per SM (7.47 TB/s, the pure-write ceiling; 7.0 TB/s
-// with 32 warps), v4 4 + 3, v5 4 + 12.
+// with 32 warps), v4 4 + 3, v5 4 + 4.
 #pragma once
 #include "lmz_v2.cuh"
 #include "lmz_v5.cuh"
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
       } else {
         // partial tile (batch tail, reset mask, render-window edge): guarded 32-bit stores
         for (uint32_t q = ctid; q < TOTAL; q += CTHREADS) {
-          const uint32_t en = t.lut[ent], a = en & 1023u, b = (en >> 10) & 1023u, k = en >> 20;
+          const uint32_t en = t.lut[ent], a = en & 2047u, b = (en >> 11) & 2047u, k = en >> 22;
           const float *gv = tv + grp * 4 * W::VALS;
 #pragma unroll
           for (uint32_t j = 0; j < 4; ++j) {
@@ -217,9 +217,8 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
           uint32_t ent = ctid % PER, env = ctid / PER;
 #pragma unroll 4
           for (uint32_t q = ctid; q < 32 * PER; q += CTHREADS) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);                  // IndexError in the reference: the row is all zero
-            if (!((s_info[buf][env] >> 22) & 1u)) v = pick(loclut[ent], tv + env * W::VALS);
-            st_stream_v4(dst + ((size_t)q << 4), v);
+            // (an IndexError row is all zero: the producer zeroed the four local planes of that env)
+            st_stream_v4(dst + ((size_t)q << 4), pick(loclut[ent], tv + env * W::VALS));
             ent += CTHREADS;
             while (ent >= PER) { ent -= PER; ++env; }
           }
@@ -227,12 +226,8 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
           while (flags) {                                          // a few envs of the tile (masked plannerStep)
             const uint32_t env = __ffs(flags) - 1;
             flags &= flags - 1;
-            const bool err = (s_info[buf][env] >> 22) & 1u;
-            for (uint32_t q = ctid; q < PER; q += CTHREADS) {
-              uint4 v = make_uint4(0u, 0u, 0u, 0u);
-              if (!err) v = pick(loclut[q], tv + env * W::VALS);
-              st_stream_v4(dst + ((size_t)(env * PER + q) << 4), v);
-            }
+            for (uint32_t q = ctid; q < PER; q += CTHREADS)
+              st_stream_v4(dst + ((size_t)(env * PER + q) << 4), pick(loclut[q], tv + env * W::VALS));
           }
         }
       }
@@ -374,7 +369,7 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
 #pragma unroll
         for (int k = 0; k < KK; ++k) {
           const uint32_t pos = lane + 32 * k, c = pos / 25;
-          const uint32_t slot = c == 0 ? 0u : c == 1 ? 7u : c == 2 ? 8u : 3u;
+          const uint32_t slot = c == 0 ? 9u : c == 1 ? 7u : c == 2 ? 8u : 10u;
           if (pos < PER) __stcs(dst + env * PER + pos, err ? 0.0f : value(env, slot, pos % 25));
         }
       }

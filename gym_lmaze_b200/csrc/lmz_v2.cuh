@@ -92,10 +92,11 @@ struct FovTables {
         xcell(reinterpret_cast<const uint16_t *>(smem + W::XCELL_OFF)) {}
 };
 
-// One float4 of an x7-upsampled image from its table entry (A:10 | B:10 | k:3, built by the host: the first k
-// floats show value plane entry A, the rest entry B) -- see lmz_fov.cuh.
+// One float4 of an x7-upsampled image from its table entry (A:11 | B:11 | k:3, built by the host: the first k
+// floats show value-plane entry A, the rest entry B) -- see lmz_fov.cuh.  (Byte offsets instead of indices were
+// tried and were slower: the casts cost the compiler the shared-memory address space of the loads.)
 __device__ __forceinline__ uint4 f4_pick(uint32_t en, const float *gv) {
-  const uint32_t va = __float_as_uint(gv[en & 1023u]), vb = __float_as_uint(gv[(en >> 10) & 1023u]), k = en >> 20;
+  const uint32_t va = __float_as_uint(gv[en & 2047u]), vb = __float_as_uint(gv[(en >> 11) & 2047u]), k = en >> 22;
   return make_uint4(va, k > 1 ? va : vb, k > 2 ? va : vb, k > 3 ? va : vb);
 }
 

@@ -28,16 +28,17 @@ struct V5 {
   static constexpr int ID = 5;
   static constexpr int G = 18, E = 7, F = 5, C = 7, CL = 4, S = F * E;       // lmaze_env_v5.py:25-37,357-358
   static constexpr int NLAYOUT = 5, MAX_CAND = 80;
-  static constexpr int NBIT = 7;      // bit planes: free, goal, fovealGoal, last free, last goal, ball rel, previous ball rel
+  static constexpr int NBIT = 9;      // bit planes: free, goal, fovealGoal, last free, last goal, ball rel, previous ball rel,
+                                      // + the local obs's own copies of free / fovealGoal (all-zero on an IndexError row)
   static constexpr int NVIS = 2;      // float planes: visit crop at the ball, visit crop at retStatelast's window
   static constexpr bool HAS_LOC = true;
   // 5x5 value planes per env: slots 0-6 are the foveal channels -- crop(free, goal, visit), fovealGoal,
-  // retStatelast(free, goal, visit) (:314-333) -- 7/8 the ball / previous ball relative to the planner-time fovea;
-  // the local obs (:356-380) is slots 0, 7, 8, 3
-  static constexpr int NSLOT = 9;
+  // retStatelast(free, goal, visit) (:314-333) -- 7/8 the ball / previous ball relative to the planner-time fovea,
+  // 9/10 the local obs's free crop / fovealGoal; the local obs (:356-380) is slots 9, 7, 8, 10
+  static constexpr int NSLOT = 11;
   static constexpr int VALS = NSLOT * 25;
   static constexpr int VIS_SLOT0 = 2, VIS_SLOT1 = 6;
-  __host__ __device__ static constexpr int bit_slot(int b) { return b < 2 ? b : (b < 5 ? b + 1 : b + 2); }
+  __host__ __device__ static constexpr int bit_slot(int b) { return b < 2 ? b : (b < 5 ? b + 1 : b + 2); }   // 0 1 3 4 5 7 8 9 10
   __device__ static __forceinline__ float visit_reset(bool) { return 0.0f; }   // self.state = zeros (:134), no averaging
   static constexpr bool MAZE_FIRST = true;                                   // reset(): setGrid() first (:104,115-116)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                          // 8,575 (foveal)
@@ -212,6 +213,8 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
   out.mask[4] = v2_goal_crop(slx, sly, r.gx, r.gy);
   out.mask[5] = loc_ok ? (1u << (i0 * 5 + i1)) : 0u;                                 // :365
   out.mask[6] = loc_ok ? (1u << (j0 * 5 + j1)) : 0u;                                 // :366
+  out.mask[7] = loc_ok ? out.mask[0] : 0u;                                           // :360, local copy
+  out.mask[8] = loc_ok ? out.mask[2] : 0u;                                           // :368, local copy
   return out;
 }
 
@@ -253,10 +256,10 @@ __global__ void __launch_bounds__(THREADS) lmz_planner_kernel(const KParams p) {
       const bool err = (__shfl_sync(0xffffffffu, v.info, src) >> 22) & 1u;
       __syncwarp();
       if (lane < 25) {
-        mv[0 * 25 + lane] = ((m0 >> lane) & 1u) ? 1.0f : 0.0f;
+        mv[9 * 25 + lane] = ((m0 >> lane) & 1u) ? 1.0f : 0.0f;
         mv[7 * 25 + lane] = ((m5 >> lane) & 1u) ? 1.0f : 0.0f;
         mv[8 * 25 + lane] = ((m6 >> lane) & 1u) ? 1.0f : 0.0f;
-        mv[3 * 25 + lane] = ((m2 >> lane) & 1u) ? 1.0f : 0.0f;
+        mv[10 * 25 + lane] = ((m2 >> lane) & 1u) ? 1.0f : 0.0f;
       }
       __syncwarp();
       unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs2) + (tl * 32 + src - p.win_lo) * (int64_t)W::LOC_BYTES;
