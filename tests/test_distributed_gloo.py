@@ -66,3 +66,60 @@ def test_sharded_stats_allreduce_matches_single_process():
     for lo, hi, p in gathered:
         assert p == pos[lo:hi]            # shard-invariant trajectories
     assert tmax == 11.0
+
+
+def _hier_run(n, env_id0, lo_global, total, iters=40):
+    """The planner / actor loop of lmaze-v5 on the CPU oracle for envs [lo_global, lo_global + n) of a batch of
+    `total`: goals / actions are drawn for the WHOLE batch and sliced, spawns come from the global-id keyed RNG."""
+    import numpy as np
+    from oracle import oracle as O
+    o = O.OracleHier(n, seed=5, env_id0=env_id0)
+    o.reset(want_obs=False)
+    rng = np.random.RandomState(9)
+    mask = np.ones(n, np.uint8)
+    n_gd = 0
+    for _ in range(iters):
+        goals = rng.randint(0, 25, size=total)[lo_global:lo_global + n]
+        acts = rng.randint(0, 4, size=total)[lo_global:lo_global + n]
+        o.planner_step(goals, mask=mask)
+        _, _, _, _, gd, ld, _ = o.step(acts)
+        if gd.any():
+            o.reset(mask=gd, want_obs=False)
+        mask = (gd | ld).astype(np.uint8)
+        n_gd += int(gd.sum())
+    return o.export().tolist(), n_gd
+
+
+def _hier_worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gym_lmaze_b200 import shard_range
+    lo, hi = shard_range(total, rank, world)
+    state, n_gd = _hier_run(hi - lo, lo, lo, total)
+    t = torch.tensor([n_gd], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)                  # the only collective: integer statistics
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, state))
+    if rank == 0:
+        q.put((int(t), gathered))
+    dist.destroy_process_group()
+
+
+def test_hier_shards_reproduce_the_single_process_batch():
+    """lmaze-v5: rank r of 2 owns a contiguous global-id range; trajectories (resets included, device-RNG spec keyed
+    by global env id) are identical to the un-sharded batch and the summed episode count matches."""
+    total, world = 131, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hier_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    n_gd, gathered = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    state, n_gd_single = _hier_run(total, 0, 0, total)
+    assert n_gd == n_gd_single and n_gd > 0
+    for lo, hi, s in gathered:
+        assert s == state[lo:hi]
