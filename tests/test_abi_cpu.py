@@ -119,3 +119,22 @@ def test_missing_extension_fails_loudly(abi, monkeypatch):
     monkeypatch.setattr(abi, "LIB_PATH", os.path.join(ROOT, "gym_lmaze_b200", "does_not_exist.so"))
     with pytest.raises(ImportError, match="no CPU fallback"):
         abi.load()
+
+
+def test_shard_range_partitions_the_batch():
+    """Contiguous global-id shards: disjoint, ordered, covering, sizes differ by at most one."""
+    from hypothesis import given, settings, strategies as st
+    from gym_lmaze_b200 import shard_range
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 1 << 40), st.integers(1, 64))
+    def check(total, world):
+        edges = [shard_range(total, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == total
+        for (lo, hi), (lo2, hi2) in zip(edges, edges[1:]):
+            assert lo <= hi == lo2 <= hi2
+        sizes = [hi - lo for lo, hi in edges]
+        assert max(sizes) - min(sizes) <= 1
+    check()
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 3)
