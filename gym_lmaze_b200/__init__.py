@@ -55,21 +55,41 @@ register("lmaze-vec-v3", "v3", num_envs=4096)
 register("lmaze-vec-v4", "v4", num_envs=4096)
 
 
+def gym_entry_point(env_id):
+    """(entry_point, kwargs) registered with gym for `env_id`.  The reference's ids 'lmaze-vK' point at the
+    reference-typed single-maze classes (reference gym_lmaze/__init__.py:3-38: 'gym_lmaze.envs:LmazeEnv', ...),
+    so gym.make('lmaze-v0') and gym_lmaze_b200.make('lmaze-v0') return the same kind of object; only the
+    'lmaze-vec-vK' ids construct the batched classes."""
+    variant, defaults = _REGISTRY[env_id]
+    if "-vec-" in env_id:
+        cls = "LmazeHierCuda" if variant in ("v5", "v6") else "LmazeVecCuda"
+        return "gym_lmaze_b200:" + cls, dict(defaults, variant=variant)
+    return "gym_lmaze_b200:" + _SINGLE[variant].__name__, {}
+
+
+def register_with(register_fn):
+    """Register every built id through `register_fn(id=..., entry_point=..., kwargs=...)` (gym's or gymnasium's
+    `register`).  A failing id (e.g. a clash with an installed reference package) is reported, not hidden."""
+    import warnings
+    done = []
+    for env_id in sorted(_REGISTRY):
+        entry_point, kwargs = gym_entry_point(env_id)
+        try:
+            register_fn(id=env_id, entry_point=entry_point, kwargs=kwargs)
+            done.append(env_id)
+        except Exception as exc:
+            warnings.warn("gym_lmaze_b200: could not register %r with gym: %r" % (env_id, exc), RuntimeWarning)
+    return done
+
+
 def _register_with_gym():
+    import importlib
     for modname in ("gymnasium", "gym"):
         try:
-            mod = __import__(modname + ".envs.registration", fromlist=["register"])
-            if not hasattr(__import__(modname), "__version__"):
-                continue
-            for env_id, (variant, defaults) in _REGISTRY.items():
-                try:
-                    mod.register(id=env_id, entry_point="gym_lmaze_b200:LmazeHierCuda" if variant in ("v5", "v6")
-                                 else "gym_lmaze_b200:LmazeVecCuda",
-                                 kwargs=dict(defaults, variant=variant))
-                except Exception:
-                    pass
-        except Exception:
-            continue
+            mod = importlib.import_module(modname + ".envs.registration")
+        except ImportError:
+            continue                     # that package is not installed: nothing to register with
+        register_with(mod.register)
 
 
 _register_with_gym()

@@ -14,6 +14,7 @@ RENDER_TMA, RENDER_ST128, RENDER_INCREMENTAL = 0, 1, 2
 OBS_FULL, OBS_COMPACT = 0, 1
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 NUM_STATS = 8
+SPAWN_FORCE = 64          # LMZ_SPAWN_FORCE
 ST_COLS = 8
 ST_COLS_HIER = 17
 STAT_NAMES = ("steps", "episodes", "goals", "timeouts", "wall_bumps", "moves", "stale", "eplen_sum")

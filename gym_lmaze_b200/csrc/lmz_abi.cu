@@ -40,8 +40,9 @@ int fail(int code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------ mazes
 // Cell letters as in the reference: W wall, B blank, S start, X goal.
-// v0: lmaze_env.py:37-48.  v3: lmaze_env_v3.py:26-43.  tests/test_layouts.py checks
-// both against the golden extraction from the reference.
+// v0: lmaze_env.py:37-48.  v3: lmaze_env_v3.py:26-43.  tests/test_abi_cpu.py
+// (test_static_queries_and_layouts) checks both against the golden extraction
+// from the reference (tests/golden/layouts.npz).
 const char V0_CELLS[] =
     "WWWWWWWWWWWW" "WSBBBBBBBBBW" "WBWWBWWWWWBW" "WBBBWBBBBBBW" "WBBWBBBWWWBW" "WBWBWXWBBBBW"
     "WBBBWBBWWBBW" "WBWBWBBBBWBW" "WBWBBBWBBBBW" "WBBWWWBBWWBW" "WBBBBBBBBBBW" "WWWWWWWWWWWW";
@@ -970,7 +971,10 @@ int lmz_rollout(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype
   p.reward = rewards; p.done = dones; p.obs = nullptr; p.T = T; p.t0 = h->rollout_t;
   int rc = (h->cfg.variant == LMZ_V0) ? launch_rollout_v<lmz::V0>(h, p, static_cast<cudaStream_t>(stream))
                                       : launch_rollout_v<lmz::V3>(h, p, static_cast<cudaStream_t>(stream));
-  if (rc == LMZ_OK) h->rollout_t += (uint64_t)T;
+  if (rc == LMZ_OK) {
+    h->rollout_t += (uint64_t)T;
+    h->obs_synced = false;               // every ball / goal moved and nothing was rendered (incremental render)
+  }
   return rc;
 }
 
@@ -998,14 +1002,15 @@ static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {
   const int64_t n = h->cfg.num_envs;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned int *errors = reinterpret_cast<unsigned int *>(h->stats + lmz::NUM_STATS);
   if (h->cfg.variant == LMZ_V5)
-    lmz::lmz_state_v5_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->aux2, h->episode, io, set);
+    lmz::lmz_state_v5_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->aux2, h->episode, io, set, errors);
   else if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4)
-    lmz::lmz_state_v2_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
+    lmz::lmz_state_v2_kernel<<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set, errors);
   else if (h->cfg.variant == LMZ_V0)
-    lmz::lmz_state_kernel<lmz::V0><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
+    lmz::lmz_state_kernel<lmz::V0><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set, h->blob, errors);
   else
-    lmz::lmz_state_kernel<lmz::V3><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set);
+    lmz::lmz_state_kernel<lmz::V3><<<blocks, 256, 0, s>>>(n, h->state, h->goal_count, h->episode, io, set, h->blob, errors);
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;

@@ -165,6 +165,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 constexpr uint32_t TAG_SPAWN = 0x53u, TAG_ACTION = 0x41u;
+constexpr int SPAWN_FORCE = 64;      // added to an injected spawn row's goal_x: the row overrides RANDOM_BALL / RANDOM_GOAL (v3 test mode)
 
 struct WordStream {   // words 4a..4a+3 come from Philox block `a` of (seed, env, episode)
   uint32_t c0, c1, c2, k0, k1, attempt, buf[4];
@@ -242,15 +243,20 @@ __device__ __forceinline__ void respawn(EnvRegs &r, const KParams &p, int64_t e,
                                         const uint8_t *cls, const uint16_t *cand) {
   int sx, sy, gx = r.gx, gy = r.gy;
   const int s_x = p.s_cell / V::G, s_y = p.s_cell % V::G;
+  bool forced = false;
   if (p.spawn) {
-    const int4 s = p.spawn[e];
+    int4 s = p.spawn[e];
+    // v3 reset(mode="test") (lmaze_env_v3.py:145-146,154-155): the fixed goal / ball take priority over
+    // RANDOM_GOAL / RANDOM_BALL.  The row says so with SPAWN_FORCE added to its goal_x column.
+    forced = V::ID == 3 && s.z >= SPAWN_FORCE;
+    if (forced) s.z -= SPAWN_FORCE;
     sx = s.x; sy = s.y;
     bool ok = true;
-    if (V::ID == 3 && p.random_goal && s.z >= 0) {
+    if (V::ID == 3 && (p.random_goal || forced) && s.z >= 0) {
       const bool gok = s.z >= 1 && s.z <= V::G - 2 && s.w >= 1 && s.w <= V::G - 2 && cls[s.z * V::G + s.w] != CLS_W;
       if (gok) { gx = s.z; gy = s.w; } else ok = false;
     }
-    if (p.random_ball) {
+    if (p.random_ball || forced) {
       bool bok = sx >= 1 && sx <= V::G - 2 && sy >= 1 && sy <= V::G - 2;
       if (bok) {
         const int c = cls[sx * V::G + sy];
@@ -275,7 +281,7 @@ __device__ __forceinline__ void respawn(EnvRegs &r, const KParams &p, int64_t e,
       if (!p.random_goal && sx == gx && sy == gy) { sx = cand[gi] / V::G; sy = cand[gi] % V::G; }
     }
   }
-  if (!p.random_ball) { sx = s_x; sy = s_y; }                               // lmaze_env.py:82-89
+  if (!p.random_ball && !forced) { sx = s_x; sy = s_y; }                    // lmaze_env.py:82-89
   r.x = sx; r.y = sy; r.gx = gx; r.gy = gy;
   r.step = 0; r.rcode = RC_NEG_ZERO;
   episode += 1;
@@ -919,9 +925,12 @@ __global__ void __launch_bounds__(THREADS, 3) lmz_rollout_kernel(const KParams p
 
 // ------------------------------------------------------------------ state exchange (get/set_state)
 // cols: x, y, goal_x, goal_y, step_count, reward_code, goal_count, episode
+// set: a row the env could never be in -- a coordinate outside the grid interior (it is clamped so that the
+// kernels' +-1 lookups stay inside the table), the ball on a wall, v3's goal on a wall, a reward code
+// outside 0..3 -- is COUNTED in the handle's error counter (lmz_stats errors), never fixed silently.
 template <class V>
 __global__ void lmz_state_kernel(int64_t n, uint32_t *state, uint32_t *goal_count, uint32_t *episode, int32_t *io,
-                                 int set) {
+                                 int set, const uint8_t *blob, unsigned int *errors) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   int32_t *row = io + e * 8;
@@ -931,6 +940,11 @@ __global__ void lmz_state_kernel(int64_t n, uint32_t *state, uint32_t *goal_coun
     r.x = clampi(row[0]); r.y = clampi(row[1]); r.gx = clampi(row[2]); r.gy = clampi(row[3]);
     r.step = (uint32_t)row[4] < V::STEP_SAT ? (uint32_t)row[4] : V::STEP_SAT;
     r.rcode = row[5] & 3;
+    const uint8_t *cls = blob + V::CLS_OFF;
+    bool bad = r.x != row[0] || r.y != row[1] || row[4] < 0 || cls[r.x * V::G + r.y] == CLS_W;
+    if (V::ID == 0) bad = bad || row[5] < 0 || row[5] > 3;                            // v0 has no goal columns (always 5,5)
+    else bad = bad || r.gx != row[2] || r.gy != row[3] || cls[r.gx * V::G + r.gy] == CLS_W;
+    if (bad) atomicAdd(errors, 1u);
     state[e] = V::pack(r);
     goal_count[e] = (uint32_t)row[6];
     episode[e] = (uint32_t)row[7];

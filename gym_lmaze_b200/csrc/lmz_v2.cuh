@@ -256,7 +256,10 @@ __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const Fov
 
 // get/set_state for v2.  cols: x, y, goal_x, goal_y, step_count, layout, aux, episode
 // aux = prev_x | prev_y << 5 | last_action << 10 | action_valid << 15
-__global__ void lmz_state_v2_kernel(int64_t n, uint32_t *state, uint32_t *auxw, uint32_t *episode, int32_t *io, int set) {
+// set: rows the env could never be in (ball / previous ball outside [2, 15], goal outside 0..31, maze outside 1..5,
+// action > 24) are clamped AND counted in the error counter.  (The ball MAY sit on a wall: lmaze_env_v2.py:157-159.)
+__global__ void lmz_state_v2_kernel(int64_t n, uint32_t *state, uint32_t *auxw, uint32_t *episode, int32_t *io, int set,
+                                    unsigned int *errors) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   int32_t *row = io + e * 8;
@@ -268,6 +271,9 @@ __global__ void lmz_state_v2_kernel(int64_t n, uint32_t *state, uint32_t *auxw, 
     r.L = row[5] < 1 ? 1 : (row[5] > 5 ? 5 : row[5]);
     r.px = clampi(row[6] & 31); r.py = clampi((row[6] >> 5) & 31);
     r.a = ((row[6] >> 15) & 1) ? ((row[6] >> 10) & 31) : -1;
+    bool bad = r.x != row[0] || r.y != row[1] || r.gx != row[2] || r.gy != row[3] || row[4] < 0 || r.L != row[5] ||
+               r.px != (row[6] & 31) || r.py != ((row[6] >> 5) & 31) || r.a > 24;
+    if (bad) atomicAdd(errors, 1u);
     if (r.a > 24) r.a = 24;
     uint32_t s, aux;
     v2_pack(r, s, aux);

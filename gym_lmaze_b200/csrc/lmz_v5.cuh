@@ -329,8 +329,10 @@ __global__ void lmz_safe_goal_kernel(int64_t n, const uint32_t *state, const uin
 // get/set_state for v5/v6.  int32 [n][16]: x, y, x1, y1, fx1, fy1, gx, gy, fgx, fgy, last_x, last_y, fgoal_action,
 // step, foveal_step, flags (globalDone | localDone << 1 | layout << 4);
 // the episode counter travels in a 17th column.
+// set: positions outside [2, 15], goals outside 0..31, a foveal-goal cell outside 0..24 or a maze outside 1..5 are
+// clamped AND counted in the error counter.
 __global__ void lmz_state_v5_kernel(int64_t n, uint32_t *state, uint32_t *aux1, uint32_t *aux2, uint32_t *episode,
-                                    int32_t *io, int set) {
+                                    int32_t *io, int set, unsigned int *errors) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   int32_t *row = io + e * 17;
@@ -345,6 +347,10 @@ __global__ void lmz_state_v5_kernel(int64_t n, uint32_t *state, uint32_t *aux1, 
     r.gd = row[15] & 1; r.ld = (row[15] >> 1) & 1;
     const int L = (row[15] >> 4) & 7;
     r.L = L < 1 ? 1 : (L > 5 ? 5 : L);
+    const bool bad = r.x != row[0] || r.y != row[1] || r.x1 != row[2] || r.y1 != row[3] || r.fx1 != row[4] ||
+                     r.fy1 != row[5] || r.gx != row[6] || r.gy != row[7] || r.fgx != row[8] || r.fgy != row[9] ||
+                     r.lx != row[10] || r.ly != row[11] || r.fga != row[12] || row[13] < 0 || row[14] < 0 || r.L != L;
+    if (bad) atomicAdd(errors, 1u);
     uint32_t w0, w1, w2;
     v5_pack(r, w0, w1, w2);
     state[e] = w0; aux1[e] = w1; aux2[e] = w2; episode[e] = (uint32_t)row[16];

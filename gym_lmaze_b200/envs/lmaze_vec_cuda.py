@@ -72,6 +72,10 @@ class LmazeVecCuda(object):
         self.autoreset = bool(autoreset)
         self.env_id0 = int(env_id0)
         self.seed = int(seed)
+        self.render_mode = render_mode
+        # incremental render: True while `obs` may not hold a full render of the current state (mirrors the
+        # handle's own flag); a captured graph of the incremental kernel must not be replayed then
+        self._obs_desync = True
 
         shape = (ctypes.c_int64 * 3)()
         _abi.check(self._lib.lmz_obs_shape(self.variant, ctypes.byref(shape)))
@@ -137,6 +141,7 @@ class LmazeVecCuda(object):
         env_lo = int(env_lo)
         po, ko = _abi.dl(self.obs)
         _abi.check(self._lib.lmz_set_window_dl(self._h, po, env_lo))
+        self._obs_desync = True
         self.window_lo = env_lo
         self._window_keepalive = ko
 
@@ -202,13 +207,16 @@ class LmazeVecCuda(object):
         if mode == "test":
             if self.variant != _abi.LMZ_V3:
                 raise ValueError("reset(mode='test') exists only in lmaze-v3")
-            spawn = torch.tensor([[7, 8, 8, 8]], dtype=torch.int32).expand(self.num_envs, 4)
+            # goal_x carries LMZ_SPAWN_FORCE: test mode beats RANDOM_BALL / RANDOM_GOAL = False (lmaze_env_v3.py:145-155)
+            spawn = torch.tensor([[7, 8, 8 + _abi.SPAWN_FORCE, 8]], dtype=torch.int32).expand(self.num_envs, 4)
         spawn = self._as_spawn(spawn)
         if mask is not None:
             mask = torch.as_tensor(mask).to(device=self.device).to(torch.uint8).contiguous()
         pm, km = _abi.dl(mask)
         ps, ks = _abi.dl(spawn)
         _abi.check(self._lib.lmz_reset_dl(self._h, pm, ps, self._stream()))
+        if mask is None:
+            self._obs_desync = False
         return self.obs
 
     def step(self, actions, spawn=None):
@@ -224,6 +232,7 @@ class LmazeVecCuda(object):
         pa, ka = _abi.dl(actions)
         ps, ks = _abi.dl(spawn)
         _abi.check(self._lib.lmz_step_dl(self._h, pa, ps, self._stream()))
+        self._obs_desync = False         # a step always leaves the window fully rendered (full render when out of sync)
         return self.obs, self.reward, self.done, {"action": actions}
 
     def capture_step(self, actions_buf, spawn_buf=None):
@@ -234,6 +243,10 @@ class LmazeVecCuda(object):
         bound tensors.  For small batches the step is launch-bound (a 4,096-env step is ~65 us of
         GPU work), and a graph replay skips the Python + ctypes + validation cost.  The kernels
         re-arm their own work counters, so a captured launch replays correctly any number of times.
+
+        render_mode="incremental": the captured launch is the patch kernel, which is only correct while `obs`
+        holds a full render of the current state.  After set_state / rollout / set_window call render_obs()
+        (or step() / reset()) before the next replay; replay() raises RuntimeError otherwise.
         """
         actions_buf = self._as_actions(actions_buf)
         spawn_buf = self._as_spawn(spawn_buf)
@@ -244,7 +257,15 @@ class LmazeVecCuda(object):
         with torch.cuda.graph(graph):
             self.step(actions_buf, spawn=spawn_buf)
         self._graphs = getattr(self, "_graphs", []) + [(graph, actions_buf, spawn_buf)]
-        return graph.replay
+        if self.render_mode != "incremental":
+            return graph.replay
+
+        def replay():
+            if self._obs_desync:
+                raise RuntimeError("incremental render: obs is out of sync with the env state (set_state / rollout / "
+                                   "set_window since the last render); call render_obs() before replaying the graph")
+            graph.replay()
+        return replay
 
     def step_host(self, actions_host, reward_host, done_host, obs_host=None):
         """End-to-end step with HOST buffers (pinned CPU tensors): H2D actions, fused
@@ -266,6 +287,7 @@ class LmazeVecCuda(object):
         _abi.check(self._lib.lmz_step_host(
             self._h, actions_host.data_ptr(), ad, reward_host.data_ptr(), done_host.data_ptr(),
             None if obs_host is None else obs_host.data_ptr(), self._stream()))
+        self._obs_desync = False
         return reward_host, done_host
 
     def rollout(self, T, actions=None, rewards=None, dones=None):
@@ -283,11 +305,13 @@ class LmazeVecCuda(object):
         pr, kr = _abi.dl(rewards)
         pd, kd = _abi.dl(dones_u8)
         _abi.check(self._lib.lmz_rollout_dl(self._h, T, pa, pr, pd, self._stream()))
+        self._obs_desync = True          # every env moved, nothing was rendered
         return rewards, dones_u8.view(torch.bool)
 
     def render_obs(self):
         """Re-render the current state into `obs` without stepping."""
         _abi.check(self._lib.lmz_render(self._h, self._stream()))
+        self._obs_desync = False
         return self.obs
 
     def render(self, mode="human", close=False):
@@ -312,6 +336,7 @@ class LmazeVecCuda(object):
         state = torch.as_tensor(state).to(device=self.device, dtype=torch.int32).contiguous()
         p, k = _abi.dl(state)
         _abi.check(self._lib.lmz_set_state_dl(self._h, p, self._stream()))
+        self._obs_desync = True
 
     def get_visit(self):
         """v4: the float visit layer state[2] of every env, f32 [N, 18, 18]."""
@@ -330,8 +355,8 @@ class LmazeVecCuda(object):
         err = ctypes.c_int64()
         _abi.check(self._lib.lmz_stats(self._h, ctypes.byref(out), ctypes.byref(err), self._stream()))
         if check_errors and err.value:
-            raise ValueError("%d injected spawn cells were rejected (wall/goal/out of range) or actions were out "
-                             "of range" % err.value)
+            raise ValueError("%d injected spawn cells were rejected (wall/goal/out of range), actions were out of "
+                             "range, or set_state rows were not reachable states" % err.value)
         return dict(zip(_abi.STAT_NAMES, (int(v) for v in out)))
 
     def stats_reset(self):

@@ -165,7 +165,9 @@ int lmz_set_window_dl(lmz_env *env, DLManagedTensor *obs, int64_t env_lo);
  * goal_y (the cells the reference's rejection loop would have accepted; goal
  * ignored by v0; for v2 the last column is goal_y | new_layout << 5, because its
  * reset also re-rolls the maze, lmaze_env_v2.py:90-92).  Re-renders obs for the
- * envs it resets. */
+ * envs it resets.  v3: a row with LMZ_SPAWN_FORCE added to goal_x overrides RANDOM_BALL /
+ * RANDOM_GOAL = 0 -- the priority reset(mode="test") has in lmaze_env_v3.py:145-146,154-155. */
+#define LMZ_SPAWN_FORCE 64
 int lmz_reset(lmz_env *env, const uint8_t *mask, const int32_t *spawn, void *stream);
 int lmz_reset_dl(lmz_env *env, DLManagedTensor *mask, DLManagedTensor *spawn, void *stream);
 
@@ -199,7 +201,10 @@ int lmz_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedT
 /* Unpacked per-env state, int32 [N][LMZ_ST_COLS] on the device (checkpoint /
  * resume, and how parity tests start both sides from the same state).  For v2 columns
  * 5 and 6 are: layout (1..5), and prev_x | prev_y << 5 | last_action << 10 | action_valid << 15
- * (the position of the previous crop and the action plane of the current obs). */
+ * (the position of the previous crop and the action plane of the current obs).
+ * lmz_set_state never repairs a row silently: a row the env could not be in (coordinate outside the
+ * grid interior, ball on a wall (v0/v3), v3 goal on a wall, reward code / maze / action out of range,
+ * negative counters) is clamped so that the kernels stay in bounds AND counted in lmz_stats' error counter. */
 /* For v5/v6 the rows are int32 [N][LMZ_ST_COLS_HIER] (see lmz_state_cols). */
 int lmz_get_state(lmz_env *env, int32_t *out, void *stream);
 int lmz_set_state(lmz_env *env, const int32_t *in, void *stream);
@@ -265,7 +270,8 @@ int lmz_safe_goal_dl(lmz_env *env, DLManagedTensor *draws, DLManagedTensor *goal
                      void *stream);
 
 /* Copies the device counters to out_host[LMZ_NUM_STATS] (synchronises `stream`).
- * *errors_host (may be NULL) receives the number of rejected injected spawns. */
+ * *errors_host (may be NULL) receives the number of rejected injected spawns, out-of-range actions
+ * (v2/v4/v5), IndexError rows (v5 local obs) and invalid lmz_set_state rows. */
 int lmz_stats(lmz_env *env, int64_t *out_host, int64_t *errors_host, void *stream);
 int lmz_stats_reset(lmz_env *env, void *stream);
 

@@ -2,6 +2,7 @@
 declares, validates arguments, and refuses to run without a CUDA device (no fallback)."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -98,6 +99,39 @@ def test_registry_and_spaces():
     a, o = make_spaces(4, (4, 84, 84))
     assert a.n == 4 and tuple(o.shape) == (4, 84, 84) and o.dtype == np.float32
     assert float(np.min(o.low)) == 0.0 and float(np.max(o.high)) == 1.0
+
+
+def test_gym_registration_entry_points(monkeypatch):
+    """The reference ids resolve to the reference-typed single-maze classes -- the class names of reference
+    gym_lmaze/__init__.py:3-38 -- and only the 'lmaze-vec-*' ids to the batched classes."""
+    import importlib
+    import warnings
+    import gym_lmaze_b200 as g
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(__file__), "_gymstub"))
+    for m in [k for k in sys.modules if k == "gym" or k.startswith("gym.")]:
+        monkeypatch.delitem(sys.modules, m)
+    reg = importlib.import_module("gym.envs.registration")
+    reg.registry.clear()
+    done = g.register_with(reg.register)
+    assert set(done) == set(g.registered_ids()) == set(reg.registry)
+    ref_names = {"lmaze-v0": "LmazeEnv", "lmaze-v2": "LmazeEnv_v2", "lmaze-v3": "LmazeEnv_v3", "lmaze-v4": "LmazeEnv_v4",
+                 "lmaze-v5": "LmazeEnv_v5", "lmaze-v6": "LmazeEnv_v6"}
+    for env_id, name in ref_names.items():
+        rec = reg.registry[env_id]
+        assert rec["entry_point"] == "gym_lmaze_b200:" + name and rec["kwargs"] == {}
+        assert getattr(g, name) is g._SINGLE[env_id[-2:]]          # what make(env_id) constructs too
+    for k in ("0", "2", "3", "4"):
+        rec = reg.registry["lmaze-vec-v" + k]
+        assert rec["entry_point"] == "gym_lmaze_b200:LmazeVecCuda" and rec["kwargs"]["variant"] == "v" + k
+    for k in ("5", "6"):
+        assert reg.registry["lmaze-vec-v" + k]["entry_point"] == "gym_lmaze_b200:LmazeHierCuda"
+    # a failing registration is reported, not swallowed
+    def boom(**kw):
+        raise RuntimeError("id clash")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert g.register_with(boom) == []
+    assert len(w) == len(g.registered_ids()) and "id clash" in str(w[0].message)
 
 
 def test_shard_range_partitions_exactly():
