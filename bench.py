@@ -14,8 +14,15 @@ stream already resident in HBM; `e2e` = the same metric through the host-buffer
 C-ABI call lmz_step_host (pinned host actions -> H2D -> fused step -> D2H
 reward/done), observations staying in HBM where the policy consumes them (DLPack).
 `--impl reference` times the CPU oracle port (the reference's algorithm in C,
-oracle/) on all host threads; the reference itself is pure Python and cannot
-travel to the GPU box.
+oracle/) on all host threads; where the unmodified reference is importable
+(/root/reference here, baseline/_ref on the GPU box) its own Python step() loop is
+timed beside it on every host core (`cpu_baseline.reference_python`).
+
+`extras` (every world size, barrier + max over ranks like `value`): the T=64 rollout
+at 2^21 envs per GPU (BASELINE configs[4]), lmaze-v3 full render at 2^20 envs per GPU
+(configs[3]), v0 compact and incremental observations, host-consumer e2e lines, and
+`checks`: NCCL-summed step counters against launches x envs, and shard invariance
+on the real GPUs (rank r's first rows replayed by rank 0 with the same global ids).
 """
 import argparse
 import json
@@ -115,14 +122,21 @@ def measured_peak():
 
 
 def recorded_traffic(variant, render_mode, n_envs):
-    """dram bytes per launch from the committed `ncu --set full` capture, if any (scaled to this batch size)."""
+    """dram bytes per launch from the committed `ncu --set full` capture (scaled to this batch size), and whether
+    that capture was taken on the kernel sources this build was compiled from (profiles/traffic.json records the
+    hash of csrc/ + include/; a capture of other sources is reported as stale and its number withheld)."""
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s" % (variant, render_mode))
-        if isinstance(rec, dict):
-            return rec["bytes"] * n_envs / rec["envs"]
-        return rec
-    except Exception:
-        return None
+        from gym_lmaze_b200.build import source_hash
+        doc = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        rec = doc.get("%s_%s" % (variant, render_mode))
+        fresh = doc.get("csrc_hash") == source_hash()
+        src = {"file": "profiles/traffic.json", "csrc_hash": doc.get("csrc_hash"), "matches_build": fresh}
+        if not fresh or not isinstance(rec, dict):
+            return None, src
+        src["capture"] = rec.get("source")
+        return rec["bytes"] * n_envs / rec["envs"], src
+    except Exception as exc:
+        return None, {"error": repr(exc)}
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)
@@ -194,6 +208,17 @@ def python_loop_throughput(n_steps=40):
     return n_steps / (time.perf_counter() - t0)
 
 
+def reference_python_throughput(variant, budget_s):
+    """The UNMODIFIED reference's own step() loop on every host core for a fixed wall budget:
+    P independent processes, each loading gym_lmaze/envs/lmaze_env*.py by path (baseline/_ref on the GPU box,
+    /root/reference in the build container) under the test harness's gym stub.  None where it is not present."""
+    try:
+        from oracle import ref_bench
+        return ref_bench.measure(variant, os.cpu_count() or 1, budget_s)
+    except Exception as exc:  # pragma: no cover
+        return {"error": repr(exc)}
+
+
 def run_reference(args):
     """`--impl reference`: the CPU arm.  Rank 0 only; other ranks exit 0 without work."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -237,7 +262,8 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, note="CPU arm: bounded sample per step"),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "reference_python": reference_python_throughput(args.variant, 5.0)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -275,32 +301,86 @@ def workload_config(args, note=None):
 
 
 # --------------------------------------------------------------------------- our arm
+class Ranks(object):
+    """One process per GPU: barrier, max-over-ranks and the device of this rank."""
+
+    def __init__(self, torch, dist):
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize(self.dev)
+
+    def reduce_max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok):
+        if self.world == 1:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def gather(self, t):
+        """[world] list of every rank's copy of `t` (same shape on every rank)."""
+        if self.world == 1:
+            return [t]
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t.contiguous())
+        return out
+
+    def timed_ms(self, fn, reps, warm):
+        """`reps` calls of fn(i) after `warm` untimed ones: CUDA events on the launch stream, barrier +
+        synchronize on both sides, MAX over ranks.  Returns ms per call."""
+        torch = self.torch
+        for i in range(warm):
+            fn(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.reduce_max(e0.elapsed_time(e1)) / reps
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rk = Ranks(torch, dist)
+    world, rank, dev = rk.world, rk.rank, rk.dev
+    barrier, reduce_max = rk.barrier, rk.reduce_max
 
     import gym_lmaze_b200 as lmz          # raises if the CUDA library is missing: no fallback
     N = args.envs
     W = args.window if 0 < args.window < N else N
     hier = args.variant == "v5"
+    SEED = 2026
     if hier:
-        env = lmz.LmazeHierCuda(N, "v5", device=dev, seed=2026, env_id0=rank * N, autoreset=True, obs_mode=args.obs_mode)
+        env = lmz.LmazeHierCuda(N, "v5", device=dev, seed=SEED, env_id0=rank * N, autoreset=True, obs_mode=args.obs_mode)
     else:
-        env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, env_id0=rank * N, autoreset=True,
+        env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=SEED, env_id0=rank * N, autoreset=True,
                                render_mode=args.render_mode, obs_mode=args.obs_mode, obs_window=W)
     windows = list(range(0, N, W))
     if windows[-1] + W > N:
         windows[-1] = N - W
     obs_bytes = env.obs[0].numel() * env.obs.element_size()
-    step_bytes = obs_bytes + 14 + (2 * 324 * 4 if args.variant == "v4" else 0)   # v4: visit layer read + write
+    step_bytes = obs_bytes + 14 + (2 * VISIT_BYTES if args.variant == "v4" else 0)   # v4: visit layer read + write
     if hier:
         step_bytes = 0        # filled in after the timed region from the measured localDone / planner fractions
     if args.render_mode == "incremental":
@@ -321,29 +401,21 @@ def run_ours(args):
         for lo in windows[1:]:
             env.render_window(lo)
     R = 4
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    ring = torch.randint(0, env.num_actions, (R, N), generator=gen, device=dev, dtype=torch.uint8)
-    goal_ring = torch.randint(0, 25, (R, N), generator=gen, device=dev, dtype=torch.uint8) if hier else None
+
+    def action_ring(r):
+        """rank r's device-resident action ring (any rank can regenerate it: shard-invariance replay)"""
+        gen = torch.Generator(device=dev).manual_seed(1234 + r)
+        ring_ = torch.randint(0, env.num_actions, (R, N), generator=gen, device=dev, dtype=torch.uint8)
+        goals_ = torch.randint(0, 25, (R, N), generator=gen, device=dev, dtype=torch.uint8) if hier else None
+        return ring_, goals_
+    ring, goal_ring = action_ring(rank)
     env.reset()
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # ---- device-resident inputs: K launches of the fused kernel, CUDA events on the launch stream
     for i in range(args.warmup):
         full_step(i)
     launches0 = env.launch_count
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(rk.local_rank)
     if rank == 0:
         sampler.start()
     barrier()
@@ -370,20 +442,27 @@ def run_ours(args):
         # 2 rewards, 4 flag bytes, action; planner launch: 3 state words read, and for the waiting envs goal +
         # state write + local obs
         fov_b, loc_b = (34300, 19600) if args.obs_mode == "full" else (700, 400)
-        step_bytes = int(fov_b + loc_b + 1296 * (1 + ld) + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
+        step_bytes = int(fov_b + loc_b + VISIT_BYTES * (1 + ld) + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
         hier_note = {"local_done_fraction": ld, "planner_fraction": pf,
-                     "bytes": "34,300 foveal + 19,600 local obs + 1,296 visit read (+1,296 x localDone written) + state/"
-                              "rewards/flags/action 37 + planner launch: 12 + planner_fraction x (19,600 local obs + 15)"}
+                     "bytes": "34,300 foveal + 19,600 local obs + %d visit read (+%d x localDone written) + state/"
+                              "rewards/flags/action 37 + planner launch: 12 + planner_fraction x (19,600 local obs + 15)"
+                              % (VISIT_BYTES, VISIT_BYTES)}
     achieved = N * step_bytes / (step_ms * 1e-3) / 1e9
 
+    # ---- checks on the real GPUs: counters and shard invariance
+    checks = main_workload_checks(rk, lmz, env, args, hier, SEED, N, W, R, action_ring,
+                                  steps_done=args.warmup + args.steps)
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory)
-    a_host = torch.randint(0, env.num_actions, (R, N), dtype=torch.uint8).pin_memory()
+    hgen = torch.Generator().manual_seed(4321 + rank)
+    a_host = torch.randint(0, env.num_actions, (R, N), generator=hgen, dtype=torch.uint8).pin_memory()
     r_host = torch.empty(N, dtype=torch.float32).pin_memory()
     d_host = torch.empty(N, dtype=torch.uint8).pin_memory()
     if hier:
-        g_host = torch.randint(0, 25, (R, N), dtype=torch.uint8).pin_memory()
+        g_host = torch.randint(0, 25, (R, N), generator=hgen, dtype=torch.uint8).pin_memory()
         r2_host = torch.empty(N, dtype=torch.float32).pin_memory()
         d2_host = torch.empty(N, dtype=torch.uint8).pin_memory()
+
     def full_step_host(i):
         if hier:
             env.step_host(g_host[i % R], a_host[i % R], r_host, r2_host, d_host, d2_host)
@@ -411,23 +490,24 @@ def run_ours(args):
     e2e_value = world * N * args.steps / (e2e_ms * 1e-3)
     checksum = float(r_host.sum())               # the host really consumes the result
 
-    extras = {}
-    if not args.no_extras and rank == 0 and world == 1:
-        extras = side_measurements(env, args, torch, dev)
-
     stats = env.stats_allreduce(check_errors=not hier) if world > 1 else env.stats(check_errors=not hier)   # v5: random actors hit the reference's IndexError rows
-    if extras and args.variant in ("v0", "v3") and args.obs_mode == "full" and args.render_mode != "incremental":
-        # (3) same workload, obs tensor kept PERSISTENT and patched in place (needs the 118 GB back first)
-        env.close()
-        del env
-        torch.cuda.empty_cache()
-        extras["incremental_render"] = incremental_measurement(args, torch, dev, N, ring)
+    launches_total = env.launch_count
+    env.close()
+    del env, ring, goal_ring
+    torch.cuda.empty_cache()
+
+    # ---- other operating points, at EVERY world size (each names its own mode; never mixed into `value`)
+    extras = {}
+    if not args.no_extras:
+        extras = side_measurements(rk, lmz, args, SEED)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak()
+    traffic, traffic_src = (recorded_traffic(args.variant, args.render_mode, N)
+                            if (args.obs_mode == "full" and W == N) else (None, None))
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
@@ -439,12 +519,14 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps,
                 "api": "LmazeHierCuda.step_host -> lmz_hier_step_host (C ABI)" if hier
                 else "LmazeVecCuda.step_host -> lmz_step_host (C ABI)",
-                "obs": "device-resident (consumed on the GPU via DLPack); see extras.e2e_obs_to_host for the "
-                       "full obs D2H variant", "reward_checksum": checksum},
+                "obs": "device-resident: this e2e assumes a GPU-resident consumer (the policy reads the obs tensor "
+                       "zero-copy via DLPack); actions H2D and reward/done D2H are inside the timed region, the "
+                       "observation is NOT copied to the host.  For a HOST consumer see extras.e2e_host_consumer "
+                       "(compact / bit-packed obs landing in pinned host memory) and extras.e2e_obs_to_host "
+                       "(every f32 obs byte over PCIe).", "reward_checksum": checksum},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(args.variant, args.render_mode, N)
-                     if (args.obs_mode == "full" and W == N) else None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "lmz_fov_small_kernel<%s>" % args.variant.upper()
                      if (args.variant in ("v2", "v4", "v5") and args.obs_mode == "compact") else
                      "lmz_env_fov_kernel<%s>" % args.variant.upper() if args.variant in ("v2", "v4", "v5") else
@@ -458,7 +540,14 @@ def run_ours(args):
                      "kernel_ms_avg": kernel_ms, "kernel_ms_min": per_step[0],
                      "kernel_ms_median": per_step[len(per_step) // 2]},
         "episode_stats": stats,
+        "checks": checks,
     }
+    checks["nccl_steps_sum"] = {"steps": stats["steps"], "expected": world * N * (launches_total // launches_per_step)
+                                if not hier else None,
+                                "what": "sum over ranks of the device step counters (one all_reduce(int64[8])) vs "
+                                        "world x envs x step launches of the whole run"}
+    if not hier:
+        checks["nccl_steps_sum"]["ok"] = checks["nccl_steps_sum"]["steps"] == checks["nccl_steps_sum"]["expected"]
     if hier_note:
         line["roofline"]["v5"] = hier_note
     if extras:
@@ -474,90 +563,114 @@ def run_ours(args):
             "sample": "%d steps of a 16384-env slice of the workload (%.1f s), C oracle port, %d pthreads"
                       % (k_all, dt_all, P),
             "single_core": {"value": v_one, "sample": "%d steps x 2048 envs (%.1f s)" % (k_one, dt_one)},
+            "reference_python": reference_python_throughput(args.variant, min(8.0, args.cpu_budget)),
             "python_loop": None if hier else {"value": python_loop_throughput(), "cores": 1,
-                            "sample": "40 steps of the interpreted per-pixel loop restatement (oracle/pyloop.py), "
-                                      "the reference's implementation style; survey-time probe of the real "
-                                      "reference: ~40 env-steps/s/core"},
+                            "sample": "40 steps of oracle/pyloop.py, a RESTATEMENT of the reference's interpreted "
+                                      "per-pixel loop (not the reference: it runs ~2x faster than the real "
+                                      "lmaze_env.py, see reference_python / profiles/r1_config0_reference_cpu.json)"},
         }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def incremental_measurement(args, torch, dev, N, ring):
-    """render_mode='incremental': full f32 obs tensor, bit-identical to a re-render after every step, but a
-    step only rewrites the ball's old and new ExE block (its own bytes figure; not the headline)."""
-    import gym_lmaze_b200 as lmz
-    try:
-        env = lmz.LmazeVecCuda(N, args.variant, device=dev, seed=2026, autoreset=True, render_mode="incremental")
-        env.reset()
-        for i in range(5):
-            env.step(ring[i % ring.shape[0]])
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 50
-        e0.record()
-        for i in range(reps):
-            env.step(ring[i % ring.shape[0]])
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / reps
-        E = 7 if args.variant == "v0" else 4
-        out = {"value": N / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "envs": N,
-               "bytes_per_env_step": 2 * E * E * 4 + 14,
-               "mode": "lmz_env_incr_kernel: persistent f32 obs tensor patched in place (old block erased, new block "
-                       "drawn); tensor content identical to the full render after every step"}
-        env.close()
-        return out
-    except Exception as exc:  # pragma: no cover
-        return {"error": repr(exc)}
+VISIT_BYTES = 18 * 18 * 4     # one env's float visit layer (v4 / v5)
 
 
-def side_measurements(env, args, torch, dev):
-    """Other operating points, each named with its own mode (never mixed into `value`)."""
+def main_workload_checks(rk, lmz, env, args, hier, seed, N, W, R, action_ring, steps_done, K=1024, KO=32):
+    """Shard invariance ON THE REAL GPUs: rank r's env i has global id r*N + i.  Rank 0 replays,
+    for every rank r, the first K envs of r's shard -- a K-env handle with env_id0 = r*N, r's action ring, the same
+    number of steps -- and compares reward bits, done flags, packed state rows and the first KO observation rows with
+    what rank r computed inside its N-env batch."""
+    torch = rk.torch
+    if W != N:
+        return {"shard_invariance": {"skipped": "render window in use"}}
+    K = min(K, N)
+    KO = min(KO, K)
+    mine = {"reward": env.reward[:K].view(torch.int32).clone(), "done": env._done_u8[:K].clone(),
+            "state": env.get_state()[:K].clone(), "obs": env.obs[:KO].clone()}
+    if hier:
+        mine["reward2"] = env.local_reward[:K].view(torch.int32).clone()
+        mine["loc"] = env.loc_obs[:KO].clone()
+    gathered = {k: rk.gather(v) for k, v in mine.items()}
+    out = {"envs_replayed_per_rank": K, "obs_rows_compared": KO, "steps_replayed": steps_done, "ranks": rk.world,
+           "what": "rank 0 re-runs the first %d envs of every rank's shard as a separate %d-env handle with the same "
+                   "global ids and compares reward bits / done / state rows / obs rows bit for bit" % (K, K)}
+    if rk.rank == 0:
+        ok, bad = True, []
+        for r in range(rk.world):
+            ring_r, goals_r = action_ring(r)
+            if hier:
+                ref = lmz.LmazeHierCuda(K, "v5", device=rk.dev, seed=seed, env_id0=r * N, autoreset=True, obs_mode=args.obs_mode)
+            else:
+                ref = lmz.LmazeVecCuda(K, args.variant, device=rk.dev, seed=seed, env_id0=r * N, autoreset=True,
+                                       render_mode=args.render_mode, obs_mode=args.obs_mode)
+            ref.reset()
+            for i in list(range(args.warmup)) + list(range(args.steps)):
+                if hier:
+                    ref.plannerStep(goals_r[i % R][:K].contiguous(), mask="auto")
+                    ref.step(ring_r[i % R][:K].contiguous(), goal_plane=False)
+                else:
+                    ref.step(ring_r[i % R][:K].contiguous())
+            same = (torch.equal(ref.reward.view(torch.int32), gathered["reward"][r])
+                    and torch.equal(ref._done_u8, gathered["done"][r])
+                    and torch.equal(ref.get_state(), gathered["state"][r])
+                    and torch.equal(ref.obs[:KO], gathered["obs"][r]))
+            if hier:
+                same = same and torch.equal(ref.local_reward.view(torch.int32), gathered["reward2"][r]) \
+                    and torch.equal(ref.loc_obs[:KO], gathered["loc"][r])
+            if not same:
+                ok = False
+                bad.append(r)
+            ref.close()
+            del ring_r, goals_r
+        out["ok"], out["mismatching_ranks"] = ok, bad
+    return {"shard_invariance": out}
+
+
+def _free(torch, *envs):
+    for e in envs:
+        e.close()
+    torch.cuda.empty_cache()
+
+
+def side_measurements(rk, lmz, args, seed):
+    """Other operating points, each named with its own mode (never mixed into `value`).  Run on EVERY rank with the
+    rank's own global-id shard; every `value` is the whole-job aggregate: world x envs x steps / max-over-ranks time."""
+    torch, dev, world, rank = rk.torch, rk.dev, rk.world, rk.rank
     out = {}
-    N = env.num_envs
-    # (0) what a trivial streaming-write kernel gets on this GPU right now (8 GB torch fill_)
+    # (0) what a trivial streaming-write kernel gets on this GPU right now (8 GiB torch fill_), rank 0's GPU
     scratch = torch.empty(2 << 30, dtype=torch.float32, device=dev)
-    scratch.fill_(1.0)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        scratch.fill_(1.0)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    out["pure_write_fill_gbs"] = {"value": 5 * scratch.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9,
-                                  "what": "torch.fill_ over 8 GiB, same process: the write-only ceiling; "
-                                          "MEASURED_PEAKS hbm_gbs is a read+write copy, so a pure-write kernel "
+    ms = rk.timed_ms(lambda i: scratch.fill_(1.0), 5, 1)
+    out["pure_write_fill_gbs"] = {"value": scratch.numel() * 4 / (ms * 1e-3) / 1e9,
+                                  "what": "torch.fill_ over 8 GiB on every rank at once (slowest rank): the write-only "
+                                          "ceiling; MEASURED_PEAKS hbm_gbs is a read+write copy, so a pure-write kernel "
                                           "can exceed it"}
     del scratch
-    if args.variant in ("v2", "v4", "v5"):
+    torch.cuda.empty_cache()
+    if args.variant != "v0" or args.obs_mode != "full" or args.render_mode != "tma":
+        return out            # the side measurements belong to the default (headline) run
+    try:
+        out["rollout_T64"] = rollout_measurement(rk, lmz, seed)
+    except Exception as exc:  # pragma: no cover
+        out["rollout_T64"] = {"error": repr(exc)}
+    for name, fn in (("v3_full_render", lambda: fused_step_measurement(rk, lmz, seed, "v3", 1 << 20, reps=20)),
+                     ("v0_compact", lambda: fused_step_measurement(rk, lmz, seed, "v0", 1 << 24, reps=30, obs_mode="compact")),
+                     ("v3_compact", lambda: fused_step_measurement(rk, lmz, seed, "v3", 1 << 23, reps=30, obs_mode="compact")),
+                     ("incremental_render", lambda: fused_step_measurement(rk, lmz, seed, "v0", 1 << 20, reps=50,
+                                                                           render_mode="incremental")),
+                     ("e2e_host_consumer", lambda: host_consumer_measurement(rk, lmz, seed))):
+        try:
+            out[name] = fn()
+        except Exception as exc:  # pragma: no cover
+            out[name] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+    if world > 1 or rank != 0:
         return out
-    # (1) BASELINE configs[4]-style: T=64 fused rollout, device-side Philox actions, no per-step obs
-    T = 64
-    rew = torch.empty((T, N), dtype=torch.float32, device=dev)
-    don = torch.empty((T, N), dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        env.rollout(T, rewards=rew, dones=don)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        env.rollout(T, rewards=rew, dones=don)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
-    out["rollout_T64"] = {"value": N * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_rollout": ms, "envs": N,
-                          "mode": "lmz_rollout_kernel, no per-step obs, device Philox actions, reward f32 + done u8 "
-                                  "[T,N] written", "bytes_per_env_step": 5.25,
-                          "achieved_gbs": N * T * 5.25 / (ms * 1e-3) / 1e9}
-    del rew, don
+    # ---- single-GPU host-side costs (wall clock; not multi-rank quantities)
     # (1b) BASELINE configs[1]-size batch (4,096 envs): the step is launch-bound (~65 us of GPU work), so what the host
     # side costs per call matters -- plain Python step() vs a CUDA-graph replay of the same fused launch
     try:
-        import gym_lmaze_b200 as lmz
         n1 = 4096
         env1 = lmz.LmazeVecCuda(n1, args.variant, device=dev, seed=1, render_mode=args.render_mode)
         env1.reset()
@@ -588,7 +701,6 @@ def side_measurements(env, args, torch, dev):
         out["small_batch_4096"] = {"error": repr(exc)}
     # (2) e2e including the full observation D2H, on a bounded slice (PCIe-bound by construction)
     try:
-        import gym_lmaze_b200 as lmz
         n2 = 16384
         env2 = lmz.LmazeVecCuda(n2, args.variant, device=dev, seed=1, render_mode=args.render_mode)
         env2.reset()
@@ -606,10 +718,141 @@ def side_measurements(env, args, torch, dev):
         out["e2e_obs_to_host"] = {"value": n2 / dt, "unit": "env-steps/s", "envs": n2,
                                   "d2h_bytes_per_step": n2 * (o[0].numel() * 4 + 5),
                                   "d2h_gbs": n2 * o[0].numel() * 4 / dt / 1e9,
-                                  "mode": "lmz_step_host with obs_host: every obs byte copied to pinned host memory"}
+                                  "mode": "lmz_step_host with obs_host: every f32 obs byte copied to pinned host memory "
+                                          "(PCIe-bound by construction; a host consumer should take the compact or "
+                                          "bit-packed observation instead: extras.e2e_host_consumer)"}
         env2.close()
+        del o
     except Exception as exc:  # pragma: no cover
         out["e2e_obs_to_host"] = {"error": repr(exc)}
+    return out
+
+
+def rollout_measurement(rk, lmz, seed, n=1 << 21, T=64, K=1024):
+    """BASELINE configs[4]: T=64 fused rollout, device-side Philox actions, no per-step obs, 2^21 envs per GPU
+    (16 M on 8).  Also the on-hardware checks: NCCL-summed step counter and shard invariance of the rollout."""
+    torch, dev, world, rank = rk.torch, rk.dev, rk.world, rk.rank
+    env = lmz.LmazeVecCuda(n, "v0", device=dev, seed=seed, env_id0=rank * n, autoreset=True, with_obs=False)
+    env.reset()
+    rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+    don = torch.empty((T, n), dtype=torch.uint8, device=dev)
+    env.rollout(T, rewards=rew, dones=don)                      # the first rollout is the one rank 0 replays
+    first = rk.gather(torch.cat([rew[:, :K].reshape(-1).view(torch.int32), don[:, :K].reshape(-1).to(torch.int32)]))
+    inv = {"envs_replayed_per_rank": K, "steps": T, "ranks": world}
+    if rank == 0:
+        bad = []
+        for r in range(world):
+            ref = lmz.LmazeVecCuda(K, "v0", device=dev, seed=seed, env_id0=r * n, autoreset=True, with_obs=False)
+            ref.reset()
+            rr, dd = ref.rollout(T)
+            want = torch.cat([rr.reshape(-1).view(torch.int32), dd.reshape(-1).to(torch.int32)])
+            if not torch.equal(want, first[r]):
+                bad.append(r)
+            ref.close()
+        inv["ok"], inv["mismatching_ranks"] = not bad, bad
+    reps, warm = 10, 2
+    launches0 = env.launch_count
+    ms = rk.timed_ms(lambda i: env.rollout(T, rewards=rew, dones=don), reps, warm)
+    stats = env.stats_allreduce() if world > 1 else env.stats()
+    expected = world * n * T * (1 + reps + warm)
+    res = {"value": world * n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_rollout": ms, "envs_per_gpu": n,
+           "envs_total": world * n, "T": T,
+           "mode": "lmz_rollout_kernel<V0>: T fused steps, state in registers, NO per-step obs, device Philox actions, "
+                   "reward f32 + done u8 [T,N] written; barrier + max over ranks",
+           "bytes_per_env_step": 5.25, "achieved_gbs_per_gpu": n * T * 5.25 / (ms * 1e-3) / 1e9,
+           "launches_timed": env.launch_count - launches0 - warm,
+           "checks": {"nccl_steps_sum": {"steps": stats["steps"], "expected": expected, "ok": stats["steps"] == expected},
+                      "shard_invariance": inv}}
+    # same rollout with the 1-byte reward CODE instead of the f32 reward (2 B per env-step instead of 5)
+    try:
+        codes = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        ms2 = rk.timed_ms(lambda i: env.rollout(T, reward_codes=codes, dones=don), reps, warm)
+        res["reward_code_u8"] = {"value": world * n * T / (ms2 * 1e-3), "unit": "env-steps/s", "ms_per_rollout": ms2,
+                                 "bytes_per_env_step": 2.25,
+                                 "mode": "same kernel, rewards written as u8 codes (0: -0.0, 1: -1.0, 2: -0.01, 3: 100.0; "
+                                         "LmazeVecCuda.REWARD_TABLE[codes] is the f32 tensor)"}
+        del codes
+    except Exception as exc:  # pragma: no cover
+        res["reward_code_u8"] = {"error": repr(exc)}
+    del rew, don
+    _free(torch, env)
+    return res
+
+
+def fused_step_measurement(rk, lmz, seed, variant, n, reps, obs_mode="full", render_mode="tma"):
+    """One fused step launch per step over `n` envs per GPU in the given mode (its own bytes figure)."""
+    torch, dev, world, rank = rk.torch, rk.dev, rk.world, rk.rank
+    env = lmz.LmazeVecCuda(n, variant, device=dev, seed=seed, env_id0=rank * n, autoreset=True, obs_mode=obs_mode,
+                           render_mode=render_mode)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    ring = torch.randint(0, env.num_actions, (4, n), generator=gen, device=dev, dtype=torch.uint8)
+    env.reset()
+    launches0 = env.launch_count
+    ms = rk.timed_ms(lambda i: env.step(ring[i % 4]), reps, 5)
+    stats = env.stats_allreduce() if world > 1 else env.stats()
+    G, E, C = {"v0": (12, 7, 4), "v3": (18, 4, 3)}[variant]
+    if render_mode == "incremental":
+        b, kern = 2 * E * E * 4 + 14, "lmz_env_incr_kernel"
+        mode = ("persistent f32 (%d,%d,%d) obs tensor patched in place (old block erased, new block drawn); tensor content "
+                "identical to the full render after every step" % (C, G * E, G * E))
+    elif obs_mode == "compact":
+        b, kern = C * G * G + 14, "lmz_env_compact_kernel"
+        mode = "u8 (%d,%d,%d) compact observation (un-expanded layers; reference image = x%d replication)" % (C, G, G, E)
+    else:
+        b, kern = C * G * E * G * E * 4 + 14, "lmz_env_tma_kernel"
+        mode = "f32 (%d,%d,%d) full render, fused step + auto-reset" % (C, G * E, G * E)
+    expected = world * n * (reps + 5)
+    res = {"value": world * n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "envs_per_gpu": n,
+           "envs_total": world * n, "variant": variant, "kernel": "%s<%s>" % (kern, variant.upper()), "mode": mode,
+           "bytes_per_env_step": b, "achieved_gbs_per_gpu": n * b / (ms * 1e-3) / 1e9,
+           "launches_timed": env.launch_count - launches0 - 5,
+           "nccl_steps_sum": {"steps": stats["steps"], "expected": expected, "ok": stats["steps"] == expected}}
+    del ring
+    _free(torch, env)
+    return res
+
+
+def host_consumer_measurement(rk, lmz, seed):
+    """End to end for a HOST consumer: every output of a step -- observation included -- lands in pinned host
+    memory, actions come from pinned host memory, through LmazeVecCuda.step_host_pipelined (lmz_step_host_async /
+    lmz_step_host_wait, double buffered: step k's D2H overlaps step k+1's kernel).  Wall clock, max over ranks."""
+    torch, dev, world, rank = rk.torch, rk.dev, rk.world, rk.rank
+    out = {}
+    for name, variant, obs_mode, n in (("v0_compact_u8", "v0", "compact", 1 << 20), ("v0_bits", "v0", "bits", 1 << 22),
+                                       ("v3_bits", "v3", "bits", 1 << 22)):
+        try:
+            env = lmz.LmazeVecCuda(n, variant, device=dev, seed=seed, env_id0=rank * n, autoreset=True, obs_mode=obs_mode)
+            env.reset()
+            pipe = env.host_pipeline()
+            gen = torch.Generator().manual_seed(7 + rank)
+            acts = torch.randint(0, 4, (4, n), generator=gen, dtype=torch.uint8).pin_memory()
+            reps, warm = 20, 4
+            for i in range(warm):
+                pipe.submit(acts[i % 4])
+            pipe.drain()
+            rk.barrier()
+            t0 = time.perf_counter()
+            csum = 0
+            for i in range(reps):
+                res = pipe.submit(acts[i % 4])          # returns the PREVIOUS step's host buffers (or None)
+                if res is not None:
+                    csum += int(res.done[:64].sum())    # the host really touches the result
+            last = pipe.drain()
+            csum += int(last.done[:64].sum())
+            dt = time.perf_counter() - t0
+            rk.barrier()
+            ms = rk.reduce_max(dt * 1e3) / reps
+            per_env = env.obs[0].numel() * env.obs.element_size()
+            out[name] = {"value": world * n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "envs_per_gpu": n,
+                         "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * (per_env + 5), "obs_bytes_per_env": per_env,
+                         "d2h_gbs_per_gpu": n * (per_env + 5) / (ms * 1e-3) / 1e9,
+                         "mode": "obs_mode=%s: obs + reward + done ALL copied to pinned host memory every step, actions "
+                                 "from pinned host memory, double-buffered (lmz_step_host_async/_wait)" % obs_mode,
+                         "done_checksum": csum}
+            del pipe, acts
+            _free(torch, env)
+        except Exception as exc:  # pragma: no cover
+            out[name] = {"error": repr(exc)}
     return out
 
 

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("LMAZE_B200_LIB") or os.path.join(_PKG, "liblmaze_b200
 
 LMZ_V0, LMZ_V2, LMZ_V3, LMZ_V4, LMZ_V5 = 0, 2, 3, 4, 5
 RENDER_TMA, RENDER_ST128, RENDER_INCREMENTAL = 0, 1, 2
-OBS_FULL, OBS_COMPACT = 0, 1
+OBS_FULL, OBS_COMPACT, OBS_BITS = 0, 1, 2
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 NUM_STATS = 8
 SPAWN_FORCE = 64          # LMZ_SPAWN_FORCE
@@ -27,7 +27,8 @@ EXPORTS = (
     "lmz_abi_version", "lmz_last_error", "lmz_default_config", "lmz_obs_shape", "lmz_grid_size", "lmz_obs_desc",
     "lmz_layout", "lmz_num_layouts", "lmz_layout_ex", "lmz_num_actions", "lmz_set_window", "lmz_set_window_dl",
     "lmz_create", "lmz_destroy", "lmz_bind", "lmz_bind_dl", "lmz_reset", "lmz_reset_dl", "lmz_step",
-    "lmz_step_dl", "lmz_step_host", "lmz_render", "lmz_rollout", "lmz_rollout_dl", "lmz_get_state",
+    "lmz_step_dl", "lmz_step_host", "lmz_step_host_async", "lmz_step_host_wait", "lmz_render", "lmz_rollout",
+    "lmz_rollout_dl", "lmz_rollout_codes", "lmz_rollout_codes_dl", "lmz_get_state",
     "lmz_set_state", "lmz_get_state_dl", "lmz_set_state_dl", "lmz_get_visit", "lmz_set_visit", "lmz_get_visit_dl",
     "lmz_set_visit_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
     "lmz_state_cols", "lmz_local_obs_shape", "lmz_bind_local", "lmz_bind_local_dl", "lmz_planner_step",
@@ -96,6 +97,10 @@ def load():
     L.lmz_step.argtypes = [vp, vp, i32, vp, vp]
     L.lmz_step_dl.argtypes = [vp, vp, vp, vp]
     L.lmz_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.lmz_step_host_async.argtypes = [vp, vp, i32, vp, vp, vp, vp, ctypes.POINTER(i32)]
+    L.lmz_step_host_wait.argtypes = [vp, i32]
+    L.lmz_rollout_codes.argtypes = [vp, i32, vp, i32, vp, vp, vp]
+    L.lmz_rollout_codes_dl.argtypes = [vp, i32, vp, vp, vp, vp]
     L.lmz_render.argtypes = [vp, vp]
     L.lmz_rollout.argtypes = [vp, i32, vp, i32, vp, vp, vp]
     L.lmz_rollout_dl.argtypes = [vp, i32, vp, vp, vp, vp]

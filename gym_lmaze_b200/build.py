@@ -29,6 +29,18 @@ def nvcc_command(out=LIB_PATH, extra=()):
             "-I", os.path.join(_ROOT, "include"), *extra, "-o", out, *SOURCES]
 
 
+def source_hash():
+    """sha256 over the kernel sources and the public headers (path-sorted): what profiles/traffic.json and the
+    ncu summaries are keyed by, so that a capture of older kernels cannot pass as evidence for the current ones."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        h.update(os.path.relpath(f, _ROOT).encode())
+        h.update(b"\0")
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def is_stale():
     if not os.path.isfile(LIB_PATH):
         return True

@@ -119,6 +119,11 @@ void build_blob(const char *cells, std::vector<unsigned char> &blob, int &n_cand
       compact[i] = (c == 'B' || c == 'S' || c == 'X');
     }
     blob[V::CLS_OFF + i] = (unsigned char)cls_of(c);
+    for (int ch = 0; ch < V::C; ++ch)                    // the same static layers, one bit per cell
+      if (compact[ch * V::G * V::G + i]) {
+        const int k = ch * V::G * V::G + i;
+        reinterpret_cast<uint32_t *>(blob.data() + V::BITS_OFF)[k >> 5] |= 1u << (k & 31);
+      }
     if (c == 'S' && s_cell == 0) s_cell = i;
     if (c == 'X' && x_cell == 0) x_cell = i;
     // spawn candidates: v0 not in {W,X} (lmaze_env.py:73); v3 not W (lmaze_env_v3.py:148,157)
@@ -221,6 +226,19 @@ struct lmz_env {
   int n_cand, s_cell, x_cell;
   uint64_t rollout_t;            // rollout steps taken so far (keys the action RNG)
   int64_t launches;
+  // double-buffered host pipeline (lmz_step_host_async / lmz_step_host_wait), lazily created
+  struct {
+    bool init;
+    cudaStream_t copy;           // D2H stream: step k's copies overlap step k+1's H2D + kernel
+    cudaEvent_t ready[2];        // step outputs of slot s are complete on the caller's stream
+    cudaEvent_t drained[2];      // the D2H copies out of slot s have finished
+    bool inflight[2];
+    void *act[2];                // device staging of the host actions
+    void *obs[2];                // device obs buffers the kernel writes in pipelined mode (compact / bits rows)
+    float *reward[2];
+    uint8_t *done[2];
+    uint64_t k;                  // steps submitted
+  } pipe;
 };
 
 namespace {
@@ -254,7 +272,15 @@ lmz::KParams base_params(lmz_env *h) {
   p.bulk_split = (uint32_t)h->cfg.tune[3];
   p.aux2 = h->aux2; p.obs2 = h->loc_obs; p.reward2 = h->reward2; p.done2 = h->done2; p.loc_err = h->loc_err;
   p.fgoal_out = h->fgoal_out;
+  p.obs_bits = h->cfg.obs_mode == LMZ_OBS_BITS;
   return p;
+}
+
+// bytes of one env's row in the bound obs tensor
+size_t obs_row_bytes(const lmz_env *h) {
+  if (h->cfg.obs_mode == LMZ_OBS_COMPACT) return h->compact_bytes_per_env;
+  if (h->cfg.obs_mode == LMZ_OBS_BITS) return h->cfg.variant == LMZ_V0 ? lmz::V0::BITS_WORDS * 4 : lmz::V3::BITS_WORDS * 4;
+  return h->obs_bytes_per_env;
 }
 
 constexpr int TMA_THREADS = 32;      // one warp per SM issues the bulk copies: the TMA engine does the moving
@@ -340,7 +366,8 @@ int launch_incremental(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 
 template <class V>
 int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (p.obs == nullptr || h->cfg.obs_mode == LMZ_OBS_COMPACT) return launch_compact<V>(h, p, s);
+  if (p.obs == nullptr || h->cfg.obs_mode == LMZ_OBS_COMPACT || h->cfg.obs_mode == LMZ_OBS_BITS)
+    return launch_compact<V>(h, p, s);
   if (h->cfg.render_mode == LMZ_RENDER_INCREMENTAL) {
     if (p.mode == lmz::MODE_STEP && h->obs_synced) return launch_incremental<V>(h, p, s);
     // not in sync yet (first call after bind / set_window / set_state), or a reset / render call:
@@ -629,6 +656,12 @@ int lmz_obs_desc(int32_t variant, int32_t obs_mode, int64_t shape[3], int32_t *e
     const bool fov = variant == LMZ_V2 || variant == LMZ_V4 || variant == LMZ_V5;
     shape[1] = shape[2] = fov ? 5 : lmz_grid_size(variant);        // foveal variants: the 5x5 crops, as float32
     if (elem_bytes) *elem_bytes = fov ? 4 : 1;
+  } else if (obs_mode == LMZ_OBS_BITS) {
+    if (variant != LMZ_V0 && variant != LMZ_V3)
+      return fail(LMZ_ERR_UNSUPPORTED, "bit-packed observations exist for the full-view variants (v0, v3) only");
+    shape[0] = variant == LMZ_V0 ? lmz::V0::BITS_WORDS * 4 : lmz::V3::BITS_WORDS * 4;   // one row of bytes per env
+    shape[1] = shape[2] = 1;
+    if (elem_bytes) *elem_bytes = 1;
   } else if (obs_mode == LMZ_OBS_FULL) {
     if (elem_bytes) *elem_bytes = 4;
   } else {
@@ -675,8 +708,10 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     return fail(LMZ_ERR_UNSUPPORTED, "incremental render needs a full-view variant (v0, v3): a foveal crop changes entirely every step");
   for (int i = 0; i < 2; ++i)
     if (cfg->reserved[i] != 0) return fail(LMZ_ERR_INVALID, "lmz_config.reserved must be zero");
-  if (cfg->obs_mode != LMZ_OBS_FULL && cfg->obs_mode != LMZ_OBS_COMPACT)
+  if (cfg->obs_mode != LMZ_OBS_FULL && cfg->obs_mode != LMZ_OBS_COMPACT && cfg->obs_mode != LMZ_OBS_BITS)
     return fail(LMZ_ERR_INVALID, "unknown obs_mode %d", cfg->obs_mode);
+  if (cfg->obs_mode == LMZ_OBS_BITS && (foveal || hier))
+    return fail(LMZ_ERR_UNSUPPORTED, "bit-packed observations exist for the full-view variants (v0, v3) only");
   {
     const int t = cfg->tune[0];
     if (t < 0 || t > 1024 || (t & 31))
@@ -800,6 +835,14 @@ int lmz_destroy(lmz_env *h) {
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->goal_count); cudaFree(h->episode); cudaFree(h->blob); cudaFree(h->stats);
   cudaFree(h->act_stage); cudaFree(h->visit); cudaFree(h->aux2);
+  if (h->pipe.init) {
+    cudaStreamSynchronize(h->pipe.copy);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(h->pipe.ready[i]); cudaEventDestroy(h->pipe.drained[i]);
+      cudaFree(h->pipe.act[i]); cudaFree(h->pipe.obs[i]); cudaFree(h->pipe.reward[i]); cudaFree(h->pipe.done[i]);
+    }
+    cudaStreamDestroy(h->pipe.copy);
+  }
   delete h;
   return LMZ_OK;
 }
@@ -816,6 +859,10 @@ int lmz_bind(lmz_env *h, void *obs, float *reward, uint8_t *done) {
 }
 
 static int check_obs_dl(lmz_env *h, DLManagedTensor *obs, int64_t rows, void **po) {
+  if (h->cfg.obs_mode == LMZ_OBS_BITS) {
+    Want w{"obs", kDLUInt, 8, 2, {rows, (int64_t)obs_row_bytes(h), 0, 0}, false, 16};
+    return check_dl(h, obs, w, po, nullptr);
+  }
   if (h->cfg.obs_mode == LMZ_OBS_COMPACT) {
     if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4 || h->cfg.variant == LMZ_V5) {
       Want w{"obs", kDLFloat, 32, 4, {rows, h->C, 5, 5}, false, 16};
@@ -937,10 +984,73 @@ int lmz_step_host(lmz_env *h, const void *actions_host, int32_t action_dtype, fl
   LMZ_CUDA(cudaMemcpyAsync(reward_host, h->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
   LMZ_CUDA(cudaMemcpyAsync(done_host, h->done, n, cudaMemcpyDeviceToHost, s));
   if (obs_host) {
-    const size_t per_env = h->cfg.obs_mode == LMZ_OBS_COMPACT ? h->compact_bytes_per_env : h->obs_bytes_per_env;
-    LMZ_CUDA(cudaMemcpyAsync(obs_host, h->obs, (size_t)h->win_n * per_env, cudaMemcpyDeviceToHost, s));
+    LMZ_CUDA(cudaMemcpyAsync(obs_host, h->obs, (size_t)h->win_n * obs_row_bytes(h), cudaMemcpyDeviceToHost, s));
   }
   LMZ_CUDA(cudaStreamSynchronize(s));
+  return LMZ_OK;
+}
+
+// Double-buffered host step.  Slot s = k & 1 owns a device staging buffer for the actions and device buffers for
+// reward / done / (compact or bit-packed) obs that the kernel of step k writes DIRECTLY; the D2H copies of step k run
+// on the handle's copy stream while the caller's stream already carries step k+1's H2D + kernel into the other slot.
+int lmz_step_host_async(lmz_env *h, const void *actions_host, int32_t action_dtype, float *reward_host,
+                        uint8_t *done_host, void *obs_host, void *stream, int32_t *ticket) {
+  if (int rc = check_handle(h)) return rc;
+  if (int rc = check_bound(h)) return rc;
+  if (!actions_host || !reward_host || !done_host || !ticket) return fail(LMZ_ERR_INVALID, "host buffers / ticket must not be NULL");
+  if (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64)
+    return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
+  if (h->cfg.variant == LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_step_host_async is not built for lmaze-v5/v6");
+  if (obs_host && h->cfg.obs_mode == LMZ_OBS_FULL)
+    return fail(LMZ_ERR_UNSUPPORTED, "the full f32 observation is not double-buffered (2 x N x %zu bytes of HBM): a host "
+                "consumer takes obs_mode compact or bits; pass obs_host = NULL to keep the observation on the device",
+                h->obs_bytes_per_env);
+  if (obs_host && h->win_n != h->cfg.num_envs) return fail(LMZ_ERR_STATE, "obs_host needs the whole batch bound, not a render window");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)h->cfg.num_envs;
+  const size_t row = obs_row_bytes(h);
+  auto &pp = h->pipe;
+  if (!pp.init) {
+    LMZ_CUDA(cudaStreamCreateWithFlags(&pp.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      LMZ_CUDA(cudaEventCreateWithFlags(&pp.ready[i], cudaEventDisableTiming));
+      LMZ_CUDA(cudaEventCreateWithFlags(&pp.drained[i], cudaEventDisableTiming));
+      LMZ_CUDA(cudaMalloc(&pp.act[i], n * 8));
+      LMZ_CUDA(cudaMalloc(&pp.reward[i], n * sizeof(float)));
+      LMZ_CUDA(cudaMalloc(&pp.done[i], n));
+      pp.inflight[i] = false; pp.obs[i] = nullptr;
+    }
+    pp.k = 0; pp.init = true;
+  }
+  const int slot = (int)(pp.k & 1);
+  if (obs_host && !pp.obs[slot]) LMZ_CUDA(cudaMalloc(&pp.obs[slot], n * row));
+  if (pp.inflight[slot]) LMZ_CUDA(cudaStreamWaitEvent(s, pp.drained[slot], 0));   // slot's previous copies must be out
+  const size_t esz = action_dtype == LMZ_ACT_U8 ? 1 : action_dtype == LMZ_ACT_I32 ? 4 : 8;
+  LMZ_CUDA(cudaMemcpyAsync(pp.act[slot], actions_host, n * esz, cudaMemcpyHostToDevice, s));
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_STEP; p.actions = pp.act[slot]; p.action_dtype = action_dtype;
+  p.reward = pp.reward[slot]; p.done = pp.done[slot];
+  if (obs_host) p.obs = pp.obs[slot];                       // compact / bits rows are rewritten whole every step
+  if (int rc = launch_env(h, p, s)) return rc;
+  LMZ_CUDA(cudaEventRecord(pp.ready[slot], s));
+  LMZ_CUDA(cudaStreamWaitEvent(pp.copy, pp.ready[slot], 0));
+  LMZ_CUDA(cudaMemcpyAsync(reward_host, pp.reward[slot], n * sizeof(float), cudaMemcpyDeviceToHost, pp.copy));
+  LMZ_CUDA(cudaMemcpyAsync(done_host, pp.done[slot], n, cudaMemcpyDeviceToHost, pp.copy));
+  if (obs_host) LMZ_CUDA(cudaMemcpyAsync(obs_host, pp.obs[slot], n * row, cudaMemcpyDeviceToHost, pp.copy));
+  LMZ_CUDA(cudaEventRecord(pp.drained[slot], pp.copy));
+  pp.inflight[slot] = true;
+  pp.k += 1;
+  *ticket = slot;
+  return LMZ_OK;
+}
+
+int lmz_step_host_wait(lmz_env *h, int32_t ticket) {
+  if (int rc = check_handle(h)) return rc;
+  if (ticket < 0 || ticket > 1 || !h->pipe.init || !h->pipe.inflight[ticket])
+    return fail(LMZ_ERR_STATE, "no step in flight for ticket %d", ticket);
+  DeviceGuard guard(h->cfg.device);
+  LMZ_CUDA(cudaEventSynchronize(h->pipe.drained[ticket]));
   return LMZ_OK;
 }
 
@@ -956,19 +1066,34 @@ int lmz_render(lmz_env *h, void *stream) {
   return launch_env(h, p, static_cast<cudaStream_t>(stream));
 }
 
+static int rollout_impl(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype, float *rewards,
+                        uint8_t *reward_codes, uint8_t *dones, void *stream);
+
 int lmz_rollout(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype, float *rewards, uint8_t *dones,
                 void *stream) {
+  if (!rewards) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
+  return rollout_impl(h, T, actions, action_dtype, rewards, nullptr, dones, stream);
+}
+
+int lmz_rollout_codes(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype, uint8_t *reward_codes,
+                      uint8_t *dones, void *stream) {
+  if (!reward_codes) return fail(LMZ_ERR_INVALID, "reward_codes/dones must not be NULL");
+  return rollout_impl(h, T, actions, action_dtype, nullptr, reward_codes, dones, stream);
+}
+
+static int rollout_impl(lmz_env *h, int32_t T, const void *actions, int32_t action_dtype, float *rewards,
+                        uint8_t *reward_codes, uint8_t *dones, void *stream) {
   if (int rc = check_handle(h)) return rc;
   if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
   if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4 || h->cfg.variant == LMZ_V5)
     return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2/v4/v5 yet");
-  if (!rewards || !dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
+  if (!dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
   if (actions && (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64))
     return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
   DeviceGuard guard(h->cfg.device);
   lmz::KParams p = base_params(h);
   p.mode = lmz::MODE_STEP; p.actions = actions; p.action_dtype = action_dtype;
-  p.reward = rewards; p.done = dones; p.obs = nullptr; p.T = T; p.t0 = h->rollout_t;
+  p.reward = rewards; p.reward_code = reward_codes; p.done = dones; p.obs = nullptr; p.T = T; p.t0 = h->rollout_t;
   int rc = (h->cfg.variant == LMZ_V0) ? launch_rollout_v<lmz::V0>(h, p, static_cast<cudaStream_t>(stream))
                                       : launch_rollout_v<lmz::V3>(h, p, static_cast<cudaStream_t>(stream));
   if (rc == LMZ_OK) {
@@ -993,6 +1118,23 @@ int lmz_rollout_dl(lmz_env *h, int32_t T, DLManagedTensor *actions, DLManagedTen
   Want wd{"dones", kDLUInt, 8, 2, {T, n, 0, 0}, false, 1};
   if (int rc = check_dl(h, dones, wd, &pd, nullptr)) return rc;
   return lmz_rollout(h, T, pa, ad, static_cast<float *>(pr), static_cast<uint8_t *>(pd), stream);
+}
+
+int lmz_rollout_codes_dl(lmz_env *h, int32_t T, DLManagedTensor *actions, DLManagedTensor *reward_codes,
+                         DLManagedTensor *dones, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pa = nullptr, *pr = nullptr, *pd = nullptr;
+  int ad = 0;
+  if (actions) {
+    Want wa{"actions", 255, 0, 2, {T, n, 0, 0}, false, 1};
+    if (int rc = check_dl(h, actions, wa, &pa, &ad)) return rc;
+  }
+  Want wr{"reward_codes", kDLUInt, 8, 2, {T, n, 0, 0}, false, 1};
+  if (int rc = check_dl(h, reward_codes, wr, &pr, nullptr)) return rc;
+  Want wd{"dones", kDLUInt, 8, 2, {T, n, 0, 0}, false, 1};
+  if (int rc = check_dl(h, dones, wd, &pd, nullptr)) return rc;
+  return lmz_rollout_codes(h, T, pa, ad, static_cast<uint8_t *>(pr), static_cast<uint8_t *>(pd), stream);
 }
 
 static int state_xfer(lmz_env *h, int32_t *io, int set, void *stream) {

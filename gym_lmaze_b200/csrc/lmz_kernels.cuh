@@ -36,7 +36,7 @@ namespace lmz {
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_RENDER = 2 };
 enum : int { ACT_U8 = 0, ACT_I32 = 1, ACT_I64 = 2 };
 enum : int { RENDER_TMA = 0, RENDER_ST128 = 1, RENDER_INCREMENTAL = 2 };
-enum : int { OBS_FULL = 0, OBS_COMPACT = 1 };
+enum : int { OBS_FULL = 0, OBS_COMPACT = 1, OBS_BITS = 2 };
 enum : int {
   STAT_STEPS = 0, STAT_EPISODES, STAT_GOALS, STAT_TIMEOUTS, STAT_WALL_BUMPS, STAT_MOVES, STAT_STALE,
   STAT_EPLEN_SUM, NUM_STATS
@@ -58,6 +58,8 @@ struct KParams {
   int64_t tile_begin, tile_end; // tiles (32 envs) this launch visits
   float *reward;                // [n] or [T][n]
   uint8_t *done;                // [n] or [T][n]
+  uint8_t *reward_code;         // rollout only: RC_* codes u8 [T][n] instead of the f32 rewards, or null
+  int obs_bits;                 // compact kernel: the observation is the bit-packed form (OBS_BITS)
   const uint8_t *blob;          // template blob in global memory
   unsigned long long *stats;    // [NUM_STATS]
   unsigned int *errors;         // rejected injected spawns
@@ -643,6 +645,32 @@ __global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams 
       rmask[k] = __ballot_sync(0xffffffffu, valid && o.render);
     }
     preload_group<G>(p, t1, lane, tiles, pre);       // next group's loads fly while this group's rows are stored
+    if (p.obs_bits) {
+      // bit-packed rows (OBS_BITS): BW words per env, the tile's 32 rows are ONE flat run of 32 * BW words; lane l
+      // stores words l, l+32, ... of the run (coalesced), each the static template word with the env's hot bit(s)
+      constexpr uint32_t BW = V::BITS_WORDS;
+      const uint32_t *btmpl = reinterpret_cast<const uint32_t *>(tab + (V::BITS_OFF - V::TABLES_OFF));
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        if (!rmask[k]) continue;
+        uint32_t hot[V::NHOT];
+        V::hot_bytes(V::unpack(st[k]), hot);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(p.obs) + ((t0 + k) * 32 - p.win_lo) * (int64_t)BW;
+#pragma unroll
+        for (uint32_t j = 0; j < BW; ++j) {
+          const uint32_t w = lane + 32 * j, env = w / BW, kk = w - env * BW;
+          uint32_t v = btmpl[kk];
+#pragma unroll
+          for (int q = 0; q < V::NHOT; ++q) {
+            const uint32_t h = __shfl_sync(0xffffffffu, hot[q], env);
+            v |= ((h >> 5) == kk) ? (1u << (h & 31)) : 0u;
+          }
+          if ((rmask[k] >> env) & 1u) __stcs(dst + w, v);
+        }
+      }
+      t0 = t1; t1 = t2;
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       if (!rmask[k]) continue;
@@ -832,13 +860,14 @@ __global__ void __launch_bounds__(THREADS, 3) lmz_rollout_kernel(const KParams p
     if (fast_spawn) { draw_spawn<V>(p, gid, ep, cand, nball, ngoal); have_next = true; }
     float *rp = p.reward + e;
     uint8_t *dp = p.done + e;
+    uint8_t *cp = p.reward_code + e;    // (only dereferenced when reward codes were asked for)
     // action source: a [T][N] buffer, or Philox (one block = 64 two-bit actions, consumed 2 bits a step)
     uint32_t w[4] = {0, 0, 0, 0}, cur = 0;
     int left = 0;                       // actions left in `cur`
     uint64_t tg = p.t0;
     constexpr int CH = 8;               // caller-supplied actions are fetched CH steps ahead (independent loads)
     long long abuf[CH];
-    for (int t = 0; t < p.T; ++t, ++tg, rp += p.n, dp += p.n) {
+    for (int t = 0; t < p.T; ++t, ++tg, rp += p.n, dp += p.n, cp += p.n) {
       int d;                            // linear offset of the move: -G, +G, -1, +1 or 0 (lmaze_env.py:153-170)
       if (p.actions) {
         if ((t & (CH - 1)) == 0) {
@@ -886,7 +915,8 @@ __global__ void __launch_bounds__(THREADS, 3) lmz_rollout_kernel(const KParams p
         branch = wall ? CLS_W : goal ? CLS_X : CLS_B;
         done = goal || (step > (uint32_t)V::STEP_LIMIT);
       }
-      __stcs(rp, __uint_as_float(c_reward_bits[rcode]));
+      if (p.reward_code) __stcs(cp, (uint8_t)rcode);               // 1 B instead of 4: the reward takes four values
+      else __stcs(rp, __uint_as_float(c_reward_bits[rcode]));
       __stcs(dp, (uint8_t)(done ? 1 : 0));
       c_wall += (branch == CLS_W); c_stale += (branch == CLS_S);
       if (done) {

@@ -16,7 +16,9 @@
 // All segment offsets and lengths are multiples of 16 bytes (row = 336 B / 288 B),
 // which is what both cp.async.bulk and st.global.v4 need.  The blob also carries
 // the G*G cell-class table and the spawn-candidate table, so one bulk load stages
-// everything a CTA needs.
+// everything a CTA needs.  The blob ends with the un-expanded static layers twice more: as bytes (u8 [C][G][G], the
+// compact observation) and as bits (bit k of word k/32 = cell k of the flattened [C][G][G] layers, the bit-packed
+// observation); an env's compact / bit-packed row is that template with its one-hot cell(s) set.
 #pragma once
 #include <stdint.h>
 
@@ -59,7 +61,9 @@ struct V0 {
   static constexpr int MAX_CAND = 80;
   static constexpr uint32_t COMPACT_OFF = CAND_OFF + align16(MAX_CAND * 2);   // u8 [C][G][G] un-expanded layers
   static constexpr uint32_t COMPACT_BYTES = C * G * G;                         // 576
-  static constexpr uint32_t BLOB_BYTES = COMPACT_OFF + align16(COMPACT_BYTES);
+  static constexpr uint32_t BITS_OFF = COMPACT_OFF + align16(COMPACT_BYTES);    // the same layers, one BIT per cell
+  static constexpr uint32_t BITS_WORDS = (C * G * G + 31) / 32;                // 18 words = 72 B per env
+  static constexpr uint32_t BLOB_BYTES = BITS_OFF + align16(BITS_WORDS * 4);
   static constexpr uint32_t TABLES_OFF = CLS_OFF, TABLES_BYTES = BLOB_BYTES - CLS_OFF;
   static constexpr int NHOT = 1;                                               // one-hot bytes per env in the compact obs
   static constexpr int NSEG = 3;
@@ -103,7 +107,9 @@ struct V3 {
   static constexpr int MAX_CAND = 80;
   static constexpr uint32_t COMPACT_OFF = CAND_OFF + align16(MAX_CAND * 2);
   static constexpr uint32_t COMPACT_BYTES = C * G * G;                         // 972
-  static constexpr uint32_t BLOB_BYTES = COMPACT_OFF + align16(COMPACT_BYTES);
+  static constexpr uint32_t BITS_OFF = COMPACT_OFF + align16(COMPACT_BYTES);
+  static constexpr uint32_t BITS_WORDS = (C * G * G + 31) / 32;                // 31 words = 124 B per env (972 bits + 20 pad)
+  static constexpr uint32_t BLOB_BYTES = BITS_OFF + align16(BITS_WORDS * 4);
   static constexpr uint32_t TABLES_OFF = CLS_OFF, TABLES_BYTES = BLOB_BYTES - CLS_OFF;
   static constexpr int NHOT = 2;
   static constexpr int NSEG = 5;

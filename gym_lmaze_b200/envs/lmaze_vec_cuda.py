@@ -28,7 +28,7 @@ _VARIANTS = {"v0": _abi.LMZ_V0, 0: _abi.LMZ_V0, "lmaze-v0": _abi.LMZ_V0,
              "v3": _abi.LMZ_V3, 3: _abi.LMZ_V3, "lmaze-v3": _abi.LMZ_V3,
              "v5": _abi.LMZ_V5, 5: _abi.LMZ_V5, "lmaze-v5": _abi.LMZ_V5}    # v5/v6: use LmazeHierCuda
 _RENDER = {"tma": _abi.RENDER_TMA, "st128": _abi.RENDER_ST128, "incremental": _abi.RENDER_INCREMENTAL}
-_OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT}
+_OBS_MODE = {"full": _abi.OBS_FULL, "compact": _abi.OBS_COMPACT, "bits": _abi.OBS_BITS}
 # lmaze_env_v3.py:236-247 -- the strings v3's step() accepts; anything else is its unmatched branch
 _V3_WORDS = {"left": 0, "0": 0, "right": 1, "1": 1, "up": 2, "2": 2, "down": 3, "3": 3}
 INVALID_ACTION = 255
@@ -58,7 +58,7 @@ class LmazeVecCuda(object):
         if render_mode not in _RENDER:
             raise ValueError("render_mode must be 'tma', 'st128' or 'incremental'")
         if obs_mode not in _OBS_MODE:
-            raise ValueError("obs_mode must be 'full' or 'compact'")
+            raise ValueError("obs_mode must be 'full', 'compact' or 'bits'")
         self._lib = _abi.load()          # raises if the CUDA extension is missing: no fallback
         if not torch.cuda.is_available():
             raise RuntimeError("LmazeVecCuda needs a CUDA device; gym_lmaze_b200 has no CPU path")
@@ -83,6 +83,8 @@ class LmazeVecCuda(object):
         self.obs_mode = obs_mode
         _abi.check(self._lib.lmz_obs_desc(self.variant, _OBS_MODE[obs_mode], ctypes.byref(shape), None))
         self.obs_shape = tuple(shape)                    # shape of one row of `self.obs` in this obs_mode
+        if obs_mode == "bits":                           # u8 [N, R]: one bit per cell of the compact layers
+            self.obs_shape = (int(shape[0]),)
         foveal = self.variant in (_abi.LMZ_V2, _abi.LMZ_V4, _abi.LMZ_V5)
         # compact observations: u8 [C,G,G] layers for the full-view variants, f32 [C,5,5] crops for the foveal ones
         self.obs_dtype = torch.float32 if (obs_mode == "full" or foveal) else torch.uint8
@@ -151,13 +153,23 @@ class LmazeVecCuda(object):
         return self.render_obs()
 
     def expand(self, obs=None):
-        """Compact u8 [n,C,G,G] (foveal variants: f32 [n,C,5,5]) -> the reference's f32 [n,C,G*E,G*E] image (torch plumbing;
-        exact, because the reference upsample is a pure xE replication, lmaze_env.py:219-234)."""
+        """Compact u8 [n,C,G,G] (foveal variants: f32 [n,C,5,5]) or bit-packed u8 [n,R] -> the reference's f32
+        [n,C,G*E,G*E] image (torch plumbing; exact, because the reference upsample is a pure xE replication,
+        lmaze_env.py:219-234, and every value of the un-expanded layers is 0.0 or 1.0)."""
         obs = self.obs if obs is None else obs
+        if self.obs_mode == "bits" and obs.dim() == 2:
+            obs = self.unpack_bits(obs)
         if obs.shape[-1] == self.full_obs_shape[-1]:
             return obs
         e = self.expansion
         return obs.to(torch.float32).repeat_interleave(e, dim=2).repeat_interleave(e, dim=3)
+
+    def unpack_bits(self, bits):
+        """Bit-packed rows u8 [n,R] -> the compact layers u8 [n,C,G,G] (bit k%8 of byte k/8 = cell k)."""
+        C, G = self.full_obs_shape[0], self.grid_size
+        shifts = torch.arange(8, dtype=torch.uint8, device=bits.device)
+        cells = (bits.unsqueeze(-1) >> shifts) & 1
+        return cells.reshape(bits.shape[0], -1)[:, :C * G * G].reshape(bits.shape[0], C, G, G)
 
     def initState(self):
         """Reference initState() (lmaze_env.py:243-244): the un-expanded state layers, last reward,
@@ -290,23 +302,43 @@ class LmazeVecCuda(object):
         self._obs_desync = False
         return reward_host, done_host
 
-    def rollout(self, T, actions=None, rewards=None, dones=None):
+    # f32 value of each reward code (lmaze_env.py:21-23,109): REWARD_TABLE[codes] is the reward tensor, bit for bit
+    REWARD_BITS = (0x80000000, 0xBF800000, 0xBC23D70A, 0x42C80000)
+
+    @classmethod
+    def reward_table(cls, device=None):
+        return torch.tensor([b - (1 << 32) if b >= (1 << 31) else b for b in cls.REWARD_BITS],
+                            dtype=torch.int32, device=device).view(torch.float32)
+
+    def rollout(self, T, actions=None, rewards=None, dones=None, reward_codes=None):
         """T fused steps, no per-step obs.  actions None => device-side random actions.
-        Returns (rewards f32 [T, N], dones bool [T, N])."""
+        Returns (rewards f32 [T, N], dones bool [T, N]); with reward_codes=True (or a u8 [T, N] tensor) the first
+        element is the 1-byte reward code instead (0: -0.0, 1: -1.0, 2: -0.01, 3: 100.0; `reward_table()[codes]`)."""
         T = int(T)
         if actions is not None:
             actions = self._as_actions(actions)
-        if rewards is None:
-            rewards = torch.empty((T, self.num_envs), dtype=torch.float32, device=self.device)
         if dones is None:
             dones = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self.device)
         dones_u8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones
         pa, ka = _abi.dl(actions)
-        pr, kr = _abi.dl(rewards)
         pd, kd = _abi.dl(dones_u8)
-        _abi.check(self._lib.lmz_rollout_dl(self._h, T, pa, pr, pd, self._stream()))
+        if reward_codes is not None and reward_codes is not False:
+            if reward_codes is True:
+                reward_codes = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self.device)
+            pr, kr = _abi.dl(reward_codes)
+            _abi.check(self._lib.lmz_rollout_codes_dl(self._h, T, pa, pr, pd, self._stream()))
+            rewards = reward_codes
+        else:
+            if rewards is None:
+                rewards = torch.empty((T, self.num_envs), dtype=torch.float32, device=self.device)
+            pr, kr = _abi.dl(rewards)
+            _abi.check(self._lib.lmz_rollout_dl(self._h, T, pa, pr, pd, self._stream()))
         self._obs_desync = True          # every env moved, nothing was rendered
         return rewards, dones_u8.view(torch.bool)
+
+    def host_pipeline(self, with_obs=True):
+        """Double-buffered end-to-end stepping for a HOST consumer (lmz_step_host_async / lmz_step_host_wait)."""
+        return HostPipeline(self, with_obs)
 
     def render_obs(self):
         """Re-render the current state into `obs` without stepping."""
@@ -388,6 +420,63 @@ class LmazeVecCuda(object):
             self.close()
         except Exception:
             pass
+
+
+class HostStep(object):
+    """Pinned host buffers one pipelined step lands in."""
+    __slots__ = ("obs", "reward", "done")
+
+    def __init__(self, obs, reward, done):
+        self.obs, self.reward, self.done = obs, reward, done
+
+
+class HostPipeline(object):
+    """Pipeline depth 2 over lmz_step_host_async / lmz_step_host_wait: `submit(actions_host)` enqueues step k (H2D
+    actions, fused step, D2H of reward / done / obs into this pipeline's pinned buffers on the handle's copy stream)
+    and then waits for step k-1, whose HostStep it returns (None on the first call); `drain()` waits for the last
+    one.  Step k's D2H overlaps step k+1's H2D + kernel.  obs needs obs_mode 'compact' or 'bits'; the buffers of a
+    returned HostStep are overwritten by the second submit after it."""
+
+    def __init__(self, env, with_obs=True):
+        if with_obs and (env.obs is None or env.obs_mode == "full"):
+            raise ValueError("a host pipeline carries compact or bit-packed observations (obs_mode='compact' / 'bits'); "
+                             "use with_obs=False to keep the f32 observation on the device")
+        self.env = env
+        n = env.num_envs
+        self.slots = [HostStep(torch.empty((n,) + env.obs_shape, dtype=env.obs_dtype).pin_memory() if with_obs else None,
+                               torch.empty(n, dtype=torch.float32).pin_memory(),
+                               torch.empty(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self._pending = None            # ticket of the step in flight
+        self._keep = None
+        self._k = 0                     # steps submitted (one pipeline per env handle)
+
+    def submit(self, actions_host):
+        env = self.env
+        if actions_host.device.type != "cpu" or not actions_host.is_contiguous() or actions_host.numel() != env.num_envs \
+                or actions_host.dtype not in _ACTION_DTYPES:
+            raise ValueError("submit takes a contiguous CPU uint8/int32/int64 tensor of num_envs actions")
+        ticket = ctypes.c_int32(-1)
+        slot = self.slots[self._k & 1]                       # the handle alternates its two device slots the same way
+        self._k += 1
+        _abi.check(env._lib.lmz_step_host_async(
+            env._h, actions_host.data_ptr(), _ACTION_DTYPES.index(actions_host.dtype), slot.reward.data_ptr(),
+            slot.done.data_ptr(), None if slot.obs is None else slot.obs.data_ptr(), env._stream(), ctypes.byref(ticket)))
+        assert self.slots[ticket.value] is slot
+        prev, self._pending = self._pending, ticket.value
+        keep, self._keep = self._keep, actions_host          # actions must outlive their H2D copy
+        if prev is None:
+            return None
+        _abi.check(env._lib.lmz_step_host_wait(env._h, prev))
+        del keep
+        return self.slots[prev]
+
+    def drain(self):
+        if self._pending is None:
+            return None
+        prev, self._pending = self._pending, None
+        _abi.check(self.env._lib.lmz_step_host_wait(self.env._h, prev))
+        self._keep = None
+        return self.slots[prev]
 
 
 def allreduce_stats(local, device, group=None):

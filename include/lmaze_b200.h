@@ -69,10 +69,15 @@ typedef enum {
 /* What the observation tensor holds. */
 typedef enum {
   LMZ_OBS_FULL = 0,       /* f32 [N,C,G*E,G*E]: the reference's upsampled image (lmaze_env.py:217-234), bit-exact */
-  LMZ_OBS_COMPACT = 1     /* u8  [N,C,G,G]: the same layers BEFORE the xE upsample (lmaze_env.py:208-215);
+  LMZ_OBS_COMPACT = 1,    /* u8  [N,C,G,G]: the same layers BEFORE the xE upsample (lmaze_env.py:208-215);
                              the reference image is exactly repeat_interleave(compact, E) on both axes.
                              Foveal variants (v2, v4, v5): f32 [N,C,5,5] -- the 5x5 crops before the x7 upsample
                              (lmaze_env_v2.py:185-203); v5's local obs is then f32 [N,4,5,5] */
+  LMZ_OBS_BITS = 2        /* v0 / v3: u8 [N,R]: the compact layers at ONE BIT per cell -- every value of those layers is
+                             0.0 or 1.0 (lmaze_env.py:80,92-107) -- bit k of the flattened [C][G][G] layers is bit k%8 of
+                             byte k/8 (little-endian bit order), rows padded to whole 32-bit words: R = 72 (v0, 576 bits),
+                             124 (v3, 972 bits + 20 zero pad bits).  The observation for a HOST consumer: 72 B instead of
+                             112,896 B per env over PCIe; unpacking + xE replication gives the reference image exactly. */
 } lmz_obs_mode;
 
 /* Element type of an action buffer. */
@@ -186,6 +191,17 @@ int lmz_step_dl(lmz_env *env, DLManagedTensor *actions, DLManagedTensor *spawn, 
 int lmz_step_host(lmz_env *env, const void *actions_host, int32_t action_dtype,
                   float *reward_host, uint8_t *done_host, void *obs_host, void *stream);
 
+/* Double-buffered form for a host consumer (pipeline depth 2).  _async enqueues the H2D copy of the actions, the
+ * fused step and -- on an internal copy stream -- the D2H copies of reward / done / obs into the given host
+ * buffers, and returns at once with *ticket (0 or 1); _wait blocks until that step's copies have landed.  The
+ * copies of step k overlap the H2D + kernel of step k+1; a third _async call reuses the first ticket's device
+ * buffers, so wait for ticket t before submitting the second step after it.  All host buffers (actions included)
+ * must stay untouched until the step's _wait returns.  The step's outputs are written to handle-owned device
+ * buffers, NOT to the tensors given to lmz_bind; obs_host is only available for obs_mode compact / bits. */
+int lmz_step_host_async(lmz_env *env, const void *actions_host, int32_t action_dtype, float *reward_host,
+                        uint8_t *done_host, void *obs_host, void *stream, int32_t *ticket);
+int lmz_step_host_wait(lmz_env *env, int32_t ticket);
+
 /* Render the current state into the bound obs without stepping (the
  * upsample loop of lmaze_env.py:208-234 on its own). */
 int lmz_render(lmz_env *env, void *stream);
@@ -197,6 +213,12 @@ int lmz_rollout(lmz_env *env, int32_t T, const void *actions, int32_t action_dty
                 float *rewards, uint8_t *dones, void *stream);
 int lmz_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedTensor *rewards,
                    DLManagedTensor *dones, void *stream);
+/* The same rollout with the rewards written as 1-byte CODES u8 [T][N] -- a reward takes only four values
+ * (lmaze_env.py:21-23,109): 0: -0.0, 1: -1.0 (wall), 2: -0.01 (move), 3: 100.0 (goal) -- 2 B instead of 5 B per env-step. */
+int lmz_rollout_codes(lmz_env *env, int32_t T, const void *actions, int32_t action_dtype,
+                      uint8_t *reward_codes, uint8_t *dones, void *stream);
+int lmz_rollout_codes_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedTensor *reward_codes,
+                         DLManagedTensor *dones, void *stream);
 
 /* Unpacked per-env state, int32 [N][LMZ_ST_COLS] on the device (checkpoint /
  * resume, and how parity tests start both sides from the same state).  For v2 columns

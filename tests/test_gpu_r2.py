@@ -165,3 +165,120 @@ def test_set_state_counts_unreachable_rows(lmz):
     with pytest.raises(ValueError):
         h.stats()
     h.close()
+
+
+# ---------------------------------------------------------------- bit-packed observations (72 B per v0 env)
+@pytest.mark.parametrize("variant", ["v0", "v3"])
+def test_bits_obs_reconstructs_reference_image(lmz, oracle_mod, variant):
+    """obs_mode='bits': 1 bit per cell of the un-expanded layers; unpack + xE replication is the oracle's full image
+    every step (auto-resets, invalid actions, a masked reset, a render window, the batch tail)."""
+    N, T = 3001, 230
+    ov = oracle_mod.V0 if variant == "v0" else oracle_mod.V3
+    ora = oracle_mod.OracleVec(ov, N, seed=11, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, variant, seed=11, autoreset=True, obs_mode="bits")
+    assert env.obs.dtype == torch.uint8 and tuple(env.obs.shape) == (N, 72 if variant == "v0" else 124)
+    assert torch.equal(env.expand(env.reset()).cpu(), torch.from_numpy(ora.reset()))
+    gen = torch.Generator().manual_seed(2)
+    for t in range(T):
+        a = torch.randint(0, 5, (N,), generator=gen)
+        want = t % 5 == 0 or t > T - 3
+        o_ref, r_ref, d_ref = ora.step(a.numpy(), want_obs=want)
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)) and np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
+        if want:
+            assert torch.equal(env.expand(obs).cpu(), torch.from_numpy(o_ref)), t
+        if variant == "v3":
+            assert int((obs[:, 121] >> 4).max()) == 0 and int(obs[:, 122:].max()) == 0     # pad bits stay zero
+    # compact twin: the bits are exactly the compact bytes
+    twin = lmz.LmazeVecCuda(N, variant, seed=11, obs_mode="compact")
+    twin.set_state(env.get_state())
+    assert torch.equal(env.unpack_bits(env.render_obs()), twin.render_obs())
+    twin.close()
+    # masked reset: only the masked rows change
+    before = env.obs.clone()
+    mask = torch.rand(N, generator=gen) < 0.25
+    env.reset(mask=mask)
+    assert torch.equal(env.obs[~mask.cuda()], before[~mask.cuda()])
+    env.close()
+    # render window
+    env = lmz.LmazeVecCuda(N, variant, seed=11, obs_mode="bits", obs_window=1000)
+    ora = oracle_mod.OracleVec(ov, N, seed=11)
+    env.reset(); ora.reset(want_obs=False)
+    for t in range(6):
+        a = torch.randint(0, 4, (N,), generator=gen)
+        o_ref, _, _ = ora.step(a.numpy())
+        if t % 2 == 0:
+            env.set_window(777 * (t // 2) + 1)
+        obs, _, _, _ = env.step(a)
+        assert torch.equal(env.expand(obs).cpu(), torch.from_numpy(o_ref[env.window_lo:env.window_lo + 1000])), t
+    env.close()
+    with pytest.raises(Exception):
+        lmz.LmazeVecCuda(4, "v2", obs_mode="bits")
+
+
+# ---------------------------------------------------------------- rollout with 1-byte reward codes
+@pytest.mark.parametrize("variant", ["v0", "v3"])
+def test_rollout_reward_codes(lmz, variant):
+    N, T = 5000, 150
+    a = lmz.LmazeVecCuda(N, variant, seed=5, with_obs=False)
+    b = lmz.LmazeVecCuda(N, variant, seed=5, with_obs=False)
+    a.reset(); b.reset()
+    table = a.reward_table("cuda")
+    assert rbits(table).tolist() == [0x80000000, 0xBF800000, 0xBC23D70A, 0x42C80000]
+    for it in range(2):
+        rew, done_a = a.rollout(T)
+        codes, done_b = b.rollout(T, reward_codes=True)
+        assert codes.dtype == torch.uint8 and int(codes.max()) <= 3
+        assert torch.equal(table[codes.long()].view(torch.int32), rew.view(torch.int32))
+        assert torch.equal(done_a, done_b)
+    assert torch.equal(a.get_state(), b.get_state()) and a.stats() == b.stats()
+    acts = torch.randint(0, 6, (T, N), device="cuda", dtype=torch.uint8)
+    rew, _ = a.rollout(T, actions=acts)
+    codes, _ = b.rollout(T, actions=acts, reward_codes=torch.empty((T, N), dtype=torch.uint8, device="cuda"))
+    assert torch.equal(table[codes.long()].view(torch.int32), rew.view(torch.int32))
+    a.close(); b.close()
+
+
+# ---------------------------------------------------------------- double-buffered host pipeline
+@pytest.mark.parametrize("variant,obs_mode", [("v0", "compact"), ("v0", "bits"), ("v3", "bits"), ("v0", "full")])
+def test_host_pipeline_matches_oracle(lmz, oracle_mod, variant, obs_mode):
+    """lmz_step_host_async / _wait: every output of every step (obs included) lands in pinned host memory one
+    submit later and equals the oracle's; the full f32 observation stays on the device (with_obs=False)."""
+    N, T = 4099, 40
+    ov = oracle_mod.V0 if variant == "v0" else oracle_mod.V3
+    ora = oracle_mod.OracleVec(ov, N, seed=21, autoreset=True)
+    env = lmz.LmazeVecCuda(N, variant, seed=21, autoreset=True, obs_mode=obs_mode)
+    env.reset(); ora.reset(want_obs=False)
+    if obs_mode == "full":
+        with pytest.raises(ValueError):
+            env.host_pipeline()
+    pipe = env.host_pipeline(with_obs=obs_mode != "full")
+    gen = torch.Generator().manual_seed(4)
+    acts = [torch.randint(0, 5, (N,), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(T)]
+    refs = []
+
+    def check(res, ref):
+        o_ref, r_ref, d_ref = ref
+        assert np.array_equal(res.reward.numpy().view(np.uint32), r_ref.view(np.uint32))
+        assert np.array_equal(res.done.numpy(), d_ref)
+        if res.obs is not None:
+            assert torch.equal(env.expand(res.obs.cuda()).cpu(), torch.from_numpy(o_ref))
+    for t in range(T):
+        refs.append(ora.step(acts[t].numpy().astype(np.int64)))
+        res = pipe.submit(acts[t])
+        assert (res is None) == (t == 0)
+        if res is not None:
+            check(res, refs[t - 1])
+    check(pipe.drain(), refs[-1])
+    assert pipe.drain() is None
+    # the pipeline can be resumed after a drain, and the serial host call still works beside it
+    refs.append(ora.step(acts[0].numpy().astype(np.int64)))
+    assert pipe.submit(acts[0]) is None
+    check(pipe.drain(), refs[-1])
+    r = torch.empty(N, dtype=torch.float32).pin_memory(); d = torch.empty(N, dtype=torch.uint8).pin_memory()
+    o_ref, r_ref, d_ref = ora.step(acts[1].numpy().astype(np.int64))
+    env.step_host(acts[1], r, d)
+    assert np.array_equal(r.numpy().view(np.uint32), r_ref.view(np.uint32)) and np.array_equal(d.numpy(), d_ref)
+    assert torch.equal(env.expand(env.obs).cpu(), torch.from_numpy(o_ref))
+    assert env.stats()["steps"] == (T + 2) * N
+    env.close()
