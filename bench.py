@@ -491,7 +491,7 @@ def run_ours(args):
     checksum = float(r_host.sum())               # the host really consumes the result
 
     stats = env.stats_allreduce(check_errors=not hier) if world > 1 else env.stats(check_errors=not hier)   # v5: random actors hit the reference's IndexError rows
-    launches_total = env.launch_count
+    steps_launched = args.warmup + args.steps + max(3, args.warmup) + args.steps
     env.close()
     del env, ring, goal_ring
     torch.cuda.empty_cache()
@@ -542,10 +542,10 @@ def run_ours(args):
         "episode_stats": stats,
         "checks": checks,
     }
-    checks["nccl_steps_sum"] = {"steps": stats["steps"], "expected": world * N * (launches_total // launches_per_step)
-                                if not hier else None,
+    checks["nccl_steps_sum"] = {"steps": stats["steps"], "expected": world * N * steps_launched if not hier else None,
                                 "what": "sum over ranks of the device step counters (one all_reduce(int64[8])) vs "
-                                        "world x envs x step launches of the whole run"}
+                                        "world x envs x step calls of the whole run (%d: warm-up + timed, device and "
+                                        "host-buffer loops)" % steps_launched}
     if not hier:
         checks["nccl_steps_sum"]["ok"] = checks["nccl_steps_sum"]["steps"] == checks["nccl_steps_sum"]["expected"]
     if hier_note:
@@ -641,7 +641,7 @@ def side_measurements(rk, lmz, args, seed):
     out = {}
     # (0) what a trivial streaming-write kernel gets on this GPU right now (8 GiB torch fill_), rank 0's GPU
     scratch = torch.empty(2 << 30, dtype=torch.float32, device=dev)
-    ms = rk.timed_ms(lambda i: scratch.fill_(1.0), 5, 1)
+    ms = rk.timed_ms(lambda i: scratch.fill_(1.0), 20, 20)
     out["pure_write_fill_gbs"] = {"value": scratch.numel() * 4 / (ms * 1e-3) / 1e9,
                                   "what": "torch.fill_ over 8 GiB on every rank at once (slowest rank): the write-only "
                                           "ceiling; MEASURED_PEAKS hbm_gbs is a read+write copy, so a pure-write kernel "
