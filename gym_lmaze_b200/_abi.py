@@ -33,7 +33,7 @@ EXPORTS = (
     "lmz_set_visit_dl", "lmz_stats", "lmz_stats_reset", "lmz_launch_count",
     "lmz_state_cols", "lmz_local_obs_shape", "lmz_bind_local", "lmz_bind_local_dl", "lmz_planner_step",
     "lmz_planner_step_dl", "lmz_safe_goal", "lmz_safe_goal_dl", "lmz_planner_step_auto", "lmz_planner_step_auto_dl",
-    "lmz_hier_step_host",
+    "lmz_hier_step_host", "lmz_hier_rollout", "lmz_hier_rollout_dl",
 )
 
 
@@ -121,6 +121,8 @@ def load():
     L.lmz_planner_step_auto.argtypes = [vp, vp, i32, vp]
     L.lmz_planner_step_auto_dl.argtypes = [vp, vp, vp]
     L.lmz_hier_step_host.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.lmz_hier_rollout.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.lmz_hier_rollout_dl.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.lmz_safe_goal.argtypes = [vp, vp, i32, vp, vp, vp]
     L.lmz_safe_goal_dl.argtypes = [vp, vp, vp, vp, vp]
     L.lmz_stats.argtypes = [vp, ctypes.POINTER(i64 * NUM_STATS), ctypes.POINTER(i64), vp]

@@ -17,6 +17,7 @@
 #include "../../include/lmaze_b200.h"
 #include "lmz_kernels.cuh"
 #include "lmz_fov.cuh"
+#include "lmz_fov_rollout.cuh"
 
 namespace {
 
@@ -389,6 +390,11 @@ int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   }
 }
 
+// default CTA size of the foveal render kernel per variant (1 producer warp + the rendering warps)
+#ifndef LMZ_FOV_THREADS
+#define LMZ_FOV_THREADS(id) ((id) == 2 ? 128 : (id) == 4 ? 128 : 160)
+#endif
+
 template <class W, int THREADS>
 int launch_fov_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   auto kern = lmz::lmz_env_fov_kernel<W, THREADS>;
@@ -418,19 +424,20 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
   // CTA size and CTAs per SM (tools/fov_sweep2.py).  FEWER storing warps reach a HIGHER write bandwidth on a B200:
   // v2 with ONE 128-thread CTA per SM (1 producer warp + 3 rendering warps) streams 7.47 TB/s, the pure-write
-  // ceiling, against 7.0 TB/s with 1024 threads and 6.3 TB/s with two 128-thread CTAs per SM; v4 is best with 224
-  // threads (4 producer warps for the visit layers + 3 rendering warps, 6.5 TB/s), v5 (two tensors per env) with
-  // 256 (4 + 4 warps, 6.4 TB/s; 6.0 TB/s with 512 threads).
-  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : (W::ID == 2 ? 128 : W::ID == 4 ? 224 : 256);
+  // ceiling, against 7.0 TB/s with 1024 threads and 6.3 TB/s with two 128-thread CTAs per SM.  v4 / v5 run the
+  // same organisation since round 2 (the scaled visit layer needs no producer warps of its own).
+  const int t = h->cfg.tune[0] ? h->cfg.tune[0] : LMZ_FOV_THREADS(W::ID);
   switch (t) {
-    case 128: if (W::NVIS == 0) return launch_fov_t<W, (W::NVIS == 0 ? 128 : 512)>(h, p, s); break;   // v2 only: the visit
-    case 224: return launch_fov_t<W, 224>(h, p, s);                                  // variants keep 128 producer threads
+    case 128: return launch_fov_t<W, 128>(h, p, s);
+    case 160: return launch_fov_t<W, 160>(h, p, s);
+    case 192: return launch_fov_t<W, 192>(h, p, s);
+    case 224: return launch_fov_t<W, 224>(h, p, s);
     case 256: return launch_fov_t<W, 256>(h, p, s);
     case 512: return launch_fov_t<W, 512>(h, p, s);
     case 1024: return launch_fov_t<W, 1024>(h, p, s);
     default: break;
   }
-  return fail(LMZ_ERR_INVALID, "foveal kernels are built for tune[0] = 128 (v2 only), 224, 256, 512 or 1024 threads (got %d)", t);
+  return fail(LMZ_ERR_INVALID, "foveal kernels are built for tune[0] = 128, 160, 192, 224, 256, 512 or 1024 threads (got %d)", t);
 }
 
 // compact observations / nothing to render (foveal variants): warp-granular kernel, several small CTAs per SM
@@ -440,10 +447,11 @@ int launch_fov_small(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (W::HAS_LOC && !h->local_bound)
     return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
   auto kern = lmz::lmz_fov_small_kernel<W, THREADS>;
-  constexpr int SMEM = (int)(W::BLOB_BYTES - W::ROWBITS_OFF);
+  constexpr int SMEM = (int)lmz::FovSmall<W>::smem_bytes(THREADS);      // tables + one 32-env tile of rows per warp
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
   if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, SMEM));
     if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal compact kernel does not fit on an SM");
     configured_dev = h->cfg.device;
@@ -511,6 +519,28 @@ int launch_rollout_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   lmz::lmz_rollout_kernel<V, THREADS><<<(unsigned)blocks, THREADS, 0, s>>>(p);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return LMZ_OK;
+}
+
+template <class W>
+int launch_fov_rollout(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  constexpr int THREADS = 128;
+  constexpr int SMEM = (int)(W::BLOB_BYTES - W::ROWBITS_OFF);
+  auto kern = lmz::lmz_fov_rollout_kernel<W, THREADS>;
+  static thread_local int configured_dev = -1;
+  static thread_local int ctas_per_sm = 1;
+  if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, SMEM));
+    if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal rollout kernel does not fit on an SM");
+    configured_dev = h->cfg.device;
+  }
+  int64_t blocks = (p.n + THREADS - 1) / THREADS;
+  const int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, THREADS, SMEM, s>>>(p);
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
@@ -789,7 +819,7 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     uint32_t packed = (cfg->variant == LMZ_V0) ? lmz::V0::pack(r) : lmz::V3::pack(r);
     if (foveal) {                          // maze 1, ball on 'S', goal on 'X', no previous action
       lmz::V2Regs v;
-      v.L = 1; v.x = v.px = 4; v.y = v.py = 4; v.gx = 8; v.gy = 8; v.a = -1; v.step = 0;
+      v.L = 1; v.x = v.px = 4; v.y = v.py = 4; v.gx = 8; v.gy = 8; v.a = -1; v.step = 0; v.vt = 0;
       uint32_t aux;
       lmz::v2_pack(v, packed, aux);
       std::vector<uint32_t> auxv(n < (1u << 20) ? n : (1u << 20), aux);
@@ -801,7 +831,7 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
     if (hier) {                            // maze 1, everything on 'S', goal on 'X' (the state reset() would leave there)
       lmz::V5Regs v;
       v.L = 1; v.x = v.x1 = v.fx1 = v.fgx = v.lx = 4; v.y = v.y1 = v.fy1 = v.fgy = v.ly = 4; v.gx = 8; v.gy = 8;
-      v.fga = 12; v.step = 0; v.fstep = 0; v.ld = 0; v.gd = 0;
+      v.fga = 12; v.step = 0; v.fstep = 0; v.ld = 0; v.gd = 0; v.vt = 0;
       uint32_t w1, w2;
       lmz::v5_pack(v, packed, w1, w2);
       std::vector<uint32_t> tmp(n < (1u << 20) ? n : (1u << 20), w1);
@@ -1085,8 +1115,8 @@ static int rollout_impl(lmz_env *h, int32_t T, const void *actions, int32_t acti
                         uint8_t *reward_codes, uint8_t *dones, void *stream) {
   if (int rc = check_handle(h)) return rc;
   if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
-  if (h->cfg.variant == LMZ_V2 || h->cfg.variant == LMZ_V4 || h->cfg.variant == LMZ_V5)
-    return fail(LMZ_ERR_UNSUPPORTED, "lmz_rollout is not built for lmaze-v2/v4/v5 yet");
+  if (h->cfg.variant == LMZ_V5)
+    return fail(LMZ_ERR_UNSUPPORTED, "lmaze-v5/v6 roll out through lmz_hier_rollout (planner goals + actor actions)");
   if (!dones) return fail(LMZ_ERR_INVALID, "rewards/dones must not be NULL");
   if (actions && (action_dtype < LMZ_ACT_U8 || action_dtype > LMZ_ACT_I64))
     return fail(LMZ_ERR_INVALID, "unknown action dtype %d", action_dtype);
@@ -1094,8 +1124,11 @@ static int rollout_impl(lmz_env *h, int32_t T, const void *actions, int32_t acti
   lmz::KParams p = base_params(h);
   p.mode = lmz::MODE_STEP; p.actions = actions; p.action_dtype = action_dtype;
   p.reward = rewards; p.reward_code = reward_codes; p.done = dones; p.obs = nullptr; p.T = T; p.t0 = h->rollout_t;
-  int rc = (h->cfg.variant == LMZ_V0) ? launch_rollout_v<lmz::V0>(h, p, static_cast<cudaStream_t>(stream))
-                                      : launch_rollout_v<lmz::V3>(h, p, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = h->cfg.variant == LMZ_V0   ? launch_rollout_v<lmz::V0>(h, p, s)
+           : h->cfg.variant == LMZ_V3 ? launch_rollout_v<lmz::V3>(h, p, s)
+           : h->cfg.variant == LMZ_V2 ? launch_fov_rollout<lmz::V2>(h, p, s)
+                                      : launch_fov_rollout<lmz::V4>(h, p, s);
   if (rc == LMZ_OK) {
     h->rollout_t += (uint64_t)T;
     h->obs_synced = false;               // every ball / goal moved and nothing was rendered (incremental render)
@@ -1183,9 +1216,14 @@ static int visit_xfer(lmz_env *h, float *buf, int set, void *stream) {
     return fail(LMZ_ERR_UNSUPPORTED, "only lmaze-v4/v5/v6 have a visit layer");
   if (!buf) return fail(LMZ_ERR_INVALID, "visit buffer is NULL");
   DeviceGuard guard(h->cfg.device);
-  const size_t bytes = (size_t)h->cfg.num_envs * 324 * sizeof(float);
-  LMZ_CUDA(cudaMemcpyAsync(set ? (void *)h->visit : (void *)buf, set ? (const void *)buf : (const void *)h->visit, bytes,
-                           cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  // the layer is stored scaled by 2^T per env (lmz_v2.cuh, "visit layer"); it crosses the ABI as true values
+  const int64_t n = h->cfg.num_envs;
+  const bool v5 = h->cfg.variant == LMZ_V5;
+  const unsigned blocks = (unsigned)((n * 324 + 255) / 256);
+  lmz::lmz_visit_xfer_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n, h->visit, v5 ? h->state : h->goal_count, v5 ? 25 : 16, buf, set);
+  LMZ_CUDA(cudaGetLastError());
+  h->launches += 1;
   return LMZ_OK;
 }
 int lmz_get_visit(lmz_env *h, float *out, void *stream) { return visit_xfer(h, out, 0, stream); }
@@ -1299,6 +1337,54 @@ int lmz_hier_step_host(lmz_env *h, const void *goals_host, const void *actions_h
   LMZ_CUDA(cudaMemcpyAsync(local_done_host, h->done2, n, cudaMemcpyDeviceToHost, s));
   LMZ_CUDA(cudaStreamSynchronize(s));
   return LMZ_OK;
+}
+
+int lmz_hier_rollout(lmz_env *h, int32_t T, const void *goals, const void *actions, int32_t dtype, float *global_rewards,
+                     float *local_rewards, uint8_t *global_dones, uint8_t *local_dones, void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.variant != LMZ_V5) return fail(LMZ_ERR_UNSUPPORTED, "lmz_hier_rollout: only lmaze-v5/v6");
+  if (T < 1) return fail(LMZ_ERR_INVALID, "T must be >= 1 (got %d)", T);
+  if (!global_rewards || !local_rewards || !global_dones || !local_dones)
+    return fail(LMZ_ERR_INVALID, "reward / done buffers must not be NULL");
+  if ((goals == nullptr) != (actions == nullptr))
+    return fail(LMZ_ERR_INVALID, "goals and actions must both be given, or both NULL (device-side random goals and actions)");
+  if (actions && (dtype < LMZ_ACT_U8 || dtype > LMZ_ACT_I64)) return fail(LMZ_ERR_INVALID, "unknown dtype %d", dtype);
+  DeviceGuard guard(h->cfg.device);
+  lmz::KParams p = base_params(h);
+  p.mode = lmz::MODE_STEP; p.actions = actions; p.goals = goals; p.action_dtype = dtype;
+  p.reward = global_rewards; p.reward2 = local_rewards; p.done = global_dones; p.done2 = local_dones;
+  p.obs = nullptr; p.obs2 = nullptr; p.loc_err = nullptr; p.T = T; p.t0 = h->rollout_t;
+  const int rc = launch_fov_rollout<lmz::V5>(h, p, static_cast<cudaStream_t>(stream));
+  if (rc == LMZ_OK) h->rollout_t += (uint64_t)T;
+  return rc;
+}
+
+int lmz_hier_rollout_dl(lmz_env *h, int32_t T, DLManagedTensor *goals, DLManagedTensor *actions, DLManagedTensor *global_rewards,
+                        DLManagedTensor *local_rewards, DLManagedTensor *global_dones, DLManagedTensor *local_dones,
+                        void *stream) {
+  if (int rc = check_handle(h)) return rc;
+  const int64_t n = h->cfg.num_envs;
+  void *pg = nullptr, *pa = nullptr, *pr = nullptr, *pr2 = nullptr, *pd = nullptr, *pd2 = nullptr;
+  int ad = 0, gd = 0;
+  if (actions) {
+    Want wa{"actions", 255, 0, 2, {T, n, 0, 0}, false, 1};
+    if (int rc = check_dl(h, actions, wa, &pa, &ad)) return rc;
+  }
+  if (goals) {
+    Want wg{"goals", 255, 0, 2, {T, n, 0, 0}, false, 1};
+    if (int rc = check_dl(h, goals, wg, &pg, &gd)) return rc;
+    if (actions && gd != ad) return fail(LMZ_ERR_INVALID, "goals and actions must have the same dtype");
+  }
+  Want wr{"global_rewards", kDLFloat, 32, 2, {T, n, 0, 0}, false, 4};
+  if (int rc = check_dl(h, global_rewards, wr, &pr, nullptr)) return rc;
+  Want wr2{"local_rewards", kDLFloat, 32, 2, {T, n, 0, 0}, false, 4};
+  if (int rc = check_dl(h, local_rewards, wr2, &pr2, nullptr)) return rc;
+  Want wd{"global_dones", kDLUInt, 8, 2, {T, n, 0, 0}, false, 1};
+  if (int rc = check_dl(h, global_dones, wd, &pd, nullptr)) return rc;
+  Want wd2{"local_dones", kDLUInt, 8, 2, {T, n, 0, 0}, false, 1};
+  if (int rc = check_dl(h, local_dones, wd2, &pd2, nullptr)) return rc;
+  return lmz_hier_rollout(h, T, pg, pa, ad, static_cast<float *>(pr), static_cast<float *>(pr2), static_cast<uint8_t *>(pd),
+                          static_cast<uint8_t *>(pd2), stream);
 }
 
 int lmz_planner_step_dl(lmz_env *h, DLManagedTensor *goals, DLManagedTensor *mask, void *stream) {

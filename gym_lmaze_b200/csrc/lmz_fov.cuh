@@ -16,17 +16,17 @@
 // Warp 0 is a dedicated producer: it runs the tile's 32 transitions (one env per lane, state in registers) and
 // expands each env's 25-bit planes into float planes in shared memory, one tile ahead of the rendering warps and
 // one tile ahead of its OWN loads (next tile's index, state words, actions).  For the variants with a float visit
-// layer (v4, v5) warps 0-3 are producers: the tile's 32 x 324 visit floats arrive by ONE bulk async (TMA) load,
-// the producers update them out of shared memory (coalesced write-back) and drop the two 5x5 visit crops into the
-// same planes.  Everything is double buffered; one __syncthreads per tile.  FEWER rendering warps reach a HIGHER
-// write bandwidth (tools/fov_sweep2.py): v2 runs 1 + 3 warps per SM (7.47 TB/s, the pure-write ceiling; 7.0 TB/s
-// with 32 warps), v4 4 + 3, v5 4 + 4.
+// layer (v4, v5) the same producer warp keeps the layer up to date: the layer is stored SCALED (lmz_v2.cuh, "visit
+// layer"), so an averaging step touches only the 25 cells of the window around the ball instead of all 324 -- one
+// env per lane, 50 independent loads (the window and the previous window), 25 stores -- and the two 5x5 visit crops
+// go into the same value planes.  Everything is double buffered; one __syncthreads per tile.  FEWER rendering warps
+// reach a HIGHER write bandwidth (tools/fov_sweep2.py): 1 producer + 3 rendering warps per SM for v2.
 #pragma once
 #include "lmz_v2.cuh"
 #include "lmz_v5.cuh"
 
 #ifndef LMZ_VISIT_PROD
-#define LMZ_VISIT_PROD 128
+#define LMZ_VISIT_PROD 32     // v4 / v5: producer threads (round 1 used 128 for a full-layer pass; the scaled layer needs one warp)
 #endif
 #ifndef LMZ_V2_PROD
 #define LMZ_V2_PROD 32    // v2: one dedicated producer warp (0: warp 0 produces, then renders with the others)
@@ -44,6 +44,124 @@ __device__ __forceinline__ float visit_average(float v, bool in_window) {
   return in_window ? __fmul_rn(__fadd_rn(v, 1.0f), 0.5f) : __fmul_rn(v, 0.5f);
 }
 
+// ---- the visit layer of one 32-env tile, one env per lane (whole warp must call) --------------------------------
+// info / vinfo: the lane's FovLane words; plane_cur / plane_prev: the lane's two 25-float visit planes in shared
+// memory (crop at the ball / crop at the previous window, both showing the layer AFTER this call's update -- the
+// reference's retStatelast is a view of the live state, lmaze_env_v4.py:122,258-259), written when want_planes.
+// Two halves, so that a kernel can put other work (a whole tile time in the render kernel) between the loads
+// and their use:  visit_issue  does the rare whole-layer operations (reset: 324 cells rewritten; direct mode: the
+// literal full pass) warp-cooperatively, env by env with 128-bit accesses, then starts every lane's 50 window loads;
+// visit_finish  adds 2^T to the window (s' = RN(s + 2^T)), stores it and writes the two planes.
+struct VisitFetch {
+  float cur[25], prv[25];
+};
+
+template <class W>
+__device__ __forceinline__ void visit_issue(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                            uint32_t vinfo, bool want_planes, VisitFetch &f) {
+  constexpr int GG = W::G * W::G;
+  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
+  const int tpre = (vinfo >> 3) & 127;
+  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+  unsigned full = __ballot_sync(0xffffffffu, op == VOP_RESET || op == VOP_FULL);
+  if (full) {
+    while (full) {
+      const int src = __ffs(full) - 1;
+      full &= full - 1;
+      const uint32_t sop = __shfl_sync(0xffffffffu, op, src);
+      const int sx = __shfl_sync(0xffffffffu, bx, src), sy = __shfl_sync(0xffffffffu, by, src);
+      const float down = visit_scale_down(__shfl_sync(0xffffffffu, tpre, src));
+      float4 *row = reinterpret_cast<float4 *>(p.visit + (e0 + src) * GG);        // 1,296 B per env: 16-byte aligned
+      for (int c4 = lane; c4 < GG / 4; c4 += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sop == VOP_FULL) v = __ldcg(row + c4);
+        float *q = reinterpret_cast<float *>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cell = 4 * c4 + k, x = cell / W::G, y = cell - x * W::G;
+          const bool in_cur = (unsigned)(x - sx + 2) < 5u && (unsigned)(y - sy + 2) < 5u;
+          q[k] = (sop == VOP_FULL) ? visit_average(__fmul_rn(q[k], down), in_cur) : W::visit_reset_stored(in_cur);
+        }
+        __stcg(row + c4, v);
+      }
+    }
+    __syncwarp();                                         // the cooperative stores are visible to the owning lane
+  }
+  if (!valid || op == VOP_RESET || (op != VOP_AVG && !want_planes)) return;
+  const float *vis = p.visit + (e0 + lane) * GG;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) f.cur[k] = __ldcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5));
+  if (want_planes) {
+#pragma unroll
+    for (int k = 0; k < 25; ++k) f.prv[k] = __ldcg(vis + (px - 2 + k / 5) * W::G + (py - 2 + k % 5));
+  }
+}
+
+template <class W>
+__device__ __forceinline__ void visit_finish(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                             uint32_t vinfo, bool want_planes, VisitFetch &f, float *plane_cur,
+                                             float *plane_prev) {
+  constexpr int GG = W::G * W::G;
+  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
+  const int tpre = (vinfo >> 3) & 127, tpost = (vinfo >> 10) & 127;
+  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+  if (!valid || (op != VOP_AVG && !want_planes)) return;
+  if (op == VOP_RESET) {                                  // the layer was just rewritten: values known
+#pragma unroll
+    for (int k = 0; k < 25; ++k) {
+      const int ax = px - 2 + k / 5, ay = py - 2 + k % 5;
+      const bool in_cur = (unsigned)(ax - bx + 2) < 5u && (unsigned)(ay - by + 2) < 5u;
+      plane_cur[k] = W::visit_reset(true);
+      plane_prev[k] = W::visit_reset(in_cur);
+    }
+    return;
+  }
+  if (op == VOP_AVG) {                                    // s' = RN(s + 2^T) on the window, nothing else changes
+    float *vis = p.visit + (e0 + lane) * GG;
+    const float add = __int_as_float((127 + tpre) << 23);
+#pragma unroll
+    for (int k = 0; k < 25; ++k) {
+      f.cur[k] = __fadd_rn(f.cur[k], add);
+      __stcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5), f.cur[k]);
+    }
+  }
+  if (!want_planes) return;
+  const float down = visit_scale_down(tpost);
+#pragma unroll
+  for (int k = 0; k < 25; ++k) plane_cur[k] = __fmul_rn(f.cur[k], down);
+  const int ox = px - bx, oy = py - by;                   // previous window relative to the current one
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    const int dx = ox + k / 5, dy = oy + k % 5;           // cell k of the previous window, in current-window coordinates
+    const bool in_cur = (unsigned)dx < 5u && (unsigned)dy < 5u;
+    plane_prev[k] = in_cur ? plane_cur[in_cur ? dx * 5 + dy : 0] : __fmul_rn(f.prv[k], down);
+  }
+}
+
+template <class W>
+__device__ __forceinline__ void visit_warp(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                           uint32_t vinfo, bool want_planes, float *plane_cur, float *plane_prev) {
+  VisitFetch f;
+  visit_issue<W>(p, e0, lane, valid, info, vinfo, want_planes, f);
+  visit_finish<W>(p, e0, lane, valid, info, vinfo, want_planes, f, plane_cur, plane_prev);
+}
+
+// lmz_get_visit / lmz_set_visit: the layer crosses the ABI as TRUE values.  get: v = s * 2^-T.  set: the values are
+// stored as given and the env goes to direct mode until its next reset (nothing is known about how small the
+// supplied values are, so the "everything stays normal" bound of the scaled form cannot be assumed).
+// tword: the state word that carries the env's T field (v4: aux word, bits 16-22; v5: w0, bits 25-31).
+__global__ void lmz_visit_xfer_kernel(int64_t n, float *visit, uint32_t *tword, int shift, float *io, int set) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * 324) return;
+  const int64_t e = idx / 324;
+  if (set) {
+    visit[idx] = io[idx];
+    if (idx - e * 324 == 0) tword[e] = (tword[e] & ~(127u << shift)) | ((uint32_t)VT_DIRECT << shift);
+  } else {
+    io[idx] = __fmul_rn(visit[idx], visit_scale_down((int)((tword[e] >> shift) & 127u)));
+  }
+}
+
 template <int ID, int C>
 __device__ __forceinline__ FovLane<5> fov_lane(const Fov<ID, C> *, const KParams &p, int64_t e,
                                                const FovTables<Fov<ID, C>> &t, const unsigned char *, const FovPre &pre) {
@@ -58,8 +176,6 @@ template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ __align__(8) uint64_t vbar[2];
-  __shared__ uint32_t s_info[2][32];
   __shared__ uint32_t s_flags[2][2];         // [buf][0 obs, 1 local obs]: bit l = env l of the tile is written
   __shared__ long long s_tile[2];
   constexpr int PROD = (W::NVIS > 0) ? LMZ_VISIT_PROD : LMZ_V2_PROD;   // threads that never render
@@ -67,31 +183,21 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   static_assert(CTHREADS >= 32, "need at least one rendering warp");
   static_assert((uint32_t)CTHREADS < W::OBS_FLOATS, "index stepping assumes fewer threads than entries");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (W::NVIS > 0 && tid == 0) { mbar_init(&vbar[0], 1); mbar_init(&vbar[1], 1); }   // fenced + synced inside stage_blob
   stage_blob<W>(smem, &bar, p.blob);
   const FovTables<W> t(smem);
   float *vals = reinterpret_cast<float *>(smem + W::BLOB_BYTES);          // [2][32][NSLOT][25]
-  float *vbuf = vals + 2 * 32 * W::VALS;                                  // [2][32][324]: TMA landing zone of the visit layers
-  uint32_t vphase = 0;                                                    // bit b: parity the next wait on vbar[b] expects
   const int64_t tiles = p.tile_end;
   const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
   WarpStats ws;
 
   // Warp 0 runs ONE TILE AHEAD of its own loads: when it turns to a tile, the tile's index was grabbed and its
-  // state words / actions (and, for the visit variants, the bulk load of its 32 visit layers) were issued a
-  // whole tile time earlier, so no DRAM or atomic round trip -- several microseconds each under a saturated
-  // write stream -- sits between two tiles of the producer.
+  // state words / actions were requested a whole tile time earlier, so no atomic round trip -- several
+  // microseconds under a saturated write stream -- sits between two tiles of the producer.  (The visit
+  // variants add ONE dependent round trip per tile: the window loads need the positions the transitions produce.)
   int64_t tl_next = 0;                       // warp 0: the tile produce() turns to next
   FovPre pre_next;                           // ... and its preloaded words (this lane's env)
   pre_next.w0 = pre_next.w1 = pre_next.w2 = 0u; pre_next.act = 0;
-  auto prefetch = [&](int64_t tl, int vb) {  // warp 0: start everything tile `tl` will need
-    if (W::NVIS > 0 && need_visit && lane == 0 && tl < tiles) {
-      // the tile's 32 visit layers are 41,472 contiguous bytes: ONE bulk async (TMA) load
-      const int64_t e0 = tl * 32;
-      const uint32_t bytes = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G * 4));
-      mbar_expect_tx(&vbar[vb], bytes);
-      bulk_g2s(vbuf + vb * (32 * W::G * W::G), p.visit + e0 * (W::G * W::G), bytes, &vbar[vb]);
-    }
+  auto prefetch = [&](int64_t tl) {          // warp 0: start everything tile `tl` will need
     const int64_t e = tl * 32 + lane;
     if (tl < tiles && e < p.n) pre_next = fov_preload<W>(p, e);
     tl_next = tl;
@@ -101,7 +207,18 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
     return __shfl_sync(0xffffffffu, tl, 0);
   };
-  auto produce = [&](int buf) {              // warp 0 only
+  // The producer works in two stages, one tile apart (the visit variants): stage A runs a tile's transitions and
+  // STARTS its visit-window loads; stage B -- a whole tile time later, when the loads have long landed -- finishes
+  // the visit update and fills the tile's value planes.  Without the split the dependent DRAM round trip of the
+  // window loads sat in the producer's critical path and the renderers waited for it (v4: 174 M env-steps/s against
+  // 218 M with the visit layer switched off; tools/fov_sweep2.py).
+  FovLane<W::NBIT> pv;                       // warp 0: stage A's results for the tile stage B completes next
+  pv.o.st = 0; pv.o.st_old = 0; pv.o.render = false; pv.o.done = false; pv.o.cls = -1; pv.o.eplen = 0;
+  pv.info = 0; pv.vinfo = 0; pv.rfov = false; pv.rloc = false;
+  VisitFetch vf;
+  int64_t ptile = 0;
+  bool pvalid = false;
+  auto stage_a = [&]() {                     // warp 0 only
     const int64_t tl = tl_next;
     const FovPre pre = pre_next;
     const int64_t tl_after = grab();         // in flight while this tile's transitions run
@@ -109,11 +226,24 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     const bool valid = tl < tiles && e < p.n;
     FovLane<W::NBIT> v;
     v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
-    v.rfov = false; v.rloc = false;
+    v.vinfo = 0; v.rfov = false; v.rloc = false;
     if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, smem, pre);
     if (p.mode == MODE_STEP) ws.add(valid, v.o);
+#ifndef LMZ_DEBUG_NO_VISIT                   // (tuning builds only: how fast is the kernel without the visit layer?)
+    if (W::NVIS > 0 && need_visit) visit_issue<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf);
+#endif
+    pv = v; ptile = tl; pvalid = valid;
+    prefetch(tl_after);
+  };
+  auto stage_b = [&](int buf) {              // warp 0 only
+    const FovLane<W::NBIT> &v = pv;
+    const bool valid = pvalid;
+    float *mv = vals + (buf * 32 + lane) * W::VALS;
+#ifndef LMZ_DEBUG_NO_VISIT
+    if (W::NVIS > 0 && need_visit)           // window update of the scaled layer + the two 5x5 visit crops
+      visit_finish<W>(p, ptile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf, mv + W::VIS_SLOT0 * 25, mv + W::VIS_SLOT1 * 25);
+#endif
     if (valid && (v.rfov || v.rloc)) {       // 25-bit planes -> float planes (lane stride VALS is odd: no bank conflicts)
-      float *mv = vals + (buf * 32 + lane) * W::VALS;
 #pragma unroll
       for (int b = 0; b < W::NBIT; ++b) {
         const uint32_t m = v.mask[b];
@@ -122,55 +252,28 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
         for (int c = 0; c < 25; ++c) pl[c] = ((m >> c) & 1u) ? 1.0f : 0.0f;
       }
     }
-    s_info[buf][lane] = valid ? v.info : 0u;
     const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
     const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
-    if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = tl; }
-    prefetch(tl_after, buf ^ 1);             // vbuf[buf ^ 1] is free: its tile's visit pass ended before the last barrier
+    if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = ptile; }
   };
-  // visit layers of one tile's 32 envs: 32 x 324 consecutive floats, coalesced pass by the PROD producer
-  // threads: state[2] = (state[2] + visitMap) / 2 in float64, stored as float32
-  // (lmaze_env_v4.py:116-119,211-214; lmaze_env_v5.py:308-312)
-  auto visit_pass = [&](int buf) {
-    const int64_t tile = s_tile[buf];
-    if (tile >= tiles || !need_visit) return;
-    const int64_t e0 = tile * 32;
-    const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
-    float *vis = p.visit + e0 * (W::G * W::G);
-    float *tv = vals + buf * 32 * W::VALS;
-    const float *vb = vbuf + buf * (32 * W::G * W::G);
-    mbar_wait(&vbar[buf], (vphase >> buf) & 1u);
-    vphase ^= 1u << buf;
-    constexpr uint32_t NP = PROD > 0 ? PROD : 1;
-#pragma unroll 4
-    for (uint32_t idx = tid; idx < cells; idx += NP) {
-      const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-      const int x = cell / W::G, y = cell - x * W::G;
-      const uint32_t info = s_info[buf][env];
-      const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-      const uint32_t op = (info >> 20) & 3u;
-      const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-      const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-      float v = vb[idx];
-      if (op == 1) v = visit_average(v, in_cur);
-      else if (op == 2) v = W::visit_reset(in_cur);
-      if (op) __stcs(vis + idx, v);
-      if (in_cur) tv[env * W::VALS + W::VIS_SLOT0 * 25 + dx * 5 + dy] = v;
-      if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) tv[env * W::VALS + W::VIS_SLOT1 * 25 + qx * 5 + qy] = v;
-    }
+  // v2 has nothing to wait for: both stages back to back (one tile ahead of the renderers, as in round 1)
+  auto produce = [&](int buf) {
+    if (W::NVIS > 0) { stage_b(buf); stage_a(); }
+    else { stage_a(); stage_b(buf); }
   };
-  auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(PROD > 0 ? PROD : 32) : "memory"); };
   auto pick = [](uint32_t en, const float *gv) -> uint4 { return f4_pick(en, gv); };
 
-  if (warp == 0) { prefetch(grab(), 0); produce(0); }
-  if (W::NVIS > 0 && tid < PROD) { producers_sync(); visit_pass(0); }
+  if (warp == 0) {
+    prefetch(grab());
+    if (W::NVIS > 0) stage_a();              // the pipeline's first tile
+    produce(0);
+  }
   for (int buf = 0;; buf ^= 1) {
     __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
     const int64_t tile = s_tile[buf];
     if (tile >= tiles) break;
     if (PROD > 0 && tid < PROD) {
       if (warp == 0) produce(buf ^ 1);
-      if (W::NVIS > 0) { producers_sync(); visit_pass(buf ^ 1); }
       continue;
     }
     if (PROD == 0 && warp == 0) produce(buf ^ 1);
@@ -245,31 +348,42 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
 // 700 + 400 bytes per env instead of 24,500 / 34,300 / 53,900; the reference image is exactly
 // repeat_interleave(compact, 7) on both axes.  The same kernel serves launches with no observation bound.  The work
 // per tile is small, so the organisation is warp-granular like lmz_env_compact_kernel: every warp grabs its own
-// tiles (the next tile's index and state words requested one tile ahead), runs the 32 transitions, makes the
-// coalesced pass over the tile's visit layers itself (v4 / v5) and stores the tile's planes as one flat run of
-// coalesced 32-bit words.
+// tiles (the next tile's index and state words requested one tile ahead), runs the 32 transitions, updates the
+// window of each env's scaled visit layer itself (v4 / v5, visit_warp), and ASSEMBLES the tile's 32 rows in shared
+// memory exactly as they lie in the tensor (lane l expands env l's 25-bit planes into floats, the visit crops land
+// in their planes directly).  The tile's rows are one contiguous, 16-byte aligned run of the tensor, so the copy
+// out is a flat LDS.128 -> st.global.cs.v4 loop with no per-float indexing at all.  (Round 1 looked every float up
+// through (plane, cell) index arithmetic and was math-pipe bound at 74 % issue-slot use, 4.7 TB/s on v2.)
+template <class W>
+struct FovSmall {
+  static constexpr uint32_t STAGE_OFF = W::ROWBITS_OFF;                 // the render tables are not needed here
+  static constexpr uint32_t TAB_BYTES = (W::BLOB_BYTES - STAGE_OFF + 15u) & ~15u;
+  static constexpr uint32_t PER = W::C * 25;                            // floats per env row (the obs channels are slots 0..C-1)
+  static constexpr uint32_t PERL = 4 * 25;                              // v5 local obs row
+  static constexpr uint32_t smem_bytes(int threads) { return TAB_BYTES + (threads / 32) * 32 * PER * 4; }
+};
+
 template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  using FS = FovSmall<W>;
   constexpr int WARPS = THREADS / 32;
-  constexpr uint32_t STAGE_OFF = W::ROWBITS_OFF;                 // the render tables are not needed here
-  __shared__ uint32_t s_mask[WARPS][32 * W::NSLOT];          // 25-bit planes indexed by value-plane slot
-  __shared__ uint32_t s_info[WARPS][32];
-  __shared__ float s_crop[W::NVIS > 0 ? WARPS : 1][W::NVIS > 0 ? 32 * 50 : 1];
+  constexpr uint32_t PER = FS::PER, PERL = FS::PERL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bar, W::BLOB_BYTES - STAGE_OFF);
-    bulk_g2s(smem, p.blob + STAGE_OFF, W::BLOB_BYTES - STAGE_OFF, &bar);
+    mbar_expect_tx(&bar, W::BLOB_BYTES - FS::STAGE_OFF);
+    bulk_g2s(smem, p.blob + FS::STAGE_OFF, W::BLOB_BYTES - FS::STAGE_OFF, &bar);
   }
   mbar_wait(&bar, 0);
-  const unsigned char *sb = smem - STAGE_OFF;                    // sb + X_OFF addresses staged table X
+  const unsigned char *sb = smem - FS::STAGE_OFF;                // sb + X_OFF addresses staged table X
   const FovTables<W> t(sb);
+  float *rows = reinterpret_cast<float *>(smem + FS::TAB_BYTES) + warp * (32 * PER);   // this warp's tile: [32][PER]
+  const uint32_t rows_s = smem_addr(rows);
   const int64_t tiles = p.tile_end;
   const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
-  uint32_t *mk = s_mask[warp];
   WarpStats ws;
   auto grab = [&]() {
     int64_t tl = 0;
@@ -281,100 +395,97 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     q.w0 = q.w1 = q.w2 = 0u; q.act = 0;
     if (tl < tiles && e < p.n) q = fov_preload<W>(p, e);
   };
-  int64_t tile = grab(), ntile = grab();
-  FovPre pre;
-  preload(tile, pre);
-  while (tile < tiles) {
-    const int64_t nntile = grab();                               // needed two tiles from now
-    const int64_t e = tile * 32 + lane;
-    const bool valid = e < p.n;
+  // flat copy of `n4` float4s of the warp's smem tile to global (both 16-byte aligned)
+  auto copy_out = [&](float *dst, uint32_t n4) {
+#pragma unroll 4
+    for (uint32_t q = lane; q < n4; q += 32) st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), lds_v4(rows_s + (q << 4)));
+  };
+  // Software pipeline over the warp's tiles (the visit variants): the transitions of tile t+1 run -- and its visit-
+  // window loads are started -- BEFORE tile t's rows are expanded and copied out, so the loads' DRAM round trip
+  // hides behind a tile's worth of shared-memory and store work instead of stalling the warp.
+  struct Slot {
     FovLane<W::NBIT> v;
+    int64_t tile;
+    bool valid;
+  };
+  VisitFetch vf;
+  int64_t ntile = grab(), nntile = grab();
+  FovPre pre;
+  preload(ntile, pre);
+  auto stage_a = [&](Slot &sl) {                                 // transitions + visit loads of the next tile
+    sl.tile = ntile;
+    const int64_t after = grab();                                // needed two tiles from now
+    const int64_t e = sl.tile * 32 + lane;
+    sl.valid = sl.tile < tiles && e < p.n;
+    FovLane<W::NBIT> &v = sl.v;
     v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
-    v.rfov = false; v.rloc = false;
+    v.vinfo = 0; v.rfov = false; v.rloc = false;
 #pragma unroll
     for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
-    if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre);
-    if (p.mode == MODE_STEP) ws.add(valid, v.o);
-    preload(ntile, pre);                                         // next tile's words fly while this tile is written
+    if (sl.valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre);
+    if (p.mode == MODE_STEP) ws.add(sl.valid, v.o);
+    ntile = nntile; nntile = after;
+    preload(ntile, pre);                                         // the tile after's words fly meanwhile
+    if (W::NVIS > 0 && need_visit && sl.tile < tiles)
+      visit_issue<W>(p, sl.tile * 32, lane, sl.valid, v.info, v.vinfo, sl.valid && v.rfov, vf);
+  };
+  Slot cur, nxt;
+  stage_a(cur);
+  while (cur.tile < tiles) {
+    const FovLane<W::NBIT> &v = cur.v;
+    const bool valid = cur.valid;
+    const int64_t tile = cur.tile;
     const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
     const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
-    __syncwarp();
+    float *mine = rows + lane * PER;
+    __syncwarp();                                                // the previous tile's copy out has read the buffer
+    if (W::NVIS > 0 && need_visit)                               // window update of the scaled layer + the two crops
+      visit_finish<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf, mine + W::VIS_SLOT0 * 25, mine + W::VIS_SLOT1 * 25);
+    stage_a(nxt);                                                // next tile: transitions, visit loads in flight
+    const int64_t row0 = tile * 32 - p.win_lo;                   // obs row of the tile's first env
+    if (ff) {
+      if (valid && v.rfov) {                                     // 25-bit planes -> float planes (stride PER is odd: no bank conflicts)
 #pragma unroll
-    for (int b = 0; b < W::NBIT; ++b) mk[lane * W::NSLOT + W::bit_slot(b)] = v.mask[b];
-    s_info[warp][lane] = valid ? v.info : 0u;
-    __syncwarp();
-    if (W::NVIS > 0 && need_visit) {
-      // the tile's 32 visit layers: coalesced read-modify-write by the warp, crops captured on the way
-      const int64_t e0 = tile * 32;
-      const uint32_t cells = (uint32_t)(((p.n - e0) < 32 ? (p.n - e0) : 32) * (W::G * W::G));
-      float *vis = p.visit + e0 * (W::G * W::G);
-      float *cr = s_crop[W::NVIS > 0 ? warp : 0];
-      constexpr uint32_t UN = 12;                                // 324 = 27 x 12 loads per lane, 12 in flight
-      for (uint32_t k0 = 0; k0 < (uint32_t)(W::G * W::G); k0 += UN) {
-        float vv[UN];
+        for (int b = 0; b < W::NBIT; ++b) {
+          if (W::bit_slot(b) >= W::C) continue;                  // (v5: the local obs's planes, below)
+          const uint32_t m = v.mask[b];
+          float *pl = mine + W::bit_slot(b) * 25;
 #pragma unroll
-        for (uint32_t j = 0; j < UN; ++j) {
-          const uint32_t idx = (k0 + j) * 32 + lane;
-          vv[j] = (idx < cells && ((s_info[warp][idx / (W::G * W::G)] >> 20) & 3u) != 2u) ? __ldcs(vis + idx) : 0.0f;
-        }
-#pragma unroll
-        for (uint32_t j = 0; j < UN; ++j) {
-          const uint32_t idx = (k0 + j) * 32 + lane;
-          if (idx >= cells) continue;
-          const uint32_t env = idx / (W::G * W::G), cell = idx - env * (W::G * W::G);
-          const int x = cell / W::G, y = cell - x * W::G;
-          const uint32_t info = s_info[warp][env];
-          const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-          const uint32_t op = (info >> 20) & 3u;
-          const int dx = x - bx + 2, dy = y - by + 2, qx = x - px + 2, qy = y - py + 2;
-          const bool in_cur = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
-          float val = vv[j];
-          if (op == 1) val = visit_average(val, in_cur);
-          else if (op == 2) val = W::visit_reset(in_cur);
-          if (op) __stcs(vis + idx, val);
-          if (in_cur) cr[env * 50 + dx * 5 + dy] = val;
-          if (qx >= 0 && qx < 5 && qy >= 0 && qy < 5) cr[env * 50 + 25 + qx * 5 + qy] = val;
+          for (int c = 0; c < 25; ++c) pl[c] = ((m >> c) & 1u) ? 1.0f : 0.0f;
         }
       }
       __syncwarp();
-    }
-    // value of plane `slot`, cell `cell` of env `env` of this tile
-    auto value = [&](uint32_t env, uint32_t slot, uint32_t cell) -> float {
-      if (W::NVIS > 0 && (slot == (uint32_t)W::VIS_SLOT0 || slot == (uint32_t)W::VIS_SLOT1))
-        return s_crop[W::NVIS > 0 ? warp : 0][env * 50 + (slot == (uint32_t)W::VIS_SLOT1 ? 25 : 0) + cell];
-      return ((mk[env * W::NSLOT + slot] >> cell) & 1u) ? 1.0f : 0.0f;
-    };
-    // Lane l owns floats l, l+32, l+64, ... of EVERY env row, so which plane / cell a lane reads is fixed for the
-    // whole kernel (no per-float index arithmetic) and a warp store covers 32 consecutive floats of one env.
-    if (ff) {
-      constexpr uint32_t PER = W::C * 25;                        // floats per env: the obs channels are slots 0..C-1
-      constexpr int KK = (PER + 31) / 32;
-      float *dst = reinterpret_cast<float *>(p.obs) + (tile * 32 - p.win_lo) * (int64_t)PER;
-      for (unsigned m = ff; m; m &= m - 1) {
-        const uint32_t env = __ffs(m) - 1;
-#pragma unroll
-        for (int k = 0; k < KK; ++k) {
-          const uint32_t pos = lane + 32 * k;
-          if (pos < PER) __stcs(dst + env * PER + pos, value(env, pos / 25, pos % 25));
+      float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)PER;
+      if (ff == 0xffffffffu && (row0 & 3) == 0) copy_out(dst, 32 * PER / 4);
+      else                                                       // batch tail, masked reset, window edge
+        for (unsigned m = ff; m; m &= m - 1) {
+          const uint32_t env = __ffs(m) - 1;
+          for (uint32_t pos = lane; pos < PER; pos += 32) __stcs(dst + env * PER + pos, rows[env * PER + pos]);
         }
-      }
     }
     if (W::HAS_LOC && fl) {
-      constexpr uint32_t PER = 4 * 25;                           // local obs planes: slots 0, 7, 8, 3 (lmaze_env_v5.py:360-368)
-      constexpr int KK = (PER + 31) / 32;
-      float *dst = reinterpret_cast<float *>(p.obs2) + (tile * 32 - p.win_lo) * (int64_t)PER;
-      for (unsigned m = fl; m; m &= m - 1) {
-        const uint32_t env = __ffs(m) - 1;
-        const bool err = (s_info[warp][env] >> 22) & 1u;         // IndexError in the reference: the row is all zero
+      // local obs (lmaze_env_v5.py:360-368): free crop, ball and previous ball relative to the planner-time fovea,
+      // fovealGoal = bit planes 7, 5, 6, 8 (all-zero on an IndexError row); 400 bytes per env, always 16-byte aligned
+      __syncwarp();                                              // the foveal rows have been copied out
+      float *minel = rows + lane * PERL;
+      if (valid && v.rloc) {
 #pragma unroll
-        for (int k = 0; k < KK; ++k) {
-          const uint32_t pos = lane + 32 * k, c = pos / 25;
-          const uint32_t slot = c == 0 ? 9u : c == 1 ? 7u : c == 2 ? 8u : 10u;
-          if (pos < PER) __stcs(dst + env * PER + pos, err ? 0.0f : value(env, slot, pos % 25));
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t m = v.mask[W::NBIT > 8 ? (c4 == 0 ? 7 : c4 == 1 ? 5 : c4 == 2 ? 6 : 8) : 0];
+#pragma unroll
+          for (int c = 0; c < 25; ++c) minel[c4 * 25 + c] = ((m >> c) & 1u) ? 1.0f : 0.0f;
         }
       }
+      __syncwarp();
+      float *dst = reinterpret_cast<float *>(p.obs2) + row0 * (int64_t)PERL;
+      if (fl == 0xffffffffu) copy_out(dst, 32 * PERL / 4);
+      else
+        for (unsigned m = fl; m; m &= m - 1) {
+          const uint32_t env = __ffs(m) - 1;
+          for (uint32_t pos = lane; pos < PERL; pos += 32) __stcs(dst + env * PERL + pos, rows[env * PERL + pos]);
+        }
     }
-    tile = ntile; ntile = nntile;
+    cur = nxt;
   }
   if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
   if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);

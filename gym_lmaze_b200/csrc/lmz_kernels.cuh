@@ -80,6 +80,7 @@ struct KParams {
   uint8_t *loc_err;             // 1 where the reference's buildLocalObservation raises IndexError [n], or null
   uint8_t *fgoal_out;           // hot cell of fovealGoal [n], or null
   int auto_mask;                // plannerStep: act on the envs that are waiting for their planner
+  const void *goals;            // v5 rollout: planner goals [T][n] (same dtype as the actions), or null with actions
 };
 
 enum : int { L2_EVICT_FIRST = 1, L2_EVICT_NORMAL = 2, L2_EVICT_LAST = 3, L2_NONE = 4 };
@@ -707,8 +708,8 @@ __global__ void __launch_bounds__(THREADS) lmz_env_compact_kernel(const KParams 
 // (392 B for v0) instead of 112,896 B, with the tensor bit-identical to a full re-render afterwards.
 // The host only selects this kernel for MODE_STEP and only while the tensor is known to be in sync
 // (after a full reset / render through the same handle); otherwise it falls back to the full render.
-// One thread per env for the transition; then, env by env, the warp writes the <= 49 elements of
-// each block cooperatively (lanes on consecutive floats of the block's rows).
+// One thread per env for the transition; then, env by env, the warp rewrites the sectors around the old
+// and the new block in ONE pass of E iterations (half-warp per block, no per-element divide).
 template <class V, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) {
   __shared__ __align__(16) unsigned char tab[V::TABLES_BYTES];
@@ -779,24 +780,22 @@ __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) 
           if (r0 == r1 && q0 == q1) continue;
           // The plane holds ONE block of ones, so every element's value follows from the new position.  Rewrite
           // whole aligned 32-byte sectors around the old and the new block (values computed, not read): full-sector
-          // writes need no read-modify-write in L2/DRAM, and the two passes may overlap freely (same values).
+          // writes need no read-modify-write in L2/DRAM, and where the two regions share a sector both write the
+          // same values.  ONE loop covers both blocks: half-warp 0 walks the E rows of the old block, half-warp 1
+          // those of the new one, lane & 15 = the float's slot in the row's <= 64-byte sector span.  A sector may
+          // reach into the neighbouring row; those floats lie in the maze's border columns, which a block never
+          // touches (the border cells are walls), so "column relative to this row" decides the value with no divide.
           float *plane = img + (size_t)ch * V::S * V::S;            // 32-byte aligned (plane = 28,224 / 20,736 B)
+          const int sel = lane >> 4, j = lane & 15;
+          const int brow = sel ? r1 : r0, bcol = sel ? q1 : q0;
+          int first = brow * V::S + bcol;                           // the row segment [first, first + E)
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int brow = pass ? r1 : r0, bcol = pass ? q1 : q0;
-#pragma unroll
-            for (int k0 = 0; k0 < V::E * 16; k0 += 32) {
-              const int kk = k0 + lane, rr = kk >> 4, j = kk & 15;    // row of the block, float slot in its <= 64-byte span
-              if (rr < V::E) {
-                const int first = (brow + rr) * V::S + bcol;          // the row segment [first, first + E)
-                const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
-                const int e = lo + j;
-                if (e < hi) {
-                  const int er = e / V::S, ec = e - er * V::S;
-                  plane[e] = (er >= r1 && er < r1 + V::E && ec >= q1 && ec < q1 + V::E) ? 1.0f : 0.0f;
-                }
-              }
-            }
+          for (int rr = 0; rr < V::E; ++rr, first += V::S) {
+            const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
+            const int e = lo + j;
+            const int c = e - first + bcol;                         // column in row brow + rr (may run over: border)
+            const bool one = (unsigned)(c - q1) < (unsigned)V::E && (unsigned)(brow + rr - r1) < (unsigned)V::E;
+            if (e < hi) plane[e] = one ? 1.0f : 0.0f;
           }
         }
       }

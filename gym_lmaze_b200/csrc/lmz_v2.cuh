@@ -34,6 +34,7 @@ struct Fov {
     return C_ == 7 ? (b < 2 ? b : b + 1) : b;
   }
   __device__ static __forceinline__ float visit_reset(bool in_cur) { return in_cur ? 0.5f : 0.0f; }   // zeros, then :110-113
+  __device__ static __forceinline__ float visit_reset_stored(bool in_cur) { return in_cur ? 1.0f : 0.0f; }   // the same, scaled by 2^VT_RESET
   static constexpr bool MAZE_FIRST = (ID_ == 4);                       // v4 re-rolls the maze BEFORE drawing goal/ball (:91-98)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                    // 6,125 (v2) / 8,575 (v4)
   static constexpr uint32_t OBS_BYTES = OBS_FLOATS * 4;                // 24,500 / 34,300
@@ -51,7 +52,8 @@ struct Fov {
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5]
   static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;                           // u16 [5]: each maze's 'X' cell
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
-  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * G * G * 4 : 0);   // + the double-buffered per-env value planes
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;   // + the double-buffered per-env value planes
+  static constexpr int VT_RESET = 1;                                   // v4 reset(): zeros, then ONE averaging (lmaze_env_v4.py:110-119)
 };
 using V2 = Fov<2, 5>;
 using V4 = Fov<4, 7>;
@@ -59,20 +61,56 @@ using V4 = Fov<4, 7>;
 struct V2Regs {
   int L, x, y, gx, gy, px, py, a;     // a: last action, -1 right after a reset (action plane all zero)
   uint32_t step;
+  int vt;                             // v4: scale exponent of the stored visit layer (see "visit layer" below)
 };
 
-// state word: L:3 | x:5 | y:5 | gx:5 | gy:5 | step:6 ; aux word: px:5 | py:5 | a:5 | a_valid:1
+// ---- the float visit layer of v4 / v5, stored SCALED --------------------------------------------------------------
+// Reference: state[2] = (state[2] + visitMap) / 2 over all 324 cells, visitMap = 1 on the 5x5 window around the ball
+// (lmaze_env_v4.py:116-119,211-214; lmaze_env_v5.py:308-312): EVERY cell halves on every averaging, so a literal
+// implementation reads and writes the whole 1,296-byte layer per env-step.  Halving a normal float is exact, so the
+// layer is kept as  s = v * 2^T  with ONE per-env exponent T = averagings since the last rebase:
+//     out-of-window cell:  v' = v / 2          <=>  s' = s                (no memory traffic at all)
+//     in-window cell:      v' = RN((v + 1) / 2) <=>  s' = RN(s + 2^T)      (25 cells read + written)
+//     shown value:         v  = s * 2^-T                                     (exact: power-of-two scaling of a normal)
+// RN(s + 2^T) = RN(v + 1) * 2^T because scaling by a power of two commutes with rounding while everything stays
+// normal, and RN32(v + 1) / 2 is what the reference's float64 expression rounds to (visit_average in lmz_fov.cuh).
+// "Everything stays normal" holds while T <= VT_MAX: every non-zero true value is >= 2^-T.  An env that is averaged
+// more than VT_MAX times without a reset (only possible by stepping on far past `done` with autoreset off, or after
+// lmz_set_visit, whose values carry no such bound) falls back to DIRECT mode (T field = VT_DIRECT): the layer holds
+// the true values and every averaging is the literal full pass, denormal roundings included.  reset() returns to
+// the scaled form.  lmz_get_visit / lmz_set_visit exchange TRUE values.
+constexpr int VT_MAX = 100, VT_DIRECT = 127;
+enum : uint32_t { VOP_READ = 0, VOP_AVG = 1, VOP_RESET = 2, VOP_FULL = 3 };
+// want: 0 nothing, 1 average with the window at the ball, 2 reset.  vinfo = op:3 | T before:7 | T after:7
+template <class W>
+__device__ __forceinline__ uint32_t visit_plan(int want, int &vt) {
+  const int tpre = vt;
+  uint32_t op = VOP_READ;
+  if (want == 2) { op = VOP_RESET; vt = W::VT_RESET; }
+  else if (want == 1) {
+    if (vt >= VT_MAX) { op = VOP_FULL; vt = VT_DIRECT; }          // direct mode, or the step that converts to it
+    else { op = VOP_AVG; vt = vt + 1; }
+  }
+  return op | ((uint32_t)tpre << 3) | ((uint32_t)vt << 10);
+}
+__device__ __forceinline__ float visit_scale_down(int t) {           // 2^-T (1.0 in direct mode)
+  return __int_as_float((127 - (t == VT_DIRECT ? 0 : t)) << 23);
+}
+
+// state word: L:3 | x:5 | y:5 | gx:5 | gy:5 | step:6 ; aux word: px:5 | py:5 | a:5 | a_valid:1 | visit T:7 (v4)
 __host__ __device__ inline V2Regs v2_unpack(uint32_t s, uint32_t aux) {
   V2Regs r;
   r.L = s & 7; r.x = (s >> 3) & 31; r.y = (s >> 8) & 31; r.gx = (s >> 13) & 31; r.gy = (s >> 18) & 31;
   r.step = (s >> 23) & 63;
   r.px = aux & 31; r.py = (aux >> 5) & 31; r.a = ((aux >> 15) & 1) ? (int)((aux >> 10) & 31) : -1;
+  r.vt = (aux >> 16) & 127;
   return r;
 }
 __host__ __device__ inline void v2_pack(const V2Regs &r, uint32_t &s, uint32_t &aux) {
   s = (uint32_t)r.L | ((uint32_t)r.x << 3) | ((uint32_t)r.y << 8) | ((uint32_t)r.gx << 13) | ((uint32_t)r.gy << 18) |
       (r.step << 23);
-  aux = (uint32_t)r.px | ((uint32_t)r.py << 5) | (r.a >= 0 ? (((uint32_t)r.a << 10) | (1u << 15)) : 0u);
+  aux = (uint32_t)r.px | ((uint32_t)r.py << 5) | (r.a >= 0 ? (((uint32_t)r.a << 10) | (1u << 15)) : 0u) |
+        ((uint32_t)r.vt << 16);
 }
 
 template <class W>
@@ -173,7 +211,8 @@ template <int NB>
 struct FovLane {
   LaneOut o;
   uint32_t mask[NB];
-  uint32_t info;            // x:5 | y:5 | px:5 | py:5 | visit op:2 (0 read only, 1 average, 2 reset) | local-obs error:1
+  uint32_t info;            // x:5 | y:5 | px:5 | py:5 | (2 unused bits) | local-obs error:1
+  uint32_t vinfo;           // visit layer: op:3 (VOP_*) | T before:7 | T after:7   (visit_plan)
   bool rfov, rloc;          // which observation rows this call writes
 };
 using V2Lane = FovLane<5>;  // free, goal, action, previous free, previous goal
@@ -192,6 +231,32 @@ __device__ __forceinline__ FovPre fov_preload(const KParams &p, int64_t e) {
   return q;
 }
 
+// One reference step() on registers (lmaze_env_v2.py:127-225 minus the observation): returns done, leaves the
+// reward code and the branch taken (CLS_X goal, CLS_W wall, CLS_B blank / start, CLS_S: an 'X' cell that is not the goal).
+template <class W>
+__device__ __forceinline__ bool v2_step_core(V2Regs &r, long long a64, const FovTables<W> &t, unsigned int *errors,
+                                             int &reward_code, int &cls) {
+  if (a64 < 0 || a64 > 24) { atomicAdd(errors, 1u); a64 = a64 < 0 ? 0 : 24; }       // reference raises IndexError
+  const int a = (int)a64;
+  reward_code = RC_NEG_ZERO;                                                         // :146
+  r.step = r.step < W::STEP_SAT ? r.step + 1 : W::STEP_SAT;                          // :148
+  const int fx = r.x + a / 5 - 2, fy = r.y + a % 5 - 2;                              // :151-152
+  r.px = r.x; r.py = r.y; r.a = a;                                                   // this obs shows the old crop
+  if (fx < W::G - 2 && fx > 1 && fy < W::G - 2 && fy > 1) { r.x = fx; r.y = fy; }    // :157-159
+  else {                                                                             // :160-169 per-axis clamp
+    if (fx >= W::G - 2) r.x = W::G - 3;
+    if (fx <= 1) r.x = 2;
+    if (fy >= W::G - 2) r.y = W::G - 3;
+    if (fy <= 1) r.y = 2;
+  }
+  const int tc = t.cls[(r.L - 1) * W::G * W::G + fx * W::G + fy];
+  if (fx == r.gx && fy == r.gy) { reward_code = RC_GOAL; cls = CLS_X; }              // :175-176
+  else if (tc == CLS_W) { reward_code = RC_WALL; cls = CLS_W; }                      // :177-178
+  else if (tc == CLS_B || tc == CLS_S) { reward_code = RC_MOVE; cls = CLS_B; }       // :179-180
+  else cls = CLS_S;                                                                  // 'X' not the goal: -0.0
+  return (reward_code == RC_GOAL) || (r.step > (uint32_t)W::STEP_LIMIT);            // :222
+}
+
 template <class W>
 __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const FovTables<W> &t, const FovPre &pre) {
   V2Lane out;
@@ -200,28 +265,10 @@ __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const Fov
   V2Regs r = v2_unpack(pre.w0, pre.w1);
   bool reset_now = false;
   int reward_code = RC_NEG_ZERO;
-  uint32_t visit_op = 0;
+  int visit_want = 0;
   if (p.mode == MODE_STEP) {
-    visit_op = 1;
-    long long a64 = pre.act;
-    if (a64 < 0 || a64 > 24) { atomicAdd(p.errors, 1u); a64 = a64 < 0 ? 0 : 24; }   // reference raises IndexError
-    const int a = (int)a64;
-    r.step = r.step < W::STEP_SAT ? r.step + 1 : W::STEP_SAT;                      // :148
-    const int fx = r.x + a / 5 - 2, fy = r.y + a % 5 - 2;                            // :151-152
-    r.px = r.x; r.py = r.y; r.a = a;                                                 // this obs shows the old crop
-    if (fx < W::G - 2 && fx > 1 && fy < W::G - 2 && fy > 1) { r.x = fx; r.y = fy; }  // :157-159
-    else {                                                                           // :160-169 per-axis clamp
-      if (fx >= W::G - 2) r.x = W::G - 3;
-      if (fx <= 1) r.x = 2;
-      if (fy >= W::G - 2) r.y = W::G - 3;
-      if (fy <= 1) r.y = 2;
-    }
-    const int tc = t.cls[(r.L - 1) * W::G * W::G + fx * W::G + fy];
-    if (fx == r.gx && fy == r.gy) { reward_code = RC_GOAL; o.cls = CLS_X; }          // :175-176
-    else if (tc == CLS_W) { reward_code = RC_WALL; o.cls = CLS_W; }                  // :177-178
-    else if (tc == CLS_B || tc == CLS_S) { reward_code = RC_MOVE; o.cls = CLS_B; }   // :179-180
-    else o.cls = CLS_S;                                                              // 'X' not the goal: -0.0
-    o.done = (reward_code == RC_GOAL) || (r.step > (uint32_t)W::STEP_LIMIT);        // :222
+    visit_want = 1;                                                                  // lmaze_env_v4.py:211-214
+    o.done = v2_step_core<W>(r, pre.act, t, p.errors, reward_code, o.cls);
     p.reward[e] = __uint_as_float(reward_bits(reward_code));
     p.done[e] = o.done ? 1 : 0;
     if (o.done) o.eplen = r.step;
@@ -237,9 +284,10 @@ __device__ __forceinline__ V2Lane v2_lane(const KParams &p, int64_t e, const Fov
     uint32_t ep = p.episode[e];
     v2_respawn<W>(r, p, e, ep, t);
     p.episode[e] = ep;
-    visit_op = 2;
+    visit_want = 2;
   }
-  out.info = (uint32_t)r.x | ((uint32_t)r.y << 5) | ((uint32_t)r.px << 10) | ((uint32_t)r.py << 15) | (visit_op << 20);
+  out.info = (uint32_t)r.x | ((uint32_t)r.y << 5) | ((uint32_t)r.px << 10) | ((uint32_t)r.py << 15);
+  out.vinfo = (W::NVIS > 0) ? visit_plan<W>(visit_want, r.vt) : 0u;
   uint32_t s, aux;
   v2_pack(r, s, aux);
   o.st = s;
@@ -275,13 +323,14 @@ __global__ void lmz_state_v2_kernel(int64_t n, uint32_t *state, uint32_t *auxw, 
                r.px != (row[6] & 31) || r.py != ((row[6] >> 5) & 31) || r.a > 24;
     if (bad) atomicAdd(errors, 1u);
     if (r.a > 24) r.a = 24;
+    r.vt = (auxw[e] >> 16) & 127;                 // the visit layer's scale exponent is not part of the row: kept
     uint32_t s, aux;
     v2_pack(r, s, aux);
     state[e] = s; auxw[e] = aux; episode[e] = (uint32_t)row[7];
   } else {
     const V2Regs r = v2_unpack(state[e], auxw[e]);
     row[0] = r.x; row[1] = r.y; row[2] = r.gx; row[3] = r.gy; row[4] = (int32_t)r.step; row[5] = r.L;
-    row[6] = (int32_t)auxw[e]; row[7] = (int32_t)episode[e];
+    row[6] = (int32_t)(auxw[e] & 0xFFFFu); row[7] = (int32_t)episode[e];
   }
 }
 

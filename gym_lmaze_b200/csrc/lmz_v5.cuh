@@ -40,6 +40,8 @@ struct V5 {
   static constexpr int VIS_SLOT0 = 2, VIS_SLOT1 = 6;
   __host__ __device__ static constexpr int bit_slot(int b) { return b < 2 ? b : (b < 5 ? b + 1 : b + 2); }   // 0 1 3 4 5 7 8 9 10
   __device__ static __forceinline__ float visit_reset(bool) { return 0.0f; }   // self.state = zeros (:134), no averaging
+  __device__ static __forceinline__ float visit_reset_stored(bool) { return 0.0f; }
+  static constexpr int VT_RESET = 0;
   static constexpr bool MAZE_FIRST = true;                                   // reset(): setGrid() first (:104,115-116)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                          // 8,575 (foveal)
   static constexpr uint32_t OBS_BYTES = OBS_FLOATS * 4;                      // 34,300
@@ -58,7 +60,7 @@ struct V5 {
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G); // u8 ng[5], nb[5]; u16 xcell[5] at +16
   static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
-  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * G * G * 4 : 0);
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;
 };
 
 struct V5Regs {
@@ -70,14 +72,15 @@ struct V5Regs {
   int fga;                    // hot cell of fovealGoal   (:166-168; 12 after reset, :131-132)
   uint32_t step, fstep;       // stepCount, fovealStepCount (saturating; only >= 10 / >= 50 / == 0 matter)
   int ld, gd;                 // localDone, globalDone
+  int vt;                     // scale exponent of the stored visit layer (lmz_v2.cuh, "visit layer")
 };
 
-// w0: L:3 | x:5 | y:5 | gx:5 | gy:5 | ld:1 | gd:1      w1: x1:5 | y1:5 | fx1:5 | fy1:5 | fgx:5 | fgy:5
+// w0: L:3 | x:5 | y:5 | gx:5 | gy:5 | ld:1 | gd:1 | visit T:7      w1: x1:5 | y1:5 | fx1:5 | fy1:5 | fgx:5 | fgy:5
 // w2: lx:5 | ly:5 | fga:5 | step:8 | fstep:8
 __host__ __device__ inline V5Regs v5_unpack(uint32_t w0, uint32_t w1, uint32_t w2) {
   V5Regs r;
   r.L = w0 & 7; r.x = (w0 >> 3) & 31; r.y = (w0 >> 8) & 31; r.gx = (w0 >> 13) & 31; r.gy = (w0 >> 18) & 31;
-  r.ld = (w0 >> 23) & 1; r.gd = (w0 >> 24) & 1;
+  r.ld = (w0 >> 23) & 1; r.gd = (w0 >> 24) & 1; r.vt = (w0 >> 25) & 127;
   r.x1 = w1 & 31; r.y1 = (w1 >> 5) & 31; r.fx1 = (w1 >> 10) & 31; r.fy1 = (w1 >> 15) & 31;
   r.fgx = (w1 >> 20) & 31; r.fgy = (w1 >> 25) & 31;
   r.lx = w2 & 31; r.ly = (w2 >> 5) & 31; r.fga = (w2 >> 10) & 31; r.step = (w2 >> 15) & 255; r.fstep = (w2 >> 23) & 255;
@@ -85,7 +88,7 @@ __host__ __device__ inline V5Regs v5_unpack(uint32_t w0, uint32_t w1, uint32_t w
 }
 __host__ __device__ inline void v5_pack(const V5Regs &r, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
   w0 = (uint32_t)r.L | ((uint32_t)r.x << 3) | ((uint32_t)r.y << 8) | ((uint32_t)r.gx << 13) | ((uint32_t)r.gy << 18) |
-       ((uint32_t)r.ld << 23) | ((uint32_t)r.gd << 24);
+       ((uint32_t)r.ld << 23) | ((uint32_t)r.gd << 24) | ((uint32_t)r.vt << 25);
   w1 = (uint32_t)r.x1 | ((uint32_t)r.y1 << 5) | ((uint32_t)r.fx1 << 10) | ((uint32_t)r.fy1 << 15) |
        ((uint32_t)r.fgx << 20) | ((uint32_t)r.fgy << 25);
   w2 = (uint32_t)r.lx | ((uint32_t)r.ly << 5) | ((uint32_t)r.fga << 10) | (r.step << 15) | (r.fstep << 23);
@@ -96,7 +99,7 @@ template <class W>
 __device__ __forceinline__ void v5_respawn(V5Regs &r, const KParams &p, int64_t e, uint32_t &episode,
                                            const FovTables<W> &t, const unsigned char *smem) {
   V2Regs v;
-  v.L = r.L; v.x = r.x; v.y = r.y; v.gx = r.gx; v.gy = r.gy; v.px = v.py = 0; v.a = -1; v.step = 0;
+  v.L = r.L; v.x = r.x; v.y = r.y; v.gx = r.gx; v.gy = r.gy; v.px = v.py = 0; v.a = -1; v.step = 0; v.vt = 0;
   v2_respawn<W>(v, p, e, episode, t);                     // MAZE_FIRST: maze, then goal, then ball (as v4); RANDOM_* flags
   r.L = v.L; r.x = v.x; r.y = v.y; r.gx = v.gx; r.gy = v.gy;
   r.x1 = r.fx1 = r.fgx = r.lx = r.x;                      // :139-148, and retStatelast = observation (:327-328)
@@ -112,6 +115,44 @@ __device__ __forceinline__ bool v5_np_index(int &i) {
   return true;
 }
 
+// step() on registers (lmaze_env_v5.py:187-262 minus the observations): returns "globalDone was raised by this
+// step"; leaves the local / global reward codes and the branch taken.
+template <class W>
+__device__ __forceinline__ bool v5_step_core(V5Regs &r, long long a, const FovTables<W> &t, int &lcode, int &gcode, int &cls) {
+  r.x1 = r.x; r.y1 = r.y;                                                            // :192-193
+  r.step = r.step < W::STEP_SAT ? r.step + 1 : W::STEP_SAT;                          // :196
+  int dx = 0, dy = 0;                                                                // :203-217
+  if (a == 0) dx = 1; else if (a == 1) dx = -1; else if (a == 2) dy = 1; else if (a == 3) dy = -1;
+  const int nx = r.x + dx, ny = r.y + dy;
+  const int tc = t.cls[(r.L - 1) * W::G * W::G + nx * W::G + ny];
+  const bool at_fgoal = (nx == r.fgx && ny == r.fgy);
+  const int was_gd = r.gd;
+  lcode = RC_NEG_ZERO;                                                               // :195
+  if (tc == CLS_W) { lcode = RC_WALL; cls = CLS_W; }                                 // :223-224
+  else if (at_fgoal) { lcode = RC_GOAL; r.x = nx; r.y = ny; r.ld = 1; cls = CLS_B; } // :226-230
+  else {                                                                             // :232-242 (B, S or X)
+    if (nx < r.fx1 - 3 || nx > r.fx1 + 2 || ny < r.fy1 - 3 || ny > r.fy1 + 2) r.ld = 1;
+    lcode = RC_MOVE; r.x = nx; r.y = ny; cls = CLS_B;
+  }
+  if (nx == r.gx && ny == r.gy) { gcode = RC_GOAL; r.gd = 1; cls = CLS_X; }          // :245-247
+  else if (at_fgoal) gcode = RC_MOVE;                                                // :248-249
+  else gcode = RC_WALL;                                                              // :250-251
+  if (r.step >= (uint32_t)W::STEP_LIMIT) r.ld = 1;                                   // :257-258
+  if (r.fstep >= (uint32_t)W::FSTEP_LIMIT) { r.gd = 1; r.ld = 1; }                   // :260-262
+  return r.gd && !was_gd;
+}
+
+// plannerStep() on registers (lmaze_env_v5.py:158-182 minus the local observation)
+template <class W>
+__device__ __forceinline__ void v5_planner_core(V5Regs &r, long long g, unsigned int *errors) {
+  if (g < 0 || g > 24) { atomicAdd(errors, 1u); g = g < 0 ? 0 : 24; }               // the reference raises IndexError (:168)
+  r.step = 0; r.ld = 0;                                                              // :161-163
+  r.fga = (int)g;                                                                    // :165-168
+  r.fgx = r.x + (int)g / 5 - 2; r.fgy = r.y + (int)g % 5 - 2;                        // :170-171
+  if (r.fstep > 0) { r.fx1 = r.x; r.fy1 = r.y; }                                     // :176-178 (fovea_x0 is the ball)
+  r.fstep = r.fstep < W::STEP_SAT ? r.fstep + 1 : W::STEP_SAT;                       // :180
+}
+
 using V5Lane = FovLane<V5::NBIT>;   // info: x | y | shown retStatelast x | y | visit op (0 read, 1 average, 2 zero) | loc_err
 
 template <class W>
@@ -123,31 +164,12 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
   out.rfov = false; out.rloc = false;
   V5Regs r = v5_unpack(pre.w0, pre.w1, pre.w2);
   bool reset_now = false, write_state = false;
-  uint32_t visit_op = 0;
+  int visit_want = 0;
   int slx = r.lx, sly = r.ly;                       // the retStatelast window the FOVEAL obs of this call shows
   if (p.mode == MODE_STEP) {
-    const long long a = pre.act;
-    r.x1 = r.x; r.y1 = r.y;                                                          // :192-193
-    r.step = r.step < W::STEP_SAT ? r.step + 1 : W::STEP_SAT;                        // :196
-    int dx = 0, dy = 0;                                                              // :203-217
-    if (a == 0) dx = 1; else if (a == 1) dx = -1; else if (a == 2) dy = 1; else if (a == 3) dy = -1;
-    const int nx = r.x + dx, ny = r.y + dy;
-    const int tc = t.cls[(r.L - 1) * W::G * W::G + nx * W::G + ny];
-    const bool at_fgoal = (nx == r.fgx && ny == r.fgy);
-    const int was_gd = r.gd;
-    int lcode = RC_NEG_ZERO, gcode;                                                  // :195
-    if (tc == CLS_W) { lcode = RC_WALL; o.cls = CLS_W; }                             // :223-224
-    else if (at_fgoal) { lcode = RC_GOAL; r.x = nx; r.y = ny; r.ld = 1; o.cls = CLS_B; }   // :226-230
-    else {                                                                           // :232-242 (B, S or X)
-      if (nx < r.fx1 - 3 || nx > r.fx1 + 2 || ny < r.fy1 - 3 || ny > r.fy1 + 2) r.ld = 1;
-      lcode = RC_MOVE; r.x = nx; r.y = ny; o.cls = CLS_B;
-    }
-    if (nx == r.gx && ny == r.gy) { gcode = RC_GOAL; r.gd = 1; o.cls = CLS_X; }      // :245-247
-    else if (at_fgoal) gcode = RC_MOVE;                                              // :248-249
-    else gcode = RC_WALL;                                                            // :250-251
-    if (r.step >= (uint32_t)W::STEP_LIMIT) r.ld = 1;                                 // :257-258
-    if (r.fstep >= (uint32_t)W::FSTEP_LIMIT) { r.gd = 1; r.ld = 1; }                 // :260-262
-    visit_op = r.ld ? 1u : 0u;                                                       // buildFovealObservation, :308-312
+    int lcode, gcode;
+    o.done = v5_step_core<W>(r, pre.act, t, lcode, gcode, o.cls);
+    visit_want = r.ld ? 1 : 0;                                                       // buildFovealObservation, :308-312
     if (r.fstep == 0) { r.lx = r.x; r.ly = r.y; }                                    // :327-328
     slx = r.lx; sly = r.ly;
     if (r.ld) { r.lx = r.x; r.ly = r.y; }                                            // :351-352, after the obs was built
@@ -155,7 +177,6 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     p.reward2[e] = __uint_as_float(reward_bits(lcode));
     p.done[e] = (uint8_t)r.gd;
     p.done2[e] = (uint8_t)r.ld;
-    o.done = r.gd && !was_gd;
     if (o.done) o.eplen = r.fstep;
     reset_now = r.gd && p.autoreset;
     out.rfov = out.rloc = true;
@@ -164,13 +185,7 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     // auto mask: the envs that are waiting for their planner -- local episode over, or no plannerStep since reset()
     const bool take = p.auto_mask ? (r.ld != 0 || r.fstep == 0) : (p.mask == nullptr || p.mask[e] != 0);
     if (take) {
-      long long g = pre.act;
-      if (g < 0 || g > 24) { atomicAdd(p.errors, 1u); g = g < 0 ? 0 : 24; }         // the reference raises IndexError (:168)
-      r.step = 0; r.ld = 0;                                                          // :161-163
-      r.fga = (int)g;                                                                // :165-168
-      r.fgx = r.x + (int)g / 5 - 2; r.fgy = r.y + (int)g % 5 - 2;                    // :170-171
-      if (r.fstep > 0) { r.fx1 = r.x; r.fy1 = r.y; }                                 // :176-178 (fovea_x0 is the ball)
-      r.fstep = r.fstep < W::STEP_SAT ? r.fstep + 1 : W::STEP_SAT;                   // :180
+      v5_planner_core<W>(r, pre.act, p.errors);
       out.rloc = true;
       write_state = true;
     }
@@ -184,7 +199,7 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     uint32_t ep = p.episode[e];
     v5_respawn<W>(r, p, e, ep, t, smem);
     p.episode[e] = ep;
-    visit_op = 2;                                   // self.state = zeros (:134); no averaging: localDone is False
+    visit_want = 2;                                 // self.state = zeros (:134); no averaging: localDone is False
     slx = r.lx; sly = r.ly;
     write_state = true;
   }
@@ -195,6 +210,7 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     if (!loc_ok) atomicAdd(p.errors, 1u);
     if (p.loc_err) p.loc_err[e] = loc_ok ? 0 : 1;
   }
+  out.vinfo = visit_plan<W>(visit_want, r.vt);
   if (write_state) {
     uint32_t w0, w1, w2;
     v5_pack(r, w0, w1, w2);
@@ -202,7 +218,7 @@ __device__ __forceinline__ V5Lane v5_lane(const KParams &p, int64_t e, const Fov
     if (p.fgoal_out) p.fgoal_out[e] = (uint8_t)r.fga;
   }
   o.st = 0;
-  out.info = (uint32_t)r.x | ((uint32_t)r.y << 5) | ((uint32_t)slx << 10) | ((uint32_t)sly << 15) | (visit_op << 20) |
+  out.info = (uint32_t)r.x | ((uint32_t)r.y << 5) | ((uint32_t)slx << 10) | ((uint32_t)sly << 15) |
              (loc_ok ? 0u : (1u << 22));
   out.rfov = out.rfov && p.obs != nullptr;
   out.rloc = out.rloc && p.obs2 != nullptr;
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(THREADS) lmz_planner_kernel(const KParams p) {
     const int64_t e = tl * 32 + lane;
     const bool valid = e < p.n;
     V5Lane v;
-    v.rloc = false; v.info = 0;
+    v.rloc = false; v.info = 0; v.vinfo = 0;
 #pragma unroll
     for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
     if (valid) v = v5_lane<W>(p, e, t, smem, fov_preload<W>(p, e));
@@ -351,6 +367,7 @@ __global__ void lmz_state_v5_kernel(int64_t n, uint32_t *state, uint32_t *aux1, 
                      r.fy1 != row[5] || r.gx != row[6] || r.gy != row[7] || r.fgx != row[8] || r.fgy != row[9] ||
                      r.lx != row[10] || r.ly != row[11] || r.fga != row[12] || row[13] < 0 || row[14] < 0 || r.L != L;
     if (bad) atomicAdd(errors, 1u);
+    r.vt = (state[e] >> 25) & 127;                  // the visit layer's scale exponent is not part of the row: kept
     uint32_t w0, w1, w2;
     v5_pack(r, w0, w1, w2);
     state[e] = w0; aux1[e] = w1; aux2[e] = w2; episode[e] = (uint32_t)row[16];

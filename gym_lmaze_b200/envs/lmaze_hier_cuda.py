@@ -143,7 +143,28 @@ class LmazeHierCuda(LmazeVecCuda):
             lreward_host.data_ptr(), gdone_host.data_ptr(), ldone_host.data_ptr(), self._stream()))
         return greward_host, lreward_host, gdone_host, ldone_host
 
+    def rollout(self, T, goals=None, actions=None):
+        """T fused planner + actor steps, no per-step observations (lmz_hier_rollout): per step plannerStep(goals[t])
+        for the envs waiting for their planner, then step(actions[t]).  goals / actions: [T, N] of one integer dtype,
+        or both None for device-side random ones.  Returns (globalReward f32, originalReward f32, globalDone bool,
+        localDone bool), each [T, N]."""
+        T = int(T)
+        if (goals is None) != (actions is None):
+            raise ValueError("give both goals and actions, or neither")
+        if goals is not None:
+            goals, actions = self._as_actions(goals), self._as_actions(actions)
+            if goals.dtype != actions.dtype:
+                goals = goals.to(actions.dtype)
+        n, dev = self.num_envs, self.device
+        gr = torch.empty((T, n), dtype=torch.float32, device=dev)
+        lr = torch.empty((T, n), dtype=torch.float32, device=dev)
+        gd = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        ld = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        ptrs = [_abi.dl(t) for t in (goals, actions, gr, lr, gd, ld)]
+        _abi.check(self._lib.lmz_hier_rollout_dl(self._h, T, *[p for p, _ in ptrs], self._stream()))
+        return gr, lr, gd.view(torch.bool), ld.view(torch.bool)
+
     def _unsupported(self, *a, **k):
         raise NotImplementedError("not available for the planner/actor env (lmaze-v5/v6)")
 
-    rollout = set_window = render_window = initState = _unsupported
+    set_window = render_window = initState = host_pipeline = _unsupported

@@ -208,7 +208,10 @@ int lmz_render(lmz_env *env, void *stream);
 
 /* T fused steps with state in registers and no per-step observation:
  * rewards f32 [T][N], dones u8 [T][N].  actions NULL => device-side random
- * actions (Philox keyed by seed, global env id, step index); else [T][N]. */
+ * actions (Philox keyed by seed, global env id, step index); else [T][N].
+ * v0 / v3: lmaze_env.py:146-237 / lmaze_env_v3.py:220-402 looped; v2 / v4: lmaze_env_v2.py:127-225 /
+ * lmaze_env_v4.py:155-275 looped (Discrete(25) actions; v4's visit layer is kept up to date in HBM).
+ * v5 / v6 roll out through lmz_hier_rollout. */
 int lmz_rollout(lmz_env *env, int32_t T, const void *actions, int32_t action_dtype,
                 float *rewards, uint8_t *dones, void *stream);
 int lmz_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *actions, DLManagedTensor *rewards,
@@ -254,7 +257,7 @@ int lmz_set_visit_dl(lmz_env *env, DLManagedTensor *in, void *stream);
  * Where the reference's buildLocalObservation raises IndexError (the actor is 3 cells right of / below the
  * planner-time fovea, :365-366) the local row is written as zeros, loc_err[i] = 1 and the error counter of
  * lmz_stats is bumped; negative indices wrap exactly like numpy's.
- * lmz_set_window, lmz_rollout and lmz_step_host are not available for this variant. */
+ * lmz_set_window and lmz_step_host are not available for this variant; its rollout is lmz_hier_rollout. */
 #define LMZ_ST_COLS_HIER 17   /* x, y, prev_x, prev_y, fovea_x1, fovea_y1, goal_x, goal_y, fgoal_x, fgoal_y, last_x, last_y,
                                  fgoal_action, step_count, foveal_step_count, globalDone | localDone << 1 | layout << 4, episode */
 int lmz_state_cols(int32_t variant);                               /* LMZ_ST_COLS, or LMZ_ST_COLS_HIER for v5 */
@@ -281,6 +284,18 @@ int lmz_planner_step_auto_dl(lmz_env *env, DLManagedTensor *goals, void *stream)
 int lmz_hier_step_host(lmz_env *env, const void *goals_host, const void *actions_host, int32_t dtype,
                        float *global_reward_host, float *local_reward_host, uint8_t *global_done_host,
                        uint8_t *local_done_host, void *stream);
+/* T fused planner + actor steps with no per-step observation (lmaze_env_v5.py:158-292 looped).  One step =
+ * plannerStep(goals[t]) for the envs that are waiting for their planner (the device-side mask of
+ * lmz_planner_step_auto) followed by step(actions[t]); with autoreset an env whose globalDone is raised is reset.
+ * Outputs [T][N]: globalReward, originalReward (f32), globalDone, localDone (u8).  goals and actions are [T][N] of
+ * the same dtype, or both NULL: device-side random goals (0..24) and actions (0..3). */
+int lmz_hier_rollout(lmz_env *env, int32_t T, const void *goals, const void *actions, int32_t dtype,
+                     float *global_rewards, float *local_rewards, uint8_t *global_dones, uint8_t *local_dones,
+                     void *stream);
+int lmz_hier_rollout_dl(lmz_env *env, int32_t T, DLManagedTensor *goals, DLManagedTensor *actions,
+                        DLManagedTensor *global_rewards, DLManagedTensor *local_rewards,
+                        DLManagedTensor *global_dones, DLManagedTensor *local_dones, void *stream);
+
 /* lmaze-v6 safeFovealGoal() (lmaze_env_v6.py:505-523): goals_out u8 [N] = a cell 0..24 of the 5x5 window around
  * the ball that is not a wall.  draws NULL => device RNG, exactly uniform over the non-wall cells (the
  * distribution of the reference's rejection loop); else int64 [N][n_draws] are the values its

@@ -157,6 +157,9 @@ void lmzo_rng_spawn_v2(uint64_t seed, uint64_t env_id, uint32_t episode, int cur
                        int *sx, int *sy, int *gx, int *gy, int *first_layout, int *new_layout);
 /* Rollout action for (seed, global env id, global rollout step t). */
 int  lmzo_rng_action(uint64_t seed, uint64_t env_id, uint64_t t);
+/* The same for the Discrete(25) variants (v2 / v4) and for the planner / actor env (goal 0..24 + action 0..3). */
+int  lmzo_rng_action25(uint64_t seed, uint64_t env_id, uint64_t t);
+void lmzo_rng_hier(uint64_t seed, uint64_t env_id, uint64_t t, int *goal, int *action);
 
 /* ---- Vectorised driver: the batched semantics of the framework composed from
  * the single-env restatement above.  For each env i: step; record f32 reward and

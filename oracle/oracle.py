@@ -63,6 +63,10 @@ def lib():
     L.lmzo_rng_spawn.restype = None
     L.lmzo_rng_action.argtypes = [u64, u64, u64]
     L.lmzo_rng_action.restype = ctypes.c_int
+    L.lmzo_rng_action25.argtypes = [u64, u64, u64]
+    L.lmzo_rng_action25.restype = ctypes.c_int
+    L.lmzo_rng_hier.argtypes = [u64, u64, u64, ip, ip]
+    L.lmzo_rng_hier.restype = None
     L.lmzo_vec_step.argtypes = [vp, i64, vp, vp, u64, u64, vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
     L.lmzo_vec_step.restype = None
     L.lmzo_vec_reset.argtypes = [vp, i64, ctypes.c_int, vp, u64, u64, vp, vp, ctypes.c_int]
@@ -144,6 +148,16 @@ def rng_spawn(variant, seed, env_id, episode):
 
 def rng_action(seed, env_id, t):
     return lib().lmzo_rng_action(seed, env_id, t)
+
+
+def rng_action25(seed, env_id, t):
+    return lib().lmzo_rng_action25(seed, env_id, t)
+
+
+def rng_hier(seed, env_id, t):
+    g, a = ctypes.c_int(), ctypes.c_int()
+    lib().lmzo_rng_hier(seed, env_id, t, ctypes.byref(g), ctypes.byref(a))
+    return g.value, a.value
 
 
 class OracleVec(object):

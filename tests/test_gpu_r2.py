@@ -282,3 +282,223 @@ def test_host_pipeline_matches_oracle(lmz, oracle_mod, variant, obs_mode):
     assert torch.equal(env.expand(env.obs).cpu(), torch.from_numpy(o_ref))
     assert env.stats()["steps"] == (T + 2) * N
     env.close()
+
+
+# ---------------------------------------------------------------- the SCALED visit layer (v4 / v5), edge cases
+def u32(t):
+    return (t.detach().cpu().numpy() if torch.is_tensor(t) else t).view(np.uint32)
+
+
+@pytest.mark.parametrize("obs_mode", ["full", "compact"])
+def test_v4_visit_layer_long_episode_without_reset(lmz, oracle_mod, obs_mode):
+    """autoreset off and no reset for 330 steps: the layer is averaged 330 times in a row, far past VT_MAX = 100
+    (conversion to direct mode at the 100th averaging) and deep into the float32 denormals (values halve down to
+    2^-149 and round to zero step by step).  Whole layer + whole observation vs the oracle, bit for bit."""
+    N, T = 777, 330
+    ora = oracle_mod.OracleVec(oracle_mod.V4, N, seed=31, autoreset=False, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, "v4", seed=31, autoreset=False, obs_mode=obs_mode)
+    assert torch.equal(env.expand(env.reset()).cpu(), torch.from_numpy(ora.reset()))
+    gen = torch.Generator().manual_seed(8)
+    small = 0
+    for t in range(T):
+        # keep most envs in one corner so that the far cells are never visited again and decay all the way down
+        a = torch.randint(0, 25, (N,), generator=gen)
+        a[N // 2:] = 12
+        o_ref, r_ref, d_ref = ora.step(a.numpy())
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(rbits(rew), r_ref.view(np.uint32)) and np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
+        assert np.array_equal(u32(env.expand(obs)), u32(o_ref)), t
+        if t % 20 == 19 or t in (98, 99, 100, 101, 148, 149, 150, 151):
+            vref = ora.export_visit()
+            assert np.array_equal(u32(env.get_visit()), u32(vref)), t
+            small = max(small, int(((vref > 0) & (vref < 1.2e-38)).sum()))
+    assert small > 0                                           # denormals really occurred
+    # a reset returns to the scaled form and everything still matches
+    assert np.array_equal(u32(env.expand(env.reset())), u32(ora.reset()))
+    for t in range(30):
+        a = torch.randint(0, 25, (N,), generator=gen)
+        o_ref, _, _ = ora.step(a.numpy())
+        obs, _, _, _ = env.step(a)
+        assert np.array_equal(u32(env.expand(obs)), u32(o_ref)), t
+    assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit()))
+    env.close()
+
+
+def test_v4_set_visit_arbitrary_values_then_steps(lmz, oracle_mod):
+    """lmz_set_visit takes TRUE values with no bound on how small they are (direct mode until the next reset):
+    tiny, denormal and > 1 values are averaged exactly like the oracle's float64 expression."""
+    N, T = 300, 60
+    ora = oracle_mod.OracleVec(oracle_mod.V4, N, seed=2, autoreset=False)
+    env = lmz.LmazeVecCuda(N, "v4", seed=2, autoreset=False)
+    env.reset(); ora.reset(want_obs=False)
+    rng = np.random.RandomState(0)
+    vis = (rng.rand(N, 18, 18).astype(np.float32) * np.float32(2.0) ** rng.randint(-149, 1, size=(N, 18, 18))).astype(np.float32)
+    vis[rng.rand(N, 18, 18) < 0.3] = 0.0
+    env.set_visit(vis)
+    for i in range(N):
+        ora.set_visit(i, vis[i])
+    assert np.array_equal(u32(env.get_visit()), u32(vis))
+    for t in range(T):
+        a = rng.randint(0, 25, size=N)
+        o_ref, _, _ = ora.step(a)
+        obs, _, _, _ = env.step(a)
+        assert np.array_equal(u32(obs), u32(o_ref)), t
+        assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), t
+    # checkpoint round trip in the middle of an episode: state + TRUE visit values into a fresh handle
+    env2 = lmz.LmazeVecCuda(N, "v4", seed=2, autoreset=False)
+    env2.set_state(env.get_state()); env2.set_visit(env.get_visit())
+    for t in range(10):
+        a = rng.randint(0, 25, size=N)
+        o1, _, _, _ = env.step(a); o2, _, _, _ = env2.step(a)
+        assert torch.equal(o1.view(torch.int32), o2.view(torch.int32))
+    assert torch.equal(env.get_visit().view(torch.int32), env2.get_visit().view(torch.int32))
+    env.close(); env2.close()
+
+
+def test_v5_visit_layer_many_averagings_without_planner(lmz, oracle_mod):
+    """lmaze-v5 averages the layer on EVERY step while the local episode is over (lmaze_env_v5.py:308-312): an actor
+    that keeps stepping without plannerStep averages it hundreds of times -- past VT_MAX and into the denormals."""
+    N, T = 600, 260
+    ora = oracle_mod.OracleHier(N, seed=9)
+    env = lmz.LmazeHierCuda(N, "v5", seed=9, autoreset=False)
+    assert np.array_equal(u32(env.reset()), u32(ora.reset()))
+    rng = np.random.RandomState(1)
+    g = rng.randint(0, 25, size=N)
+    env.plannerStep(g); ora.planner_step(g)
+    for t in range(T):
+        a = rng.randint(0, 4, size=N)
+        fov, loc, gr, lr, gd, ld, _, _ = env.step(a, goal_plane=False)
+        f_ref, l_ref, gr_ref, lr_ref, gd_ref, ld_ref, err = ora.step(a)
+        assert np.array_equal(u32(fov), u32(f_ref)), t
+        assert np.array_equal(ld.cpu().numpy(), ld_ref.astype(bool)), t
+        if t % 20 == 19 or t in (99, 100, 101, 102):
+            assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), t
+    assert int(ld_ref.sum()) > N // 2                          # most envs sat in "local episode over" for ~250 steps
+    vref = ora.export_visit()
+    assert int(((vref > 0) & (vref < 1.2e-38)).sum()) > 0      # denormals occurred
+    env.close()
+
+
+# ---------------------------------------------------------------- rollout kernels of the foveal variants
+@pytest.mark.parametrize("variant", ["v2", "v4"])
+def test_foveal_rollout_kernel_parity(lmz, oracle_mod, variant):
+    """lmz_rollout for lmaze-v2 / v4: T fused steps per launch, Philox actions (spec: DESIGN.md section 4) or a
+    [T,N] action buffer; per-step reward bits / done flags, final state, episode counters, v4's visit layer and
+    the observation rendered afterwards, all against the oracle stepped one call at a time."""
+    N, seed, T = 1537, 77, 70
+    ov = oracle_mod.V2 if variant == "v2" else oracle_mod.V4
+    ora = oracle_mod.OracleVec(ov, N, seed=seed, env_id0=3, autoreset=True, threads=os.cpu_count() or 1)
+    env = lmz.LmazeVecCuda(N, variant, seed=seed, env_id0=3, autoreset=True)
+    assert np.array_equal(u32(env.reset()), u32(ora.reset()))
+    t_glob = 0
+    for rnd in range(3):
+        if rnd == 1:                                           # caller-supplied actions (incl. a few out of range: clamped + counted)
+            acts = np.random.RandomState(rnd).randint(0, 25, size=(T, N))
+            acts[5, :7] = 30
+            rew, done = env.rollout(T, actions=torch.as_tensor(acts))
+        elif rnd == 2:
+            acts = np.array([[oracle_mod.rng_action25(seed, 3 + i, t_glob + t) for i in range(N)] for t in range(T)])
+            codes, done = env.rollout(T, reward_codes=True)
+            rew = env.reward_table("cuda")[codes.long()]
+        else:
+            acts = np.array([[oracle_mod.rng_action25(seed, 3 + i, t_glob + t) for i in range(N)] for t in range(T)])
+            rew, done = env.rollout(T)
+        t_glob += T
+        for t in range(T):
+            _, r_ref, d_ref = ora.step(acts[t], want_obs=False)
+            assert np.array_equal(rbits(rew[t]), r_ref.view(np.uint32)), (rnd, t)
+            assert np.array_equal(done[t].cpu().numpy().view(np.uint8), d_ref), (rnd, t)
+        st = env.get_state().cpu().numpy()
+        pos, sc, _, _ = ora.export()
+        assert np.array_equal(st[:, 0:4], pos) and np.array_equal(st[:, 4], sc) and np.array_equal(st[:, 7], ora.episode)
+        if variant == "v4":
+            assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), rnd
+        full = np.stack([ora.render_one(i) for i in range(N)])
+        assert np.array_equal(u32(env.render_obs()), u32(full)), rnd
+    s = env.stats(check_errors=False)
+    assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist() and s["episodes"] > N
+    # ... and ordinary steps continue from the rolled-out state
+    a = np.random.RandomState(9).randint(0, 25, size=N)
+    o_ref, r_ref, _ = ora.step(a)
+    obs, rew, _, _ = env.step(a)
+    assert np.array_equal(u32(obs), u32(o_ref)) and np.array_equal(rbits(rew), r_ref.view(np.uint32))
+    env.close()
+
+
+@pytest.mark.parametrize("philox", [True, False])
+def test_hier_rollout_kernel_parity(lmz, oracle_mod, philox):
+    """lmz_hier_rollout (lmaze-v5 / v6): per step plannerStep for the envs waiting for their planner, then step(),
+    auto-reset on globalDone; both rewards and both done flags per step, final state words and visit layer."""
+    N, seed, T = 1201, 5, 90
+    ora = oracle_mod.OracleHier(N, seed=seed, env_id0=40)
+    env = lmz.LmazeHierCuda(N, "v5", seed=seed, env_id0=40, autoreset=True)
+    assert np.array_equal(u32(env.reset()), u32(ora.reset()))
+    t_glob = 0
+    for rnd in range(2):
+        if philox:
+            ga = np.array([[oracle_mod.rng_hier(seed, 40 + i, t_glob + t) for i in range(N)] for t in range(T)])
+            goals, acts = ga[:, :, 0], ga[:, :, 1]
+            gr, lr, gd, ld = env.rollout(T)
+        else:
+            rs = np.random.RandomState(rnd)
+            goals, acts = rs.randint(0, 25, size=(T, N)), rs.randint(0, 5, size=(T, N))     # 4 = unmatched action: no move
+            gr, lr, gd, ld = env.rollout(T, goals=torch.as_tensor(goals), actions=torch.as_tensor(acts))
+        t_glob += T
+        for t in range(T):
+            st = ora.export()
+            need = (((st[:, 15] >> 1) & 1) | (st[:, 14] == 0)).astype(np.uint8)          # localDone, or no plannerStep since reset
+            if need.any():
+                ora.planner_step(goals[t], mask=need)
+            _, _, gr_ref, lr_ref, gd_ref, ld_ref, _ = ora.step(acts[t])
+            assert np.array_equal(rbits(gr[t]), gr_ref.view(np.uint32)) and np.array_equal(rbits(lr[t]), lr_ref.view(np.uint32)), (rnd, t)
+            assert np.array_equal(gd[t].cpu().numpy(), gd_ref.astype(bool)) and np.array_equal(ld[t].cpu().numpy(), ld_ref.astype(bool)), (rnd, t)
+            if gd_ref.any():
+                ora.reset(mask=gd_ref, want_obs=False)
+        st, ref = env.get_state().cpu().numpy(), ora.export()
+        assert np.array_equal(st[:, :13], ref[:, :13]) and np.array_equal(st[:, 15], ref[:, 15])
+        assert np.array_equal(np.minimum(st[:, 13:15], 255), np.minimum(ref[:, 13:15], 255))
+        assert np.array_equal(st[:, 16].astype(np.uint32), ora.episode)
+        assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), rnd
+        fov_ref, loc_ref, err_ref = ora.render()
+        env.render_obs()
+        assert np.array_equal(u32(env.obs), u32(fov_ref)) and np.array_equal(u32(env.loc_obs), u32(loc_ref))
+    assert env.stats(check_errors=False)["steps"] == 2 * T * N
+    env.close()
+
+
+@pytest.mark.parametrize("variant", ["v2", "v4", "v5"])
+def test_foveal_rollout_soak_and_shards(lmz, variant):
+    """65,536 envs x 600 rolled-out steps in chunks == the same envs stepped through the fused step kernel with the
+    same action stream (the two kernels share one transition), and two half-batch handles == the whole batch."""
+    N, T, chunks = 1 << 16, 120, 5
+    hier = variant == "v5"
+    mk = (lambda n, id0: lmz.LmazeHierCuda(n, "v5", seed=12, env_id0=id0, obs_mode="compact")) if hier else \
+         (lambda n, id0: lmz.LmazeVecCuda(n, variant, seed=12, env_id0=id0, obs_mode="compact"))
+    whole, lo, hi = mk(N, 0), mk(N // 2, 0), mk(N // 2, N // 2)
+    for e in (whole, lo, hi):
+        e.reset()
+    for c in range(chunks):
+        outs = [e.rollout(T) for e in (whole, lo, hi)]
+        for k in range(len(outs[0])):
+            assert torch.equal(outs[0][k], torch.cat([outs[1][k], outs[2][k]], dim=1)), (c, k)
+    assert torch.equal(whole.get_state(), torch.cat([lo.get_state(), hi.get_state()]))
+    sw = whole.stats(check_errors=False)
+    sl, sh = lo.stats(check_errors=False), hi.stats(check_errors=False)
+    assert all(sw[k] == sl[k] + sh[k] for k in sw) and sw["steps"] == N * T * chunks and sw["episodes"] > N
+    # replay the first chunk of a fresh handle through the step kernel with the recorded... Philox stream
+    if not hier:
+        from oracle import oracle as O
+        a = mk(4096, 0); b = mk(4096, 0)
+        a.reset(); b.reset()
+        rew, done = a.rollout(40)
+        ids = np.arange(4096, dtype=np.uint64)
+        for t in range(40):
+            acts = np.array([O.rng_action25(12, int(i), t) for i in ids[:4096]])
+            _, r, d, _ = b.step(acts)
+            assert torch.equal(r.view(torch.int32), rew[t].view(torch.int32)) and torch.equal(d, done[t]), t
+        assert torch.equal(a.get_state(), b.get_state())
+        if variant == "v4":
+            assert torch.equal(a.get_visit().view(torch.int32), b.get_visit().view(torch.int32))
+        a.close(); b.close()
+    for e in (whole, lo, hi):
+        e.close()
