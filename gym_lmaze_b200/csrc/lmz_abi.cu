@@ -392,7 +392,7 @@ int launch_env_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 
 // default CTA size of the foveal render kernel per variant (1 producer warp + the rendering warps)
 #ifndef LMZ_FOV_THREADS
-#define LMZ_FOV_THREADS(id) ((id) == 2 ? 128 : (id) == 4 ? 128 : 160)
+#define LMZ_FOV_THREADS(id) 128      /* v2, v4, v5 alike: 1 producer + 3 rendering warps (tools/fov_sweep2.py) */
 #endif
 
 template <class W, int THREADS>
@@ -457,7 +457,10 @@ int launch_fov_small(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
     configured_dev = h->cfg.device;
   }
   const int64_t units = p.tile_end - p.tile_begin;
-  int per_sm = h->cfg.tune[2] > 0 ? h->cfg.tune[2] : ctas_per_sm;
+  // resident CTAs per SM (tools/fov_compact_sweep.py): v2 writes through the TMA engine only, and ONE 4-warp CTA per
+  // SM streams more (11.5 G env-steps/s) than the three that fit (9.2 G) -- fewer writers, higher write bandwidth;
+  // the visit variants and the launches that write nothing are latency-bound and want every CTA that fits
+  int per_sm = h->cfg.tune[2] > 0 ? h->cfg.tune[2] : ((W::NVIS == 0 && p.obs != nullptr) ? 1 : ctas_per_sm);
   if (per_sm > ctas_per_sm) per_sm = ctas_per_sm;
   int64_t grid = (int64_t)h->num_sms * per_sm;
   const int64_t need = (units + THREADS / 32 - 1) / (THREADS / 32);

@@ -56,6 +56,35 @@ struct VisitFetch {
   float cur[25], prv[25];
 };
 
+// reset (324 cells rewritten) and direct-mode full passes of the tile's envs, warp-cooperatively; true if any ran
+template <class W>
+__device__ __forceinline__ bool visit_full_passes(const KParams &p, int64_t e0, int lane, uint32_t op, int tpre, int bx, int by) {
+  constexpr int GG = W::G * W::G;
+  unsigned full = __ballot_sync(0xffffffffu, op == VOP_RESET || op == VOP_FULL);
+  if (!full) return false;
+  while (full) {
+    const int src = __ffs(full) - 1;
+    full &= full - 1;
+    const uint32_t sop = __shfl_sync(0xffffffffu, op, src);
+    const int sx = __shfl_sync(0xffffffffu, bx, src), sy = __shfl_sync(0xffffffffu, by, src);
+    const float down = visit_scale_down(__shfl_sync(0xffffffffu, tpre, src));
+    float4 *row = reinterpret_cast<float4 *>(p.visit + (e0 + src) * GG);          // 1,296 B per env: 16-byte aligned
+    for (int c4 = lane; c4 < GG / 4; c4 += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sop == VOP_FULL) v = __ldcg(row + c4);
+      float *q = reinterpret_cast<float *>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cell = 4 * c4 + k, x = cell / W::G, y = cell - x * W::G;
+        const bool in_cur = (unsigned)(x - sx + 2) < 5u && (unsigned)(y - sy + 2) < 5u;
+        q[k] = (sop == VOP_FULL) ? visit_average(__fmul_rn(q[k], down), in_cur) : W::visit_reset_stored(in_cur);
+      }
+      __stcg(row + c4, v);
+    }
+  }
+  return true;
+}
+
 template <class W>
 __device__ __forceinline__ void visit_issue(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
                                             uint32_t vinfo, bool want_planes, VisitFetch &f) {
@@ -63,30 +92,7 @@ __device__ __forceinline__ void visit_issue(const KParams &p, int64_t e0, int la
   const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
   const int tpre = (vinfo >> 3) & 127;
   const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-  unsigned full = __ballot_sync(0xffffffffu, op == VOP_RESET || op == VOP_FULL);
-  if (full) {
-    while (full) {
-      const int src = __ffs(full) - 1;
-      full &= full - 1;
-      const uint32_t sop = __shfl_sync(0xffffffffu, op, src);
-      const int sx = __shfl_sync(0xffffffffu, bx, src), sy = __shfl_sync(0xffffffffu, by, src);
-      const float down = visit_scale_down(__shfl_sync(0xffffffffu, tpre, src));
-      float4 *row = reinterpret_cast<float4 *>(p.visit + (e0 + src) * GG);        // 1,296 B per env: 16-byte aligned
-      for (int c4 = lane; c4 < GG / 4; c4 += 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sop == VOP_FULL) v = __ldcg(row + c4);
-        float *q = reinterpret_cast<float *>(&v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int cell = 4 * c4 + k, x = cell / W::G, y = cell - x * W::G;
-          const bool in_cur = (unsigned)(x - sx + 2) < 5u && (unsigned)(y - sy + 2) < 5u;
-          q[k] = (sop == VOP_FULL) ? visit_average(__fmul_rn(q[k], down), in_cur) : W::visit_reset_stored(in_cur);
-        }
-        __stcg(row + c4, v);
-      }
-    }
-    __syncwarp();                                         // the cooperative stores are visible to the owning lane
-  }
+  if (visit_full_passes<W>(p, e0, lane, op, tpre, bx, by)) __syncwarp();   // the cooperative stores are visible to the owning lane
   if (!valid || op == VOP_RESET || (op != VOP_AVG && !want_planes)) return;
   const float *vis = p.visit + (e0 + lane) * GG;
 #pragma unroll
@@ -138,6 +144,104 @@ __device__ __forceinline__ void visit_finish(const KParams &p, int64_t e0, int l
   }
 }
 
+// ---- the same two halves with the TMA engine doing the memory traffic (the full-render kernel) -----------------
+// In the render kernel the LSU / L1TEX pipe belongs to the rendering warps' 128-bit stores: 75 uncoalesced 4-byte
+// accesses per env from the producer (32 different sectors per warp instruction) sit in that pipe for ~2,400 cycles
+// per tile and stall the renderers on their store-data registers (ncu: long_scoreboard on the store loop, 15 % barrier
+// wait; v4 172 M env-steps/s against 218 M with the layer switched off).  So here a window travels as its BAND -- the
+// five 72-byte grid rows that hold it, 368 bytes from a 16-byte aligned start -- by cp.async.bulk: global -> shared
+// in stage A (completion on an mbarrier), the 25 cells are updated in shared memory in stage B and the band goes
+// back with one shared -> global bulk copy.  No LSU instruction touches the layer (resets / direct mode aside).
+constexpr uint32_t VBAND_BYTES = 368, VBAND_FLOATS = VBAND_BYTES / 4;
+// byte offset of the band of the window centred on row x, rounded down to 16 (the band then never leaves the env's
+// 1,296-byte layer: rounding only happens for even x - 2, i.e. x <= 14)
+__device__ __forceinline__ uint32_t vband_off(int x) { return ((uint32_t)(x - 2) * 72u) & ~15u; }
+
+// bands: this stage's [32][2][VBAND_FLOATS] floats in shared memory; bar: this stage's mbarrier (count 1)
+template <class W>
+__device__ __forceinline__ void visit_issue_tma(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                                uint32_t vinfo, bool want_planes, float *bands, uint64_t *bar) {
+  constexpr int GG = W::G * W::G;
+  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
+  const int tpre = (vinfo >> 3) & 127;
+  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31;
+  if (visit_full_passes<W>(p, e0, lane, op, tpre, bx, by)) {
+    asm volatile("fence.proxy.async;" ::: "memory");      // the generic-proxy stores precede the async-proxy loads below
+    __syncwarp();
+  }
+  const bool need_cur = valid && op != VOP_RESET && (op == VOP_AVG || want_planes);
+#ifdef LMZ_DEBUG_NO_PREV                     // (tuning builds only)
+  const bool need_prv = false;
+#else
+  const bool need_prv = valid && op != VOP_RESET && want_planes;
+#endif
+  const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, need_cur)) + __popc(__ballot_sync(0xffffffffu, need_prv));
+  if (lane == 0) mbar_expect_tx(bar, cnt * VBAND_BYTES);   // arrives; with cnt == 0 the phase completes at once
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this buffer's previous write-back has left shared memory
+  const unsigned char *vis = reinterpret_cast<const unsigned char *>(p.visit + (e0 + lane) * GG);
+  float *mine = bands + lane * (2 * VBAND_FLOATS);
+  if (need_cur) bulk_g2s(mine, vis + vband_off(bx), VBAND_BYTES, bar);
+  if (need_prv) bulk_g2s(mine + VBAND_FLOATS, vis + vband_off(px), VBAND_BYTES, bar);
+}
+
+template <class W>
+__device__ __forceinline__ void visit_finish_tma(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                                 uint32_t vinfo, bool want_planes, float *bands, uint64_t *bar,
+                                                 uint32_t parity, float *plane_cur, float *plane_prev) {
+  constexpr int GG = W::G * W::G;
+  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
+  const int tpre = (vinfo >> 3) & 127, tpost = (vinfo >> 10) & 127;
+  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
+  mbar_wait(bar, parity);                                  // the tile's bands have landed
+  float *mine = bands + lane * (2 * VBAND_FLOATS);
+  if (valid && op == VOP_RESET) {                          // the layer was just rewritten: values known
+    if (want_planes) {
+#pragma unroll
+      for (int k = 0; k < 25; ++k) {
+        const int ax = px - 2 + k / 5, ay = py - 2 + k % 5;
+        const bool in_cur = (unsigned)(ax - bx + 2) < 5u && (unsigned)(ay - by + 2) < 5u;
+        plane_cur[k] = W::visit_reset(true);
+        plane_prev[k] = W::visit_reset(in_cur);
+      }
+    }
+  } else if (valid && (op == VOP_AVG || want_planes)) {
+    // cell (bx - 2 + i, by - 2 + j) of the layer = float (bx - 2 + i) * 18 + by - 2 + j - band offset / 4 of the band
+    float *wc = mine + ((bx - 2) * W::G + (by - 2)) - (int)(vband_off(bx) >> 2);
+    float cur[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) cur[k] = wc[(k / 5) * W::G + k % 5];
+    if (op == VOP_AVG) {                                   // s' = RN(s + 2^T) on the window, nothing else changes
+      const float add = __int_as_float((127 + tpre) << 23);
+#pragma unroll
+      for (int k = 0; k < 25; ++k) { cur[k] = __fadd_rn(cur[k], add); wc[(k / 5) * W::G + k % 5] = cur[k]; }
+    }
+    if (want_planes) {
+      const float down = visit_scale_down(tpost);
+      const float *wp = mine + VBAND_FLOATS + ((px - 2) * W::G + (py - 2)) - (int)(vband_off(px) >> 2);
+#pragma unroll
+      for (int k = 0; k < 25; ++k) plane_cur[k] = __fmul_rn(cur[k], down);
+      const int ox = px - bx, oy = py - by;                // previous window relative to the current one
+#pragma unroll
+      for (int k = 0; k < 25; ++k) {
+        const int dx = ox + k / 5, dy = oy + k % 5;
+        const bool in_cur = (unsigned)dx < 5u && (unsigned)dy < 5u;
+        plane_prev[k] = in_cur ? plane_cur[in_cur ? dx * 5 + dy : 0] : __fmul_rn(wp[(k / 5) * W::G + k % 5], down);
+      }
+    }
+  }
+  // write the updated band back: shared -> global bulk copy (the other cells of the band go back unchanged)
+#ifdef LMZ_DEBUG_NO_WB                       // (tuning builds only)
+  const bool wb = false;
+#else
+  const bool wb = valid && op == VOP_AVG;
+#endif
+  if (wb) {
+    fence_proxy_async();                                   // this lane's shared-memory writes -> async proxy
+    bulk_s2g(reinterpret_cast<unsigned char *>(p.visit + (e0 + lane) * GG) + vband_off(bx), smem_addr(mine), VBAND_BYTES);
+  }
+  bulk_commit();                                           // one group per stage B and lane, empty or not
+}
+
 template <class W>
 __device__ __forceinline__ void visit_warp(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
                                            uint32_t vinfo, bool want_planes, float *plane_cur, float *plane_prev) {
@@ -176,6 +280,7 @@ template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t vbar[2];    // visit bands of the two pipeline stages
   __shared__ uint32_t s_flags[2][2];         // [buf][0 obs, 1 local obs]: bit l = env l of the tile is written
   __shared__ long long s_tile[2];
   constexpr int PROD = (W::NVIS > 0) ? LMZ_VISIT_PROD : LMZ_V2_PROD;   // threads that never render
@@ -183,9 +288,12 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   static_assert(CTHREADS >= 32, "need at least one rendering warp");
   static_assert((uint32_t)CTHREADS < W::OBS_FLOATS, "index stepping assumes fewer threads than entries");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (W::NVIS > 0 && tid == 0) { mbar_init(&vbar[0], 1); mbar_init(&vbar[1], 1); }   // fenced + synced inside stage_blob
   stage_blob<W>(smem, &bar, p.blob);
   const FovTables<W> t(smem);
   float *vals = reinterpret_cast<float *>(smem + W::BLOB_BYTES);          // [2][32][NSLOT][25]
+  float *vbands = vals + 2 * 32 * W::VALS;                                // [2][32][2][VBAND_FLOATS]: landing zone of the visit bands
+  uint32_t vphase = 0, vstage = 0;                                        // warp 0: mbarrier parities, stage stage A fills next
   const int64_t tiles = p.tile_end;
   const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
   WarpStats ws;
@@ -215,7 +323,6 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   FovLane<W::NBIT> pv;                       // warp 0: stage A's results for the tile stage B completes next
   pv.o.st = 0; pv.o.st_old = 0; pv.o.render = false; pv.o.done = false; pv.o.cls = -1; pv.o.eplen = 0;
   pv.info = 0; pv.vinfo = 0; pv.rfov = false; pv.rloc = false;
-  VisitFetch vf;
   int64_t ptile = 0;
   bool pvalid = false;
   auto stage_a = [&]() {                     // warp 0 only
@@ -230,8 +337,10 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, smem, pre);
     if (p.mode == MODE_STEP) ws.add(valid, v.o);
 #ifndef LMZ_DEBUG_NO_VISIT                   // (tuning builds only: how fast is the kernel without the visit layer?)
-    if (W::NVIS > 0 && need_visit) visit_issue<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf);
+    if (W::NVIS > 0 && need_visit)
+      visit_issue_tma<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vbands + vstage * (32 * 2 * VBAND_FLOATS), &vbar[vstage]);
 #endif
+    vstage ^= 1u;
     pv = v; ptile = tl; pvalid = valid;
     prefetch(tl_after);
   };
@@ -240,8 +349,12 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     const bool valid = pvalid;
     float *mv = vals + (buf * 32 + lane) * W::VALS;
 #ifndef LMZ_DEBUG_NO_VISIT
-    if (W::NVIS > 0 && need_visit)           // window update of the scaled layer + the two 5x5 visit crops
-      visit_finish<W>(p, ptile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf, mv + W::VIS_SLOT0 * 25, mv + W::VIS_SLOT1 * 25);
+    if (W::NVIS > 0 && need_visit) {         // window update of the scaled layer + the two 5x5 visit crops
+      const uint32_t st = vstage ^ 1u;       // the buffer this tile's stage A filled (stage A toggled vstage afterwards)
+      visit_finish_tma<W>(p, ptile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vbands + st * (32 * 2 * VBAND_FLOATS),
+                          &vbar[st], (vphase >> st) & 1u, mv + W::VIS_SLOT0 * 25, mv + W::VIS_SLOT1 * 25);
+      vphase ^= 1u << st;
+    }
 #endif
     if (valid && (v.rfov || v.rloc)) {       // 25-bit planes -> float planes (lane stride VALS is odd: no bank conflicts)
 #pragma unroll
@@ -337,6 +450,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     }
   }
   if (warp == 0) {
+    if (W::NVIS > 0) bulk_wait_all();        // the last bands have left shared memory (and reached global memory)
     if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
     if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
   }
@@ -352,7 +466,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
 // window of each env's scaled visit layer itself (v4 / v5, visit_warp), and ASSEMBLES the tile's 32 rows in shared
 // memory exactly as they lie in the tensor (lane l expands env l's 25-bit planes into floats, the visit crops land
 // in their planes directly).  The tile's rows are one contiguous, 16-byte aligned run of the tensor, so the copy
-// out is a flat LDS.128 -> st.global.cs.v4 loop with no per-float indexing at all.  (Round 1 looked every float up
+// out is ONE shared -> global bulk copy (cp.async.bulk) per tile: no per-float indexing and no store instruction.  (Round 1 looked every float up
 // through (plane, cell) index arithmetic and was math-pipe bound at 74 % issue-slot use, 4.7 TB/s on v2.)
 template <class W>
 struct FovSmall {
@@ -395,10 +509,16 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     q.w0 = q.w1 = q.w2 = 0u; q.act = 0;
     if (tl < tiles && e < p.n) q = fov_preload<W>(p, e);
   };
-  // flat copy of `n4` float4s of the warp's smem tile to global (both 16-byte aligned)
-  auto copy_out = [&](float *dst, uint32_t n4) {
-#pragma unroll 4
-    for (uint32_t q = lane; q < n4; q += 32) st_stream_v4(reinterpret_cast<unsigned char *>(dst) + ((size_t)q << 4), lds_v4(rows_s + (q << 4)));
+  // copy of the first `bytes` of the warp's smem tile to global (both 16-byte aligned): ONE shared -> global bulk
+  // copy issued by lane 0 -- the TMA engine moves the tile's rows as one contiguous run, no LSU store is issued
+  auto copy_out = [&](float *dst, uint32_t bytes) {
+    fence_proxy_async();                                         // every lane's row writes -> async proxy
+    __syncwarp();
+    if (lane == 0) { bulk_s2g(dst, rows_s, bytes); bulk_commit(); }
+  };
+  auto rows_free = [&]() {                                       // the last bulk copy has finished READING the rows
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
   };
   // Software pipeline over the warp's tiles (the visit variants): the transitions of tile t+1 run -- and its visit-
   // window loads are started -- BEFORE tile t's rows are expanded and copied out, so the loads' DRAM round trip
@@ -438,10 +558,11 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
     const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
     float *mine = rows + lane * PER;
-    __syncwarp();                                                // the previous tile's copy out has read the buffer
+    if (W::NVIS == 0) stage_a(nxt);                              // v2: the next tile's transitions overlap the draining copy
+    rows_free();                                                 // the previous tile's copy out has read the buffer
     if (W::NVIS > 0 && need_visit)                               // window update of the scaled layer + the two crops
       visit_finish<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf, mine + W::VIS_SLOT0 * 25, mine + W::VIS_SLOT1 * 25);
-    stage_a(nxt);                                                // next tile: transitions, visit loads in flight
+    if (W::NVIS > 0) stage_a(nxt);                               // next tile: transitions, visit loads in flight
     const int64_t row0 = tile * 32 - p.win_lo;                   // obs row of the tile's first env
     if (ff) {
       if (valid && v.rfov) {                                     // 25-bit planes -> float planes (stride PER is odd: no bank conflicts)
@@ -454,19 +575,20 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
           for (int c = 0; c < 25; ++c) pl[c] = ((m >> c) & 1u) ? 1.0f : 0.0f;
         }
       }
-      __syncwarp();
       float *dst = reinterpret_cast<float *>(p.obs) + row0 * (int64_t)PER;
-      if (ff == 0xffffffffu && (row0 & 3) == 0) copy_out(dst, 32 * PER / 4);
-      else                                                       // batch tail, masked reset, window edge
+      if (ff == 0xffffffffu && (row0 & 3) == 0) copy_out(dst, 32 * PER * 4);
+      else {                                                     // batch tail, masked reset, window edge
+        __syncwarp();
         for (unsigned m = ff; m; m &= m - 1) {
           const uint32_t env = __ffs(m) - 1;
           for (uint32_t pos = lane; pos < PER; pos += 32) __stcs(dst + env * PER + pos, rows[env * PER + pos]);
         }
+      }
     }
     if (W::HAS_LOC && fl) {
       // local obs (lmaze_env_v5.py:360-368): free crop, ball and previous ball relative to the planner-time fovea,
       // fovealGoal = bit planes 7, 5, 6, 8 (all-zero on an IndexError row); 400 bytes per env, always 16-byte aligned
-      __syncwarp();                                              // the foveal rows have been copied out
+      rows_free();                                               // the foveal rows have been copied out
       float *minel = rows + lane * PERL;
       if (valid && v.rloc) {
 #pragma unroll
@@ -476,17 +598,19 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
           for (int c = 0; c < 25; ++c) minel[c4 * 25 + c] = ((m >> c) & 1u) ? 1.0f : 0.0f;
         }
       }
-      __syncwarp();
       float *dst = reinterpret_cast<float *>(p.obs2) + row0 * (int64_t)PERL;
-      if (fl == 0xffffffffu) copy_out(dst, 32 * PERL / 4);
-      else
+      if (fl == 0xffffffffu) copy_out(dst, 32 * PERL * 4);
+      else {
+        __syncwarp();
         for (unsigned m = fl; m; m &= m - 1) {
           const uint32_t env = __ffs(m) - 1;
           for (uint32_t pos = lane; pos < PERL; pos += 32) __stcs(dst + env * PERL + pos, rows[env * PERL + pos]);
         }
+      }
     }
     cur = nxt;
   }
+  if (lane == 0) bulk_wait_all();                                // the last tile's rows have left shared memory
   if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
   if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x * WARPS);
 }

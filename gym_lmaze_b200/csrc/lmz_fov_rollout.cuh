@@ -149,7 +149,7 @@ __device__ __forceinline__ void rollout_env_v5(const KParams &p, int64_t e, cons
 
 template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_fov_rollout_kernel(const KParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];          // the per-maze tables (blob from ROWBITS_OFF on)
+  extern __shared__ __align__(128) unsigned char smem[];         // the per-maze tables (blob from ROWBITS_OFF on)
   __shared__ unsigned long long blk_stats[NUM_STATS];
   constexpr uint32_t STAGE_OFF = W::ROWBITS_OFF;
   for (uint32_t i = threadIdx.x; i < (W::BLOB_BYTES - STAGE_OFF) / 4; i += THREADS)

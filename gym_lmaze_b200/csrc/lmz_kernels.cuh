@@ -781,21 +781,31 @@ __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) 
           // The plane holds ONE block of ones, so every element's value follows from the new position.  Rewrite
           // whole aligned 32-byte sectors around the old and the new block (values computed, not read): full-sector
           // writes need no read-modify-write in L2/DRAM, and where the two regions share a sector both write the
-          // same values.  ONE loop covers both blocks: half-warp 0 walks the E rows of the old block, half-warp 1
-          // those of the new one, lane & 15 = the float's slot in the row's <= 64-byte sector span.  A sector may
-          // reach into the neighbouring row; those floats lie in the maze's border columns, which a block never
-          // touches (the border cells are walls), so "column relative to this row" decides the value with no divide.
+          // same values.  ONE loop covers both blocks.  A sector may reach into the neighbouring row; those floats lie in
+          // the maze's border columns, which a block never touches (the border cells are walls), so "column relative
+          // to this row" decides the value with no divide.
           float *plane = img + (size_t)ch * V::S * V::S;            // 32-byte aligned (plane = 28,224 / 20,736 B)
-          const int sel = lane >> 4, j = lane & 15;
-          const int brow = sel ? r1 : r0, bcol = sel ? q1 : q0;
-          int first = brow * V::S + bcol;                           // the row segment [first, first + E)
+          // 2 * E rows (E of the old block, then E of the new one), each a span of <= 16 floats = <= 4 float4s:
+          // 4 lanes per row, 8 rows per warp pass, 128-bit stores
 #pragma unroll
-          for (int rr = 0; rr < V::E; ++rr, first += V::S) {
+          for (int it = 0; it < (2 * V::E * 4 + 31) / 32; ++it) {
+            const int idx = it * 32 + lane, rid = idx >> 2, q = idx & 3;
+            const bool nw = rid >= V::E;                            // this row belongs to the new block
+            const int rr = nw ? rid - V::E : rid;
+            const int brow = nw ? r1 : r0, bcol = nw ? q1 : q0;
+            const int first = (brow + rr) * V::S + bcol;            // the row segment [first, first + E)
             const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
-            const int e = lo + j;
-            const int c = e - first + bcol;                         // column in row brow + rr (may run over: border)
-            const bool one = (unsigned)(c - q1) < (unsigned)V::E && (unsigned)(brow + rr - r1) < (unsigned)V::E;
-            if (e < hi) plane[e] = one ? 1.0f : 0.0f;
+            const int e = lo + 4 * q;
+            if (rid < 2 * V::E && e < hi) {
+              const int c = e - first + bcol;                       // column of the float4's first float (may run over: border)
+              const bool row_in = (unsigned)(brow + rr - r1) < (unsigned)V::E;
+              float4 v;
+              v.x = (row_in && (unsigned)(c - q1) < (unsigned)V::E) ? 1.0f : 0.0f;
+              v.y = (row_in && (unsigned)(c + 1 - q1) < (unsigned)V::E) ? 1.0f : 0.0f;
+              v.z = (row_in && (unsigned)(c + 2 - q1) < (unsigned)V::E) ? 1.0f : 0.0f;
+              v.w = (row_in && (unsigned)(c + 3 - q1) < (unsigned)V::E) ? 1.0f : 0.0f;
+              *reinterpret_cast<float4 *>(plane + e) = v;
+            }
           }
         }
       }

@@ -52,7 +52,7 @@ struct Fov {
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5]
   static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;                           // u16 [5]: each maze's 'X' cell
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
-  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;   // + the double-buffered per-env value planes
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * 2 * 368 : 0);   // + the double-buffered per-env value planes
   static constexpr int VT_RESET = 1;                                   // v4 reset(): zeros, then ONE averaging (lmaze_env_v4.py:110-119)
 };
 using V2 = Fov<2, 5>;

@@ -381,6 +381,9 @@ def test_v3_string_actions(lmz, oracle_mod):
 # ---------------------------------------------------------------- BASELINE config 3 scale: 2^20 envs, size-independent properties
 def test_one_million_envs_properties(lmz, oracle_mod):
     N = 1 << 20
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()             # earlier tests' tensors sit in torch's caching allocator
     free_b = torch.cuda.mem_get_info()[0]
     need = N * 112896 + (4 << 30)
     if free_b < need:
@@ -640,9 +643,8 @@ def test_v2_windows_and_masks(lmz, oracle_mod):
         assert np.array_equal(rbits(rew), r_ref.view(np.uint32))
         assert torch.equal(obs.cpu(), torch.from_numpy(o_ref[lo:lo + W])), t
         assert torch.equal(env.render_window(N - W).cpu(), torch.from_numpy(o_ref[N - W:]))
-    from gym_lmaze_b200._abi import LmzError
-    with pytest.raises(LmzError, match="not built"):
-        env.rollout(4)
+    rew, done = env.rollout(4)                      # (round 2: the foveal variants have a rollout kernel too)
+    assert tuple(rew.shape) == (4, N) and tuple(done.shape) == (4, N)
     env.close()
     # out-of-range actions are clamped and reported
     env = lmz.LmazeVecCuda(8, "v2", seed=1)
