@@ -785,18 +785,11 @@ __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) 
           // the maze's border columns, which a block never touches (the border cells are walls), so "column relative
           // to this row" decides the value with no divide.
           float *plane = img + (size_t)ch * V::S * V::S;            // 32-byte aligned (plane = 28,224 / 20,736 B)
-          // 2 * E rows (E of the old block, then E of the new one), each a span of <= 16 floats = <= 4 float4s:
-          // 4 lanes per row, 8 rows per warp pass, 128-bit stores
-#pragma unroll
-          for (int it = 0; it < (2 * V::E * 4 + 31) / 32; ++it) {
-            const int idx = it * 32 + lane, rid = idx >> 2, q = idx & 3;
-            const bool nw = rid >= V::E;                            // this row belongs to the new block
-            const int rr = nw ? rid - V::E : rid;
-            const int brow = nw ? r1 : r0, bcol = nw ? q1 : q0;
-            const int first = (brow + rr) * V::S + bcol;            // the row segment [first, first + E)
-            const int lo = first & ~7, hi = (first + V::E + 7) & ~7;
+          auto put = [&](int brow, int rr, int bcol, int width, int q) {
+            const int first = (brow + rr) * V::S + bcol;            // the row segment [first, first + width)
+            const int lo = first & ~7, hi = (first + width + 7) & ~7;
             const int e = lo + 4 * q;
-            if (rid < 2 * V::E && e < hi) {
+            if (e < hi) {
               const int c = e - first + bcol;                       // column of the float4's first float (may run over: border)
               const bool row_in = (unsigned)(brow + rr - r1) < (unsigned)V::E;
               float4 v;
@@ -805,6 +798,26 @@ __global__ void __launch_bounds__(THREADS) lmz_env_incr_kernel(const KParams p) 
               v.z = (row_in && (unsigned)(c + 2 - q1) < (unsigned)V::E) ? 1.0f : 0.0f;
               v.w = (row_in && (unsigned)(c + 3 - q1) < (unsigned)V::E) ? 1.0f : 0.0f;
               *reinterpret_cast<float4 *>(plane + e) = v;
+            }
+          };
+          if (r0 == r1 && (q0 - q1 == V::E || q1 - q0 == V::E)) {
+            // a one-cell move along the row: the two blocks are side by side -- ONE box of E rows x 2E floats
+            // (<= 24 floats = 6 float4s per row, 8 lanes per row): a third fewer sectors than two separate boxes,
+            // and the step is bound by the number of scattered 32-byte sectors it writes
+            const int bcol = q0 < q1 ? q0 : q1;
+#pragma unroll
+            for (int it = 0; it < (V::E * 8 + 31) / 32; ++it) {
+              const int idx = it * 32 + lane, rr = idx >> 3;
+              if (rr < V::E) put(r0, rr, bcol, 2 * V::E, idx & 7);
+            }
+          } else {
+            // 2 * E rows (E of the old block, then E of the new one), each a span of <= 16 floats = <= 4 float4s:
+            // 4 lanes per row, 8 rows per warp pass
+#pragma unroll
+            for (int it = 0; it < (2 * V::E * 4 + 31) / 32; ++it) {
+              const int idx = it * 32 + lane, rid = idx >> 2;
+              const bool nw = rid >= V::E;                          // this row belongs to the new block
+              if (rid < 2 * V::E) put(nw ? r1 : r0, nw ? rid - V::E : rid, nw ? q1 : q0, V::E, idx & 3);
             }
           }
         }
