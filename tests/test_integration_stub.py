@@ -18,6 +18,8 @@ def load_stub():
     exec(compile(code, "INTEGRATION.md", "exec"), ns)
     hier = re.search(r"```python\n(# gym_lmaze/envs/lmaze_env_v5_cuda\.py.*?)```", md, re.S).group(1)
     exec(compile(hier, "INTEGRATION.md (v5)", "exec"), ns)
+    host = re.search(r"```python\n(# gym_lmaze/envs/lmaze_env_cuda_host\.py.*?)```", md, re.S).group(1)
+    exec(compile(host, "INTEGRATION.md (host pipeline)", "exec"), ns)
     return ns, _abi
 
 
@@ -63,4 +65,31 @@ def test_hier_stub_runs_and_matches_the_package():
         for x, y in zip(ta[:7], tb[:7]):
             assert torch.equal(x, y)
         assert ta[7] is acts
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_host_pipeline_stub_runs_and_matches_the_package():
+    """The host-consumer binding of INTEGRATION.md: raw pointers, bit-packed observations, lmz_step_host_async / _wait."""
+    import torch
+    import gym_lmaze_b200 as lmz
+    ns, _ = load_stub()
+    n = 5000
+    a = ns["LmazeHostPipe"](n, device=0, seed=4)
+    b = lmz.LmazeVecCuda(n, "v0", device="cuda:0", seed=4)
+    b.reset()
+    gen = torch.Generator().manual_seed(2)
+    acts = [torch.randint(0, 5, (n,), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(12)]
+    want = []
+    for k, act in enumerate(acts):
+        obs, rew, done, _ = b.step(act)
+        want.append((obs.cpu().clone(), rew.cpu().clone(), done.cpu().clone()))
+        got = a.submit(act)
+        assert (got is None) == (k == 0)
+        if got is not None:
+            o, r, d = got
+            wo, wr, wd = want[k - 1]
+            assert torch.equal(a.image(o), wo) and torch.equal(r.view(torch.int32), wr.view(torch.int32)) and torch.equal(d.bool(), wd)
+    o, r, d = a.drain()
+    assert torch.equal(a.image(o), want[-1][0]) and torch.equal(d.bool(), want[-1][2])
     a.close(); b.close()
