@@ -499,7 +499,12 @@ def run_ours(args):
     # ---- other operating points, at EVERY world size (each names its own mode; never mixed into `value`)
     extras = {}
     if not args.no_extras:
+        sampler2 = ClockSampler(rk.local_rank)              # the extras' timed regions are short: one sampler over all of them
+        if rank == 0:
+            sampler2.start()
         extras = side_measurements(rk, lmz, args, SEED)
+        if rank == 0:
+            extras["clocks"] = sampler2.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

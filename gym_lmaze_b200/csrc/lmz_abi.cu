@@ -441,9 +441,8 @@ int launch_fov(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
 }
 
 // compact observations / nothing to render (foveal variants): warp-granular kernel, several small CTAs per SM
-template <class W>
-int launch_fov_small(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  constexpr int THREADS = 128;
+template <class W, int THREADS>
+int launch_fov_small_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   if (W::HAS_LOC && !h->local_bound)
     return fail(LMZ_ERR_STATE, "lmaze-v5/v6: local outputs not bound: call lmz_bind_local first");
   auto kern = lmz::lmz_fov_small_kernel<W, THREADS>;
@@ -470,6 +469,13 @@ int launch_fov_small(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
+}
+
+template <class W>
+int launch_fov_small(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (h->cfg.tune[0] == 64) return launch_fov_small_t<W, 64>(h, p, s);       // (tuning: 2 warps per CTA)
+  if (h->cfg.tune[0] == 256) return launch_fov_small_t<W, 256>(h, p, s);     // (tuning: 8 warps per CTA)
+  return launch_fov_small_t<W, 128>(h, p, s);
 }
 
 template <class W>

@@ -46,7 +46,7 @@ for i in range(3):      # from the second plannerStep on the auto mask has its r
     h.step(a[i], goal_plane=False); note("v5 step #%d" % i, "lmz_env_fov_kernel", n, 54400, "v5_tma" if i == 2 else None)
 rew = h.rollout(32); note("v5 rollout T=32 (planner + actor)", "lmz_fov_rollout_kernel", n)
 torch.cuda.synchronize(); h.close()
-run("v0 compact u8", 1 << 22, "v0", "lmz_env_compact_kernel", 590).close()
+run("v0 compact u8", 1 << 22, "v0", "lmz_env_compact_kernel", 590, obs_mode="compact").close()
 run("v0 bit-packed", 1 << 22, "v0", "lmz_env_compact_kernel", 86, obs_mode="bits").close()
 run("v3 compact u8", 1 << 22, "v3", "lmz_env_compact_kernel", 986, obs_mode="compact").close()
 e = lmz.LmazeVecCuda(1 << 19, "v0", seed=1, render_mode="incremental")
