@@ -533,14 +533,16 @@ int launch_rollout_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return LMZ_OK;
 }
 
-template <class W>
-int launch_fov_rollout(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+template <class W, bool VIS_SMEM>
+int launch_fov_rollout_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   constexpr int THREADS = 128;
-  constexpr int SMEM = (int)(W::BLOB_BYTES - W::ROWBITS_OFF);
-  auto kern = lmz::lmz_fov_rollout_kernel<W, THREADS>;
+  constexpr int TAB = (int)((W::BLOB_BYTES - W::ROWBITS_OFF + 15u) & ~15u);
+  constexpr int SMEM = TAB + (VIS_SMEM ? THREADS * lmz::VIS_STRIDE * 4 : 0);
+  auto kern = lmz::lmz_fov_rollout_kernel<W, THREADS, VIS_SMEM>;
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
   if (configured_dev != h->cfg.device) {
+    LMZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, SMEM));
     if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal rollout kernel does not fit on an SM");
     configured_dev = h->cfg.device;
@@ -553,6 +555,13 @@ int launch_fov_rollout(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
+}
+
+// long rollouts of the visit variants keep every env's layer in shared memory for the whole launch (lmz_fov_rollout.cuh)
+template <class W>
+int launch_fov_rollout(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+  if (W::NVIS > 0 && p.T >= lmz::VIS_SMEM_MIN_T) return launch_fov_rollout_t<W, true>(h, p, s);
+  return launch_fov_rollout_t<W, false>(h, p, s);
 }
 
 int check_handle(lmz_env *h) {

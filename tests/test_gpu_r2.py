@@ -415,6 +415,16 @@ def test_foveal_rollout_kernel_parity(lmz, oracle_mod, variant):
             assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), rnd
         full = np.stack([ora.render_one(i) for i in range(N)])
         assert np.array_equal(u32(env.render_obs()), u32(full)), rnd
+    # short rollouts (T < 8) update v4's visit layer in global memory instead of a shared-memory copy: same results
+    for T_short in (5, 1, 7):
+        acts = np.array([[oracle_mod.rng_action25(seed, 3 + i, t_glob + t) for i in range(N)] for t in range(T_short)])
+        rew, done = env.rollout(T_short)
+        t_glob += T_short
+        for t in range(T_short):
+            _, r_ref, d_ref = ora.step(acts[t], want_obs=False)
+            assert np.array_equal(rbits(rew[t]), r_ref.view(np.uint32)) and np.array_equal(done[t].cpu().numpy().view(np.uint8), d_ref)
+    if variant == "v4":
+        assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit()))
     s = env.stats(check_errors=False)
     assert [s[k] for k in oracle_mod.STAT_NAMES] == ora.stats.tolist() and s["episodes"] > N
     # ... and ordinary steps continue from the rolled-out state
@@ -462,7 +472,21 @@ def test_hier_rollout_kernel_parity(lmz, oracle_mod, philox):
         fov_ref, loc_ref, err_ref = ora.render()
         env.render_obs()
         assert np.array_equal(u32(env.obs), u32(fov_ref)) and np.array_equal(u32(env.loc_obs), u32(loc_ref))
-    assert env.stats(check_errors=False)["steps"] == 2 * T * N
+        if rnd == 0:                                       # a short rollout in between (visit layer updated in global memory)
+            ga = np.array([[oracle_mod.rng_hier(seed, 40 + i, t_glob + t) for i in range(N)] for t in range(6)])
+            gr6, lr6, gd6, ld6 = env.rollout(6) if philox else env.rollout(6, goals=torch.as_tensor(ga[:, :, 0]), actions=torch.as_tensor(ga[:, :, 1]))
+            t_glob += 6
+            for t in range(6):
+                st6 = ora.export()
+                need = (((st6[:, 15] >> 1) & 1) | (st6[:, 14] == 0)).astype(np.uint8)
+                if need.any():
+                    ora.planner_step(ga[t, :, 0], mask=need)
+                _, _, gr_ref, lr_ref, gd_ref, ld_ref, _ = ora.step(ga[t, :, 1])
+                assert np.array_equal(rbits(gr6[t]), gr_ref.view(np.uint32)) and np.array_equal(ld6[t].cpu().numpy(), ld_ref.astype(bool)), t
+                if gd_ref.any():
+                    ora.reset(mask=gd_ref, want_obs=False)
+            assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit()))
+    assert env.stats(check_errors=False)["steps"] == (2 * T + 6) * N
     env.close()
 
 
