@@ -99,7 +99,8 @@ typedef struct lmz_config {
   int32_t  render_mode;   /* lmz_render_mode */
   int32_t  tune[4];       /* launch tuning for the TMA render path, 0 = library default:
                              [0] threads per CTA (TMA path: 32/64/128/256 issuing warps x32; ST128 path: 256/512/1024;
-                                 foveal kernels: 128 (v2), 224, 256, 512, 1024)
+                                 foveal render kernels: 128 (default), 160, 192, 224, 256, 512, 1024;
+                                 compact foveal kernel: 64, 128 (default), 256)
                              [1] L2 policy of the obs stores: 1 evict_first, 2 evict_normal, 3 evict_last, 4 none
                              [2] resident CTAs per SM (0 = library default)
                              [3] split bulk copies into pieces of at most this many bytes (multiple of 16) */
@@ -237,7 +238,9 @@ int lmz_get_state_dl(lmz_env *env, DLManagedTensor *out, void *stream);
 int lmz_set_state_dl(lmz_env *env, DLManagedTensor *in, void *stream);
 
 /* lmaze-v4 / v5 / v6: the float visit layer state[2] of every env (lmaze_env_v4.py:106-113,211-214; lmaze_env_v5.py:308-312),
- * f32 [N][18][18] on the device -- part of the checkpoint next to lmz_get_state. */
+ * f32 [N][18][18] on the device -- part of the checkpoint next to lmz_get_state.  These are the TRUE values; the handle
+ * itself keeps the layer scaled by a per-env power of two.  After lmz_set_visit an env averages
+ * its layer with the literal full pass until its next reset (nothing is known about how small the supplied values are). */
 int lmz_get_visit(lmz_env *env, float *out, void *stream);
 int lmz_set_visit(lmz_env *env, const float *in, void *stream);
 int lmz_get_visit_dl(lmz_env *env, DLManagedTensor *out, void *stream);
