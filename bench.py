@@ -380,8 +380,8 @@ def run_ours(args):
     if windows[-1] + W > N:
         windows[-1] = N - W
     obs_bytes = env.obs[0].numel() * env.obs.element_size()
-    # v4: the visit layer is stored scaled: two 5x5 windows read, one written per env-step
-    step_bytes = obs_bytes + 14 + (3 * VISIT_WINDOW_BYTES if args.variant == "v4" else 0)
+    # v4: the visit layer is kept as its history: 64 B read + one 16 B chunk written per env-step
+    step_bytes = obs_bytes + 14 + (VISIT_HIST_BYTES + 16 if args.variant == "v4" else 0)
     if hier:
         step_bytes = 0        # filled in after the timed region from the measured localDone / planner fractions
     if args.render_mode == "incremental":
@@ -443,12 +443,11 @@ def run_ours(args):
         # 2 rewards, 4 flag bytes, action; planner launch: 3 state words read, and for the waiting envs goal +
         # state write + local obs
         fov_b, loc_b = (34300, 19600) if args.obs_mode == "full" else (700, 400)
-        step_bytes = int(fov_b + loc_b + VISIT_WINDOW_BYTES * (2 + ld) + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
+        step_bytes = int(fov_b + loc_b + VISIT_HIST_BYTES + 16 * ld + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
         hier_note = {"local_done_fraction": ld, "planner_fraction": pf,
-                     "bytes": "%d foveal + %d local obs + 2 x %d visit windows read (+%d x localDone written; the layer is "
-                              "stored scaled, DESIGN.md 3.5) + state/rewards/flags/action 37 + planner launch: 12 + "
-                              "planner_fraction x (%d local obs + 15)"
-                              % (fov_b, loc_b, VISIT_WINDOW_BYTES, VISIT_WINDOW_BYTES, loc_b)}
+                     "bytes": "%d foveal + %d local obs + %d visit history read (+16 x localDone written; the layer is kept "
+                              "as its history, DESIGN.md 3.5) + state/rewards/flags/action 37 + planner launch: 12 + "
+                              "planner_fraction x (%d local obs + 15)" % (fov_b, loc_b, VISIT_HIST_BYTES, loc_b)}
     achieved = N * step_bytes / (step_ms * 1e-3) / 1e9
 
     # ---- checks on the real GPUs: counters and shard invariance
@@ -581,7 +580,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-VISIT_WINDOW_BYTES = 25 * 4     # one 5x5 window of an env's float visit layer (v4 / v5)
+VISIT_HIST_BYTES = 64          # one env's visit history (v4 / v5): the window centre of each averaging since the reset
 
 
 def main_workload_checks(rk, lmz, env, args, hier, seed, N, W, R, action_ring, steps_done, K=1024, KO=32):

@@ -207,7 +207,8 @@ struct lmz_env {
   int num_sms;
   // device memory owned by the handle
   uint32_t *state, *goal_count, *episode;
-  float *visit;                  // v4 / v5: f32 [N][324]
+  float *visit;                  // v4 / v5: f32 [N][324] (the layer of envs in direct mode)
+  uint8_t *hist;                 // v4 / v5: u8 [N][64] visit history
   uint32_t *aux2;                // v5: third packed state word
   // v5 local outputs (caller-owned), lmz_bind_local
   float *loc_obs, *reward2;
@@ -259,7 +260,7 @@ lmz::KParams base_params(lmz_env *h) {
   lmz::KParams p;
   memset(&p, 0, sizeof(p));
   p.n = h->cfg.num_envs;
-  p.state = h->state; p.goal_count = h->goal_count; p.episode = h->episode; p.visit = h->visit;
+  p.state = h->state; p.goal_count = h->goal_count; p.episode = h->episode; p.visit = h->visit; p.hist = h->hist;
   p.obs = h->obs; p.reward = h->reward; p.done = h->done;
   p.win_lo = h->win_lo; p.win_n = h->win_n;
   p.tile_begin = 0; p.tile_end = (p.n + 31) / 32;
@@ -533,16 +534,15 @@ int launch_rollout_v(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   return LMZ_OK;
 }
 
-template <class W, bool VIS_SMEM>
-int launch_fov_rollout_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
+template <class W>
+int launch_fov_rollout(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   constexpr int THREADS = 128;
   constexpr int TAB = (int)((W::BLOB_BYTES - W::ROWBITS_OFF + 15u) & ~15u);
-  constexpr int SMEM = TAB + (VIS_SMEM ? THREADS * lmz::VIS_STRIDE * 4 : 0);
-  auto kern = lmz::lmz_fov_rollout_kernel<W, THREADS, VIS_SMEM>;
+  constexpr int SMEM = TAB + THREADS * lmz::HIST_STRIDE;               // tables + one visit-history row per thread
+  auto kern = lmz::lmz_fov_rollout_kernel<W, THREADS>;
   static thread_local int configured_dev = -1;
   static thread_local int ctas_per_sm = 1;
   if (configured_dev != h->cfg.device) {
-    LMZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     LMZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, THREADS, SMEM));
     if (ctas_per_sm < 1) return fail(LMZ_ERR_CUDA, "foveal rollout kernel does not fit on an SM");
     configured_dev = h->cfg.device;
@@ -555,13 +555,6 @@ int launch_fov_rollout_t(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;
-}
-
-// long rollouts of the visit variants keep every env's layer in shared memory for the whole launch (lmz_fov_rollout.cuh)
-template <class W>
-int launch_fov_rollout(lmz_env *h, const lmz::KParams &p, cudaStream_t s) {
-  if (W::NVIS > 0 && p.T >= lmz::VIS_SMEM_MIN_T) return launch_fov_rollout_t<W, true>(h, p, s);
-  return launch_fov_rollout_t<W, false>(h, p, s);
 }
 
 int check_handle(lmz_env *h) {
@@ -822,6 +815,8 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   if (e == cudaSuccess && (cfg->variant == LMZ_V4 || hier)) {      // state[2], the float visit layer (lmaze_env_v4.py:106-113)
     e = cudaMalloc(&h->visit, n * 324 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(h->visit, 0, n * 324 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->hist, n * 64);           // the visit history (lmz_v2.cuh): empty = an all-zero layer
+    if (e == cudaSuccess) e = cudaMemset(h->hist, 0, n * 64);
   }
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, (lmz::NUM_STATS + 3) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(h->goal_count, 0, n * sizeof(uint32_t));
@@ -882,7 +877,7 @@ int lmz_destroy(lmz_env *h) {
   if (!h) return LMZ_OK;
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->goal_count); cudaFree(h->episode); cudaFree(h->blob); cudaFree(h->stats);
-  cudaFree(h->act_stage); cudaFree(h->visit); cudaFree(h->aux2);
+  cudaFree(h->act_stage); cudaFree(h->visit); cudaFree(h->hist); cudaFree(h->aux2);
   if (h->pipe.init) {
     cudaStreamSynchronize(h->pipe.copy);
     for (int i = 0; i < 2; ++i) {
@@ -1234,12 +1229,12 @@ static int visit_xfer(lmz_env *h, float *buf, int set, void *stream) {
     return fail(LMZ_ERR_UNSUPPORTED, "only lmaze-v4/v5/v6 have a visit layer");
   if (!buf) return fail(LMZ_ERR_INVALID, "visit buffer is NULL");
   DeviceGuard guard(h->cfg.device);
-  // the layer is stored scaled by 2^T per env (lmz_v2.cuh, "visit layer"); it crosses the ABI as true values
+  // the handle keeps the layer as its history (lmz_v2.cuh, "visit layer"); it crosses the ABI as values
   const int64_t n = h->cfg.num_envs;
   const bool v5 = h->cfg.variant == LMZ_V5;
   const unsigned blocks = (unsigned)((n * 324 + 255) / 256);
   lmz::lmz_visit_xfer_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      n, h->visit, v5 ? h->state : h->goal_count, v5 ? 25 : 16, buf, set);
+      n, h->visit, h->hist, v5 ? h->state : h->goal_count, v5 ? 25 : 16, buf, set);
   LMZ_CUDA(cudaGetLastError());
   h->launches += 1;
   return LMZ_OK;

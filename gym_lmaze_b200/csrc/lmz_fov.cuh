@@ -45,225 +45,173 @@ __device__ __forceinline__ float visit_average(float v, bool in_window) {
 }
 
 // ---- the visit layer of one 32-env tile, one env per lane (whole warp must call) --------------------------------
-// info / vinfo: the lane's FovLane words; plane_cur / plane_prev: the lane's two 25-float visit planes in shared
-// memory (crop at the ball / crop at the previous window, both showing the layer AFTER this call's update -- the
-// reference's retStatelast is a view of the live state, lmaze_env_v4.py:122,258-259), written when want_planes.
-// Two halves, so that a kernel can put other work (a whole tile time in the render kernel) between the loads
-// and their use:  visit_issue  does the rare whole-layer operations (reset: 324 cells rewritten; direct mode: the
-// literal full pass) warp-cooperatively, env by env with 128-bit accesses, then starts every lane's 50 window loads;
-// visit_finish  adds 2^T to the window (s' = RN(s + 2^T)), stores it and writes the two planes.
-struct VisitFetch {
-  float cur[25], prv[25];
+// The layer is kept as its HISTORY (lmz_v2.cuh, "visit layer"): hw = the lane's 64 history bytes (loaded with the
+// state words a tile ahead), entry k = the window centre of averaging k.  info / vinfo: the lane's FovLane words;
+// plane_cur / plane_prev: the lane's two 25-float visit planes in shared memory (crop at the ball / crop at the
+// previous window, both showing the layer AFTER this call's update -- the reference's retStatelast is a view of the
+// live state, lmaze_env_v4.py:122,258-259), written when want_planes.
+struct VisitHist {
+  uint32_t w[16];
 };
-
-// reset (324 cells rewritten) and direct-mode full passes of the tile's envs, warp-cooperatively; true if any ran
-template <class W>
-__device__ __forceinline__ bool visit_full_passes(const KParams &p, int64_t e0, int lane, uint32_t op, int tpre, int bx, int by) {
-  constexpr int GG = W::G * W::G;
-  unsigned full = __ballot_sync(0xffffffffu, op == VOP_RESET || op == VOP_FULL);
-  if (!full) return false;
-  while (full) {
-    const int src = __ffs(full) - 1;
-    full &= full - 1;
-    const uint32_t sop = __shfl_sync(0xffffffffu, op, src);
-    const int sx = __shfl_sync(0xffffffffu, bx, src), sy = __shfl_sync(0xffffffffu, by, src);
-    const float down = visit_scale_down(__shfl_sync(0xffffffffu, tpre, src));
-    float4 *row = reinterpret_cast<float4 *>(p.visit + (e0 + src) * GG);          // 1,296 B per env: 16-byte aligned
-    for (int c4 = lane; c4 < GG / 4; c4 += 32) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (sop == VOP_FULL) v = __ldcg(row + c4);
-      float *q = reinterpret_cast<float *>(&v);
+__device__ __forceinline__ VisitHist visit_hist_of(const FovPre &pre) {
+  VisitHist h;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int cell = 4 * c4 + k, x = cell / W::G, y = cell - x * W::G;
-        const bool in_cur = (unsigned)(x - sx + 2) < 5u && (unsigned)(y - sy + 2) < 5u;
-        q[k] = (sop == VOP_FULL) ? visit_average(__fmul_rn(q[k], down), in_cur) : W::visit_reset_stored(in_cur);
+  for (int k = 0; k < 4; ++k) { h.w[4 * k] = pre.h[k].x; h.w[4 * k + 1] = pre.h[k].y; h.w[4 * k + 2] = pre.h[k].z; h.w[4 * k + 3] = pre.h[k].w; }
+  return h;
+}
+__device__ __forceinline__ uint32_t visit_entry(int x, int y) { return (uint32_t)(((x - 2) << 4) | (y - 2)); }
+// bits i = 0..4 with |o + i - h| <= 2: the rows (columns) of the 5-window at origin o that entry centre h covers
+__device__ __forceinline__ uint32_t visit_cover(int h, int o) {
+  const int d = h - 2 - o;                                   // covered indices: [d, d + 4] cut to [0, 4]
+  const int lo = d < 0 ? 0 : d, hi = d + 4 > 4 ? 4 : d + 4;
+  return hi >= lo ? ((2u << hi) - (1u << lo)) : 0u;
+}
+
+// The layer's values on TWO 5x5 windows (origins (ax, ay) and (bx, by) = centre - 2) after the first `T` averagings
+// of the history: the reference's fold, one fma per cell and entry.  `tmax` >= T is warp-uniform (the loop bound).
+__device__ __forceinline__ void visit_fold2(const VisitHist &h, int T, int tmax, int ax, int ay, int bx, int by,
+                                            float *va, float *vb) {
+#pragma unroll
+  for (int c = 0; c < 25; ++c) { va[c] = 0.0f; vb[c] = 0.0f; }
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    if (4 * g < tmax) {                                      // (warp-uniform; no `break`: the loop must unroll completely)
+    const uint32_t w = h.w[g];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int k = 4 * g + b;
+      const bool live = k < T;
+      const uint32_t e = (w >> (8 * b)) & 255u;
+      const int hx = (int)(e >> 4) + 2, hy = (int)(e & 15u) + 2;
+      const float mul = live ? 0.5f : 1.0f;                  // entries past this lane's T leave the values alone
+      const uint32_t ra = live ? visit_cover(hx, ax) : 0u, ca = visit_cover(hy, ay);
+      const uint32_t rb = live ? visit_cover(hx, bx) : 0u, cb = visit_cover(hy, by);
+      float adda[5], addb[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { adda[j] = ((ca >> j) & 1u) ? 0.5f : 0.0f; addb[j] = ((cb >> j) & 1u) ? 0.5f : 0.0f; }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const bool ia = (ra >> i) & 1u, ib = (rb >> i) & 1u;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          va[i * 5 + j] = __fmaf_rn(va[i * 5 + j], mul, ia ? adda[j] : 0.0f);
+          vb[i * 5 + j] = __fmaf_rn(vb[i * 5 + j], mul, ib ? addb[j] : 0.0f);
+        }
       }
-      __stcg(row + c4, v);
+    }
     }
   }
-  return true;
 }
 
-template <class W>
-__device__ __forceinline__ void visit_issue(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
-                                            uint32_t vinfo, bool want_planes, VisitFetch &f) {
-  constexpr int GG = W::G * W::G;
-  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
-  const int tpre = (vinfo >> 3) & 127;
-  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-  if (visit_full_passes<W>(p, e0, lane, op, tpre, bx, by)) __syncwarp();   // the cooperative stores are visible to the owning lane
-  if (!valid || op == VOP_RESET || (op != VOP_AVG && !want_planes)) return;
-  const float *vis = p.visit + (e0 + lane) * GG;
+// one cell of the layer from the history of lane `src` (warp-cooperative materialisation: every lane a different cell)
+__device__ __forceinline__ float visit_fold_cell(const VisitHist &h, int src, int T, int x, int y) {
+  float v = 0.0f;
 #pragma unroll
-  for (int k = 0; k < 25; ++k) f.cur[k] = __ldcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5));
-  if (want_planes) {
+  for (int g = 0; g < 16; ++g) {
+    const uint32_t w = __shfl_sync(0xffffffffu, h.w[g], src);
 #pragma unroll
-    for (int k = 0; k < 25; ++k) f.prv[k] = __ldcg(vis + (px - 2 + k / 5) * W::G + (py - 2 + k % 5));
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t e = (w >> (8 * b)) & 255u;
+      const int hx = (int)(e >> 4) + 2, hy = (int)(e & 15u) + 2;
+      const bool in = (unsigned)(x - hx + 2) < 5u && (unsigned)(y - hy + 2) < 5u;
+      if (4 * g + b < T) v = visit_avg1(v, in);
+    }
   }
+  return v;
 }
 
+// The whole visit step of a tile.  Rare whole-layer work first, warp-cooperatively: an averaging in DIRECT mode is the
+// literal full pass over the env's layer in memory, and the averaging that finds the history full materialises the
+// layer from the history on the way.  Then every lane: append / reset its history (one 16-byte store of the chunk that
+// holds the new entry) and fold the two windows (history mode), or read them from the layer (direct mode).
 template <class W>
-__device__ __forceinline__ void visit_finish(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
-                                             uint32_t vinfo, bool want_planes, VisitFetch &f, float *plane_cur,
-                                             float *plane_prev) {
+__device__ __forceinline__ void visit_step(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                           uint32_t vinfo, bool want_planes, VisitHist &h, float *plane_cur,
+                                           float *plane_prev) {
   constexpr int GG = W::G * W::G;
   const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
   const int tpre = (vinfo >> 3) & 127, tpost = (vinfo >> 10) & 127;
   const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-  if (!valid || (op != VOP_AVG && !want_planes)) return;
-  if (op == VOP_RESET) {                                  // the layer was just rewritten: values known
+  unsigned full = __ballot_sync(0xffffffffu, op == VOP_FULL);
+  if (full) {
+    while (full) {
+      const int src = __ffs(full) - 1;
+      full &= full - 1;
+      const int st = __shfl_sync(0xffffffffu, tpre, src);
+      const int sx = __shfl_sync(0xffffffffu, bx, src), sy = __shfl_sync(0xffffffffu, by, src);
+      float *layer = p.visit + (e0 + src) * GG;
+      for (int c0 = 0; c0 < GG; c0 += 32) {                 // (uniform trip count: the shuffles inside need the whole warp)
+        const int c = c0 + lane, x = c / W::G, y = c - x * W::G;
+        float v = (st == VT_DIRECT) ? 0.0f : visit_fold_cell(h, src, st, x, y);
+        if (c < GG) {
+          if (st == VT_DIRECT) v = __ldcg(layer + c);
+          const bool in_cur = (unsigned)(x - sx + 2) < 5u && (unsigned)(y - sy + 2) < 5u;
+          __stcg(layer + c, visit_average(v, in_cur));
+        }
+      }
+    }
+    __syncwarp();                                           // the cooperative stores are visible to the owning lane
+  }
+  if (!valid) return;
+  if (tpost == VT_DIRECT) {                                 // direct mode: the windows come from the layer in memory
+    if (!want_planes) return;
+    const float *vis = p.visit + (e0 + lane) * GG;
 #pragma unroll
     for (int k = 0; k < 25; ++k) {
-      const int ax = px - 2 + k / 5, ay = py - 2 + k % 5;
-      const bool in_cur = (unsigned)(ax - bx + 2) < 5u && (unsigned)(ay - by + 2) < 5u;
-      plane_cur[k] = W::visit_reset(true);
-      plane_prev[k] = W::visit_reset(in_cur);
+      plane_cur[k] = __ldcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5));
+      plane_prev[k] = __ldcg(vis + (px - 2 + k / 5) * W::G + (py - 2 + k % 5));
     }
     return;
   }
-  if (op == VOP_AVG) {                                    // s' = RN(s + 2^T) on the window, nothing else changes
-    float *vis = p.visit + (e0 + lane) * GG;
-    const float add = __int_as_float((127 + tpre) << 23);
+  // history mode: a reset empties the history (v4: its first averaging is the spawn cell), an averaging appends
+  const bool app = op == VOP_AVG || (op == VOP_RESET && W::VT_RESET == 1);
+  if (app) {
+    const int pos = tpost - 1;                              // 0 .. 63
+    const uint32_t ent = visit_entry(bx, by) << (8 * (pos & 3));
+    const uint32_t keep = ~(255u << (8 * (pos & 3)));
+    uint4 chunk = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int k = 0; k < 25; ++k) {
-      f.cur[k] = __fadd_rn(f.cur[k], add);
-      __stcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5), f.cur[k]);
+    for (int g = 0; g < 16; ++g) {
+      if (g == (pos >> 2)) h.w[g] = (h.w[g] & keep) | ent;
+      if ((g >> 2) == (pos >> 4)) {
+        if ((g & 3) == 0) chunk.x = h.w[g]; else if ((g & 3) == 1) chunk.y = h.w[g]; else if ((g & 3) == 2) chunk.z = h.w[g]; else chunk.w = h.w[g];
+      }
     }
+    __stcg(reinterpret_cast<uint4 *>(p.hist + (e0 + lane) * HIST_MAX) + (pos >> 4), chunk);
   }
+  const int need = want_planes ? tpost : 0;
+  const int tmax = __reduce_max_sync(__activemask(), need);
   if (!want_planes) return;
-  const float down = visit_scale_down(tpost);
+  float vc[25], vp[25];
+  visit_fold2(h, tpost, tmax, bx - 2, by - 2, px - 2, py - 2, vc, vp);
 #pragma unroll
-  for (int k = 0; k < 25; ++k) plane_cur[k] = __fmul_rn(f.cur[k], down);
-  const int ox = px - bx, oy = py - by;                   // previous window relative to the current one
-#pragma unroll
-  for (int k = 0; k < 25; ++k) {
-    const int dx = ox + k / 5, dy = oy + k % 5;           // cell k of the previous window, in current-window coordinates
-    const bool in_cur = (unsigned)dx < 5u && (unsigned)dy < 5u;
-    plane_prev[k] = in_cur ? plane_cur[in_cur ? dx * 5 + dy : 0] : __fmul_rn(f.prv[k], down);
-  }
+  for (int k = 0; k < 25; ++k) { plane_cur[k] = vc[k]; plane_prev[k] = vp[k]; }
 }
 
-// ---- the same two halves with the TMA engine doing the memory traffic (the full-render kernel) -----------------
-// In the render kernel the LSU / L1TEX pipe belongs to the rendering warps' 128-bit stores: 75 uncoalesced 4-byte
-// accesses per env from the producer (32 different sectors per warp instruction) sit in that pipe for ~2,400 cycles
-// per tile and stall the renderers on their store-data registers (ncu: long_scoreboard on the store loop, 15 % barrier
-// wait; v4 172 M env-steps/s against 218 M with the layer switched off).  So here a window travels as its BAND -- the
-// five 72-byte grid rows that hold it, 368 bytes from a 16-byte aligned start -- by cp.async.bulk: global -> shared
-// in stage A (completion on an mbarrier), the 25 cells are updated in shared memory in stage B and the band goes
-// back with one shared -> global bulk copy.  No LSU instruction touches the layer (resets / direct mode aside).
-constexpr uint32_t VBAND_BYTES = 368, VBAND_FLOATS = VBAND_BYTES / 4;
-// byte offset of the band of the window centred on row x, rounded down to 16 (the band then never leaves the env's
-// 1,296-byte layer: rounding only happens for even x - 2, i.e. x <= 14)
-__device__ __forceinline__ uint32_t vband_off(int x) { return ((uint32_t)(x - 2) * 72u) & ~15u; }
-
-// bands: this stage's [32][2][VBAND_FLOATS] floats in shared memory; bar: this stage's mbarrier (count 1)
-template <class W>
-__device__ __forceinline__ void visit_issue_tma(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
-                                                uint32_t vinfo, bool want_planes, float *bands, uint64_t *bar) {
-  constexpr int GG = W::G * W::G;
-  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
-  const int tpre = (vinfo >> 3) & 127;
-  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31;
-  if (visit_full_passes<W>(p, e0, lane, op, tpre, bx, by)) {
-    asm volatile("fence.proxy.async;" ::: "memory");      // the generic-proxy stores precede the async-proxy loads below
-    __syncwarp();
-  }
-  const bool need_cur = valid && op != VOP_RESET && (op == VOP_AVG || want_planes);
-#ifdef LMZ_DEBUG_NO_PREV                     // (tuning builds only)
-  const bool need_prv = false;
-#else
-  const bool need_prv = valid && op != VOP_RESET && want_planes;
-#endif
-  const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, need_cur)) + __popc(__ballot_sync(0xffffffffu, need_prv));
-  if (lane == 0) mbar_expect_tx(bar, cnt * VBAND_BYTES);   // arrives; with cnt == 0 the phase completes at once
-  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this buffer's previous write-back has left shared memory
-  const unsigned char *vis = reinterpret_cast<const unsigned char *>(p.visit + (e0 + lane) * GG);
-  float *mine = bands + lane * (2 * VBAND_FLOATS);
-  if (need_cur) bulk_g2s(mine, vis + vband_off(bx), VBAND_BYTES, bar);
-  if (need_prv) bulk_g2s(mine + VBAND_FLOATS, vis + vband_off(px), VBAND_BYTES, bar);
-}
-
-template <class W>
-__device__ __forceinline__ void visit_finish_tma(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
-                                                 uint32_t vinfo, bool want_planes, float *bands, uint64_t *bar,
-                                                 uint32_t parity, float *plane_cur, float *plane_prev) {
-  constexpr int GG = W::G * W::G;
-  const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
-  const int tpre = (vinfo >> 3) & 127, tpost = (vinfo >> 10) & 127;
-  const int bx = info & 31, by = (info >> 5) & 31, px = (info >> 10) & 31, py = (info >> 15) & 31;
-  mbar_wait(bar, parity);                                  // the tile's bands have landed
-  float *mine = bands + lane * (2 * VBAND_FLOATS);
-  if (valid && op == VOP_RESET) {                          // the layer was just rewritten: values known
-    if (want_planes) {
-#pragma unroll
-      for (int k = 0; k < 25; ++k) {
-        const int ax = px - 2 + k / 5, ay = py - 2 + k % 5;
-        const bool in_cur = (unsigned)(ax - bx + 2) < 5u && (unsigned)(ay - by + 2) < 5u;
-        plane_cur[k] = W::visit_reset(true);
-        plane_prev[k] = W::visit_reset(in_cur);
-      }
-    }
-  } else if (valid && (op == VOP_AVG || want_planes)) {
-    // cell (bx - 2 + i, by - 2 + j) of the layer = float (bx - 2 + i) * 18 + by - 2 + j - band offset / 4 of the band
-    float *wc = mine + ((bx - 2) * W::G + (by - 2)) - (int)(vband_off(bx) >> 2);
-    float cur[25];
-#pragma unroll
-    for (int k = 0; k < 25; ++k) cur[k] = wc[(k / 5) * W::G + k % 5];
-    if (op == VOP_AVG) {                                   // s' = RN(s + 2^T) on the window, nothing else changes
-      const float add = __int_as_float((127 + tpre) << 23);
-#pragma unroll
-      for (int k = 0; k < 25; ++k) { cur[k] = __fadd_rn(cur[k], add); wc[(k / 5) * W::G + k % 5] = cur[k]; }
-    }
-    if (want_planes) {
-      const float down = visit_scale_down(tpost);
-      const float *wp = mine + VBAND_FLOATS + ((px - 2) * W::G + (py - 2)) - (int)(vband_off(px) >> 2);
-#pragma unroll
-      for (int k = 0; k < 25; ++k) plane_cur[k] = __fmul_rn(cur[k], down);
-      const int ox = px - bx, oy = py - by;                // previous window relative to the current one
-#pragma unroll
-      for (int k = 0; k < 25; ++k) {
-        const int dx = ox + k / 5, dy = oy + k % 5;
-        const bool in_cur = (unsigned)dx < 5u && (unsigned)dy < 5u;
-        plane_prev[k] = in_cur ? plane_cur[in_cur ? dx * 5 + dy : 0] : __fmul_rn(wp[(k / 5) * W::G + k % 5], down);
-      }
-    }
-  }
-  // write the updated band back: shared -> global bulk copy (the other cells of the band go back unchanged)
-#ifdef LMZ_DEBUG_NO_WB                       // (tuning builds only)
-  const bool wb = false;
-#else
-  const bool wb = valid && op == VOP_AVG;
-#endif
-  if (wb) {
-    fence_proxy_async();                                   // this lane's shared-memory writes -> async proxy
-    bulk_s2g(reinterpret_cast<unsigned char *>(p.visit + (e0 + lane) * GG) + vband_off(bx), smem_addr(mine), VBAND_BYTES);
-  }
-  bulk_commit();                                           // one group per stage B and lane, empty or not
-}
-
-template <class W>
-__device__ __forceinline__ void visit_warp(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
-                                           uint32_t vinfo, bool want_planes, float *plane_cur, float *plane_prev) {
-  VisitFetch f;
-  visit_issue<W>(p, e0, lane, valid, info, vinfo, want_planes, f);
-  visit_finish<W>(p, e0, lane, valid, info, vinfo, want_planes, f, plane_cur, plane_prev);
-}
-
-// lmz_get_visit / lmz_set_visit: the layer crosses the ABI as TRUE values.  get: v = s * 2^-T.  set: the values are
-// stored as given and the env goes to direct mode until its next reset (nothing is known about how small the
-// supplied values are, so the "everything stays normal" bound of the scaled form cannot be assumed).
+// lmz_get_visit / lmz_set_visit: the layer crosses the ABI as values.  get: the fold of the env's history (or the layer
+// in memory for an env in direct mode).  set: the values are stored as given and the env goes to direct mode until its
+// next reset (arbitrary values have no history).
 // tword: the state word that carries the env's T field (v4: aux word, bits 16-22; v5: w0, bits 25-31).
-__global__ void lmz_visit_xfer_kernel(int64_t n, float *visit, uint32_t *tword, int shift, float *io, int set) {
+__global__ void lmz_visit_xfer_kernel(int64_t n, float *visit, const uint8_t *hist, uint32_t *tword, int shift, float *io, int set) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * 324) return;
   const int64_t e = idx / 324;
+  const int cell = (int)(idx - e * 324);
   if (set) {
     visit[idx] = io[idx];
-    if (idx - e * 324 == 0) tword[e] = (tword[e] & ~(127u << shift)) | ((uint32_t)VT_DIRECT << shift);
-  } else {
-    io[idx] = __fmul_rn(visit[idx], visit_scale_down((int)((tword[e] >> shift) & 127u)));
+    if (cell == 0) tword[e] = (tword[e] & ~(127u << shift)) | ((uint32_t)VT_DIRECT << shift);
+    return;
   }
+  const int T = (int)((tword[e] >> shift) & 127u);
+  if (T == VT_DIRECT) { io[idx] = visit[idx]; return; }
+  const int x = cell / 18, y = cell - x * 18;
+  const uint8_t *hp = hist + e * HIST_MAX;
+  float v = 0.0f;
+  for (int k = 0; k < T; ++k) {
+    const int hx = (hp[k] >> 4) + 2, hy = (hp[k] & 15) + 2;
+    v = visit_avg1(v, (unsigned)(x - hx + 2) < 5u && (unsigned)(y - hy + 2) < 5u);
+  }
+  io[idx] = v;
 }
 
 template <int ID, int C>
@@ -280,7 +228,6 @@ template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ __align__(8) uint64_t vbar[2];    // visit bands of the two pipeline stages
   __shared__ uint32_t s_flags[2][2];         // [buf][0 obs, 1 local obs]: bit l = env l of the tile is written
   __shared__ long long s_tile[2];
   constexpr int PROD = (W::NVIS > 0) ? LMZ_VISIT_PROD : LMZ_V2_PROD;   // threads that never render
@@ -288,23 +235,22 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   static_assert(CTHREADS >= 32, "need at least one rendering warp");
   static_assert((uint32_t)CTHREADS < W::OBS_FLOATS, "index stepping assumes fewer threads than entries");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (W::NVIS > 0 && tid == 0) { mbar_init(&vbar[0], 1); mbar_init(&vbar[1], 1); }   // fenced + synced inside stage_blob
   stage_blob<W>(smem, &bar, p.blob);
   const FovTables<W> t(smem);
   float *vals = reinterpret_cast<float *>(smem + W::BLOB_BYTES);          // [2][32][NSLOT][25]
-  float *vbands = vals + 2 * 32 * W::VALS;                                // [2][32][2][VBAND_FLOATS]: landing zone of the visit bands
-  uint32_t vphase = 0, vstage = 0;                                        // warp 0: mbarrier parities, stage stage A fills next
   const int64_t tiles = p.tile_end;
   const bool need_visit = W::NVIS > 0 && p.mode != MODE_PLANNER;
   WarpStats ws;
 
   // Warp 0 runs ONE TILE AHEAD of its own loads: when it turns to a tile, the tile's index was grabbed and its
-  // state words / actions were requested a whole tile time earlier, so no atomic round trip -- several
-  // microseconds under a saturated write stream -- sits between two tiles of the producer.  (The visit
-  // variants add ONE dependent round trip per tile: the window loads need the positions the transitions produce.)
+  // state words / actions (and, for the visit variants, the envs' 64-byte visit histories: 2 KB of contiguous
+  // memory per tile) were requested a whole tile time earlier, so no DRAM or atomic round trip -- several
+  // microseconds each under a saturated write stream -- sits between two tiles of the producer.
   int64_t tl_next = 0;                       // warp 0: the tile produce() turns to next
   FovPre pre_next;                           // ... and its preloaded words (this lane's env)
   pre_next.w0 = pre_next.w1 = pre_next.w2 = 0u; pre_next.act = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pre_next.h[k] = make_uint4(0u, 0u, 0u, 0u);
   auto prefetch = [&](int64_t tl) {          // warp 0: start everything tile `tl` will need
     const int64_t e = tl * 32 + lane;
     if (tl < tiles && e < p.n) pre_next = fov_preload<W>(p, e);
@@ -315,17 +261,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
     return __shfl_sync(0xffffffffu, tl, 0);
   };
-  // The producer works in two stages, one tile apart (the visit variants): stage A runs a tile's transitions and
-  // STARTS its visit-window loads; stage B -- a whole tile time later, when the loads have long landed -- finishes
-  // the visit update and fills the tile's value planes.  Without the split the dependent DRAM round trip of the
-  // window loads sat in the producer's critical path and the renderers waited for it (v4: 174 M env-steps/s against
-  // 218 M with the visit layer switched off; tools/fov_sweep2.py).
-  FovLane<W::NBIT> pv;                       // warp 0: stage A's results for the tile stage B completes next
-  pv.o.st = 0; pv.o.st_old = 0; pv.o.render = false; pv.o.done = false; pv.o.cls = -1; pv.o.eplen = 0;
-  pv.info = 0; pv.vinfo = 0; pv.rfov = false; pv.rloc = false;
-  int64_t ptile = 0;
-  bool pvalid = false;
-  auto stage_a = [&]() {                     // warp 0 only
+  auto produce = [&](int buf) {              // warp 0 only
     const int64_t tl = tl_next;
     const FovPre pre = pre_next;
     const int64_t tl_after = grab();         // in flight while this tile's transitions run
@@ -336,24 +272,11 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     v.vinfo = 0; v.rfov = false; v.rloc = false;
     if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, smem, pre);
     if (p.mode == MODE_STEP) ws.add(valid, v.o);
-#ifndef LMZ_DEBUG_NO_VISIT                   // (tuning builds only: how fast is the kernel without the visit layer?)
-    if (W::NVIS > 0 && need_visit)
-      visit_issue_tma<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vbands + vstage * (32 * 2 * VBAND_FLOATS), &vbar[vstage]);
-#endif
-    vstage ^= 1u;
-    pv = v; ptile = tl; pvalid = valid;
-    prefetch(tl_after);
-  };
-  auto stage_b = [&](int buf) {              // warp 0 only
-    const FovLane<W::NBIT> &v = pv;
-    const bool valid = pvalid;
     float *mv = vals + (buf * 32 + lane) * W::VALS;
-#ifndef LMZ_DEBUG_NO_VISIT
-    if (W::NVIS > 0 && need_visit) {         // window update of the scaled layer + the two 5x5 visit crops
-      const uint32_t st = vstage ^ 1u;       // the buffer this tile's stage A filled (stage A toggled vstage afterwards)
-      visit_finish_tma<W>(p, ptile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vbands + st * (32 * 2 * VBAND_FLOATS),
-                          &vbar[st], (vphase >> st) & 1u, mv + W::VIS_SLOT0 * 25, mv + W::VIS_SLOT1 * 25);
-      vphase ^= 1u << st;
+#ifndef LMZ_DEBUG_NO_VISIT                   // (tuning builds only: how fast is the kernel without the visit layer?)
+    if (W::NVIS > 0 && need_visit) {         // append to / fold the visit history: the two 5x5 visit crops
+      VisitHist vh = visit_hist_of(pre);
+      visit_step<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vh, mv + W::VIS_SLOT0 * 25, mv + W::VIS_SLOT1 * 25);
     }
 #endif
     if (valid && (v.rfov || v.rloc)) {       // 25-bit planes -> float planes (lane stride VALS is odd: no bank conflicts)
@@ -367,20 +290,12 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     }
     const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
     const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
-    if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = ptile; }
-  };
-  // v2 has nothing to wait for: both stages back to back (one tile ahead of the renderers, as in round 1)
-  auto produce = [&](int buf) {
-    if (W::NVIS > 0) { stage_b(buf); stage_a(); }
-    else { stage_a(); stage_b(buf); }
+    if (lane == 0) { s_flags[buf][0] = ff; s_flags[buf][1] = fl; s_tile[buf] = tl; }
+    prefetch(tl_after);
   };
   auto pick = [](uint32_t en, const float *gv) -> uint4 { return f4_pick(en, gv); };
 
-  if (warp == 0) {
-    prefetch(grab());
-    if (W::NVIS > 0) stage_a();              // the pipeline's first tile
-    produce(0);
-  }
+  if (warp == 0) { prefetch(grab()); produce(0); }
   for (int buf = 0;; buf ^= 1) {
     __syncthreads();                          // tile(buf) is complete; buffers buf^1 are free again
     const int64_t tile = s_tile[buf];
@@ -450,7 +365,6 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
     }
   }
   if (warp == 0) {
-    if (W::NVIS > 0) bulk_wait_all();        // the last bands have left shared memory (and reached global memory)
     if (p.mode == MODE_STEP) ws.flush(p.stats, lane);
     if (lane == 0) finish_grabber(p.work, (unsigned long long)gridDim.x);
   }
@@ -463,7 +377,7 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
 // repeat_interleave(compact, 7) on both axes.  The same kernel serves launches with no observation bound.  The work
 // per tile is small, so the organisation is warp-granular like lmz_env_compact_kernel: every warp grabs its own
 // tiles (the next tile's index and state words requested one tile ahead), runs the 32 transitions, updates the
-// window of each env's scaled visit layer itself (v4 / v5, visit_warp), and ASSEMBLES the tile's 32 rows in shared
+// visit history of each env itself (v4 / v5, visit_step), and ASSEMBLES the tile's 32 rows in shared
 // memory exactly as they lie in the tensor (lane l expands env l's 25-bit planes into floats, the visit crops land
 // in their planes directly).  The tile's rows are one contiguous, 16-byte aligned run of the tensor, so the copy
 // out is ONE shared -> global bulk copy (cp.async.bulk) per tile: no per-float indexing and no store instruction.  (Round 1 looked every float up
@@ -507,6 +421,8 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
   auto preload = [&](int64_t tl, FovPre &q) {
     const int64_t e = tl * 32 + lane;
     q.w0 = q.w1 = q.w2 = 0u; q.act = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.h[k] = make_uint4(0u, 0u, 0u, 0u);
     if (tl < tiles && e < p.n) q = fov_preload<W>(p, e);
   };
   // copy of the first `bytes` of the warp's smem tile to global (both 16-byte aligned): ONE shared -> global bulk
@@ -520,15 +436,13 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
   };
-  // Software pipeline over the warp's tiles (the visit variants): the transitions of tile t+1 run -- and its visit-
-  // window loads are started -- BEFORE tile t's rows are expanded and copied out, so the loads' DRAM round trip
-  // hides behind a tile's worth of shared-memory and store work instead of stalling the warp.
+  // Software pipeline over the warp's tiles: the transitions of tile t+1 run while the TMA engine drains tile t's rows.
   struct Slot {
     FovLane<W::NBIT> v;
+    VisitHist h;
     int64_t tile;
     bool valid;
   };
-  VisitFetch vf;
   int64_t ntile = grab(), nntile = grab();
   FovPre pre;
   preload(ntile, pre);
@@ -542,17 +456,17 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     v.vinfo = 0; v.rfov = false; v.rloc = false;
 #pragma unroll
     for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
-    if (sl.valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre);
+    const FovPre pre_used = pre;
+    if (sl.valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre_used);
     if (p.mode == MODE_STEP) ws.add(sl.valid, v.o);
     ntile = nntile; nntile = after;
     preload(ntile, pre);                                         // the tile after's words fly meanwhile
-    if (W::NVIS > 0 && need_visit && sl.tile < tiles)
-      visit_issue<W>(p, sl.tile * 32, lane, sl.valid, v.info, v.vinfo, sl.valid && v.rfov, vf);
+    if (W::NVIS > 0) sl.h = visit_hist_of(pre_used);
   };
   Slot cur, nxt;
   stage_a(cur);
   while (cur.tile < tiles) {
-    const FovLane<W::NBIT> &v = cur.v;
+    const FovLane<W::NBIT> v = cur.v;
     const bool valid = cur.valid;
     const int64_t tile = cur.tile;
     const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
@@ -560,9 +474,9 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     float *mine = rows + lane * PER;
     if (W::NVIS == 0) stage_a(nxt);                              // v2: the next tile's transitions overlap the draining copy
     rows_free();                                                 // the previous tile's copy out has read the buffer
-    if (W::NVIS > 0 && need_visit)                               // window update of the scaled layer + the two crops
-      visit_finish<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vf, mine + W::VIS_SLOT0 * 25, mine + W::VIS_SLOT1 * 25);
-    if (W::NVIS > 0) stage_a(nxt);                               // next tile: transitions, visit loads in flight
+    if (W::NVIS > 0 && need_visit)                               // append to / fold the visit history: the two crops
+      visit_step<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, cur.h, mine + W::VIS_SLOT0 * 25, mine + W::VIS_SLOT1 * 25);
+    if (W::NVIS > 0) stage_a(nxt);                               // next tile's transitions overlap the draining copy
     const int64_t row0 = tile * 32 - p.win_lo;                   // obs row of the tile's first env
     if (ff) {
       if (valid && v.rfov) {                                     // 25-bit planes -> float planes (stride PER is odd: no bank conflicts)

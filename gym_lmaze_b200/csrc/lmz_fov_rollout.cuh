@@ -19,91 +19,34 @@ namespace lmz {
 
 constexpr uint32_t TAG_ACTION25 = 0x42u, TAG_HIER = 0x48u;
 
-// the visit layer of ONE env in GLOBAL memory handled by ONE thread (short rollouts)
-template <class W>
-__device__ __forceinline__ void visit_thread(float *vis, uint32_t vinfo, int bx, int by) {
-  const uint32_t op = vinfo & 7u;
-  if (op == VOP_READ) return;
-  const int tpre = (vinfo >> 3) & 127;
-  if (op == VOP_AVG) {                                     // s' = RN(s + 2^T) on the 5x5 window
-    const float add = __int_as_float((127 + tpre) << 23);
-    float *w = vis + (bx - 2) * W::G + (by - 2);
-    float v[25];
-#pragma unroll
-    for (int k = 0; k < 25; ++k) v[k] = __ldcg(w + (k / 5) * W::G + k % 5);
-#pragma unroll
-    for (int k = 0; k < 25; ++k) __stcg(w + (k / 5) * W::G + k % 5, __fadd_rn(v[k], add));
-    return;
-  }
-  const float down = visit_scale_down(tpre);               // reset, or the literal full pass of direct mode
-  float4 *row = reinterpret_cast<float4 *>(vis);
-  for (int c4 = 0; c4 < W::G * W::G / 4; ++c4) {
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (op == VOP_FULL) q = __ldcg(row + c4);
-    float *f = reinterpret_cast<float *>(&q);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int cell = 4 * c4 + k, x = cell / W::G, y = cell - x * W::G;
-      const bool in_cur = (unsigned)(x - bx + 2) < 5u && (unsigned)(y - by + 2) < 5u;
-      f[k] = (op == VOP_FULL) ? visit_average(__fmul_rn(f[k], down), in_cur) : W::visit_reset_stored(in_cur);
-    }
-    __stcg(row + c4, q);
-  }
-}
+// The visit layer during a rollout.  Nobody looks at the layer while a rollout runs, so in history mode (lmz_v2.cuh,
+// "visit layer") an averaging only APPENDS its window centre to the env's 64-byte history -- kept in shared memory for
+// the whole launch (one row per thread, 68-byte stride: no bank conflicts) -- and a reset sets the length to 0.  No
+// float is touched.  An env in DIRECT mode (history full, or a layer set through lmz_set_visit) averages its layer
+// in global memory with the literal full pass, by its own thread; the step that finds the history full
+// materialises the layer from it first.
+constexpr int HIST_STRIDE = 68;                            // bytes between two threads' history rows in shared memory
 
-// The shared-memory form used by long rollouts.  A reset must not cost 324 stores -- in a warp of 32 envs SOME lane
-// resets in every other step, and the whole warp would walk the loop -- so rows are zeroed LAZILY: `rowmask` (bit r =
-// row r of the copy holds valid data) is cleared by a reset, a row is zero-filled the first time a window touches it,
-// and whatever is still unmaterialised at the end of the launch is zero-filled before the layer is copied out.
 template <class W>
-__device__ __forceinline__ void visit_rows_valid(float *vis, uint32_t &rowmask, uint32_t want) {
-  uint32_t miss = want & ~rowmask;
-  while (miss) {
-    const int r = __ffs(miss) - 1;
-    miss &= miss - 1;
-#pragma unroll
-    for (int y = 0; y < W::G; ++y) vis[r * W::G + y] = 0.0f;
-  }
-  rowmask |= want;
-}
-template <class W>
-__device__ __forceinline__ void visit_thread_smem(float *vis, uint32_t vinfo, int bx, int by, uint32_t &rowmask) {
+__device__ __forceinline__ void visit_thread(float *layer, uint8_t *hrow, uint32_t vinfo, int bx, int by) {
   const uint32_t op = vinfo & 7u;
-  if (op == VOP_READ) return;
-  const int tpre = (vinfo >> 3) & 127;
-  float *w = vis + (bx - 2) * W::G + (by - 2);
-  if (op == VOP_RESET) {                                   // zeros everywhere (lazily), the reset value on the window
-    rowmask = 0;
-    visit_rows_valid<W>(vis, rowmask, 31u << (bx - 2));
-    const float v = W::visit_reset_stored(true);
-    if (v != 0.0f) {
-#pragma unroll
-      for (int k = 0; k < 25; ++k) w[(k / 5) * W::G + k % 5] = v;
-    }
-    return;
-  }
-  if (op == VOP_AVG) {                                     // s' = RN(s + 2^T) on the 5x5 window
-    visit_rows_valid<W>(vis, rowmask, 31u << (bx - 2));
-    const float add = __int_as_float((127 + tpre) << 23);
-#pragma unroll
-    for (int k = 0; k < 25; ++k) w[(k / 5) * W::G + k % 5] = __fadd_rn(w[(k / 5) * W::G + k % 5], add);
-    return;
-  }
-  visit_rows_valid<W>(vis, rowmask, (1u << W::G) - 1u);    // direct mode: the literal full pass
-  const float down = visit_scale_down(tpre);
+  const int tpre = (vinfo >> 3) & 127, tpost = (vinfo >> 10) & 127;
+  if (op == VOP_AVG || (op == VOP_RESET && W::VT_RESET == 1)) { hrow[tpost - 1] = (uint8_t)visit_entry(bx, by); return; }
+  if (op != VOP_FULL) return;
   for (int cell = 0; cell < W::G * W::G; ++cell) {
     const int x = cell / W::G, y = cell - x * W::G;
-    const bool in_cur = (unsigned)(x - bx + 2) < 5u && (unsigned)(y - by + 2) < 5u;
-    vis[cell] = visit_average(__fmul_rn(vis[cell], down), in_cur);
+    float v;
+    if (tpre == VT_DIRECT) v = __ldcg(layer + cell);
+    else {                                                 // the history is full: this cell's value from it
+      v = 0.0f;
+      for (int k = 0; k < tpre; ++k) {
+        const int hx = (hrow[k] >> 4) + 2, hy = (hrow[k] & 15) + 2;
+        v = visit_avg1(v, (unsigned)(x - hx + 2) < 5u && (unsigned)(y - hy + 2) < 5u);
+      }
+    }
+    __stcg(layer + cell, visit_average(v, (unsigned)(x - bx + 2) < 5u && (unsigned)(y - by + 2) < 5u));
   }
 }
-
-// Long rollouts keep every env's layer in SHARED memory for the whole launch: a window update per step in global memory
-// is 50 uncoalesced accesses per thread (32 different sectors per warp instruction; v4, 2^21 envs x T=64: 69.7 ms), in
-// shared memory it is 50 conflict-free LDS / STS.  The CTA's layers (consecutive envs: one contiguous block) are copied
-// in and out with coalesced accesses, 1,296 B read + 1,296 B written per env per LAUNCH.
-constexpr int VIS_STRIDE = 325;                            // floats between two threads' layers (odd: no bank conflicts)
-constexpr int VIS_SMEM_MIN_T = 8;                          // shorter rollouts update the layer in global memory
 
 struct RolloutCounters {
   uint32_t steps = 0, ep = 0, goal = 0, wall = 0, move = 0, stale = 0;
@@ -118,14 +61,14 @@ __device__ __forceinline__ void rollout_store_reward(const KParams &p, int64_t o
 // ---- lmaze-v2 / lmaze-v4 ------------------------------------------------------------------------------------
 // Philox action of env g at global rollout step t: word t & 3 of philox(ctr = (g_lo, g_hi, b_lo, (b_hi << 8) | 0x42)),
 // b = t >> 2; action = (word * 25) >> 32.
-template <class W, bool VIS_SMEM>
+template <class W>
 __device__ __forceinline__ void rollout_env_v2(const KParams &p, int64_t e, const FovTables<W> &t, RolloutCounters &c,
-                                               float *vis) {
+                                               uint8_t *hrow) {
   V2Regs r = v2_unpack(p.state[e], p.goal_count[e]);
   uint32_t ep = p.episode[e];
   const uint64_t gid = p.env_id0 + (uint64_t)e;
   uint32_t w[4] = {0, 0, 0, 0};
-  uint32_t rowmask = (1u << W::G) - 1u;                    // VIS_SMEM: every row of the copy is valid at the start
+  float *layer = W::NVIS > 0 ? p.visit + e * (W::G * W::G) : nullptr;
   uint64_t tg = p.t0;
   int64_t off = e;
   for (int s = 0; s < p.T; ++s, ++tg, off += p.n) {
@@ -150,12 +93,8 @@ __device__ __forceinline__ void rollout_env_v2(const KParams &p, int64_t e, cons
       c.ep += 1; c.len += r.step; c.goal += (cls == CLS_X);
       if (p.autoreset) { v2_respawn<W>(r, p, e, ep, t); want = 2; }
     }
-    if (W::NVIS > 0) {
-      const uint32_t vinfo = visit_plan<W>(want, r.vt);
-      if (VIS_SMEM) visit_thread_smem<W>(vis, vinfo, r.x, r.y, rowmask); else visit_thread<W>(vis, vinfo, r.x, r.y);
-    }
+    if (W::NVIS > 0) visit_thread<W>(layer, hrow, visit_plan<W>(want, r.vt), r.x, r.y);
   }
-  if (W::NVIS > 0 && VIS_SMEM) visit_rows_valid<W>(vis, rowmask, (1u << W::G) - 1u);   // materialise the lazy zeros
   c.steps += (uint32_t)p.T;
   uint32_t w0, w1;
   v2_pack(r, w0, w1);
@@ -165,13 +104,13 @@ __device__ __forceinline__ void rollout_env_v2(const KParams &p, int64_t e, cons
 // ---- lmaze-v5 / lmaze-v6 ------------------------------------------------------------------------------------
 // Philox goal / action of env g at global rollout step t: philox(ctr = (g_lo, g_hi, t_lo, (t_hi << 8) | 0x48));
 // goal = (word0 * 25) >> 32, action = word1 >> 30.
-template <class W, bool VIS_SMEM>
+template <class W>
 __device__ __forceinline__ void rollout_env_v5(const KParams &p, int64_t e, const FovTables<W> &t, const unsigned char *sb,
-                                               RolloutCounters &c, float *vis) {
+                                               RolloutCounters &c, uint8_t *hrow) {
   V5Regs r = v5_unpack(p.state[e], p.goal_count[e], p.aux2[e]);
   uint32_t ep = p.episode[e];
   const uint64_t gid = p.env_id0 + (uint64_t)e;
-  uint32_t rowmask = (1u << W::G) - 1u;                    // VIS_SMEM: every row of the copy is valid at the start
+  float *layer = p.visit + e * (W::G * W::G);
   uint64_t tg = p.t0;
   int64_t off = e;
   for (int s = 0; s < p.T; ++s, ++tg, off += p.n) {
@@ -198,10 +137,8 @@ __device__ __forceinline__ void rollout_env_v5(const KParams &p, int64_t e, cons
     c.wall += (cls == CLS_W); c.move += (cls == CLS_B || cls == CLS_X);
     if (done) { c.ep += 1; c.len += r.fstep; c.goal += (cls == CLS_X); }
     if (r.gd && p.autoreset) { v5_respawn<W>(r, p, e, ep, t, sb); want = 2; }
-    const uint32_t vinfo = visit_plan<W>(want, r.vt);
-    if (VIS_SMEM) visit_thread_smem<W>(vis, vinfo, r.x, r.y, rowmask); else visit_thread<W>(vis, vinfo, r.x, r.y);
+    visit_thread<W>(layer, hrow, visit_plan<W>(want, r.vt), r.x, r.y);
   }
-  if (VIS_SMEM) visit_rows_valid<W>(vis, rowmask, (1u << W::G) - 1u);                  // materialise the lazy zeros
   c.steps += (uint32_t)p.T;
   uint32_t w0, w1, w2;
   v5_pack(r, w0, w1, w2);
@@ -209,44 +146,32 @@ __device__ __forceinline__ void rollout_env_v5(const KParams &p, int64_t e, cons
   if (p.fgoal_out) p.fgoal_out[e] = (uint8_t)r.fga;
 }
 
-template <class W, int THREADS, bool VIS_SMEM>
+template <class W, int THREADS>
 __global__ void __launch_bounds__(THREADS) lmz_fov_rollout_kernel(const KParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];         // the per-maze tables (blob from ROWBITS_OFF on) [+ the layers]
+  extern __shared__ __align__(128) unsigned char smem[];         // the per-maze tables (blob from ROWBITS_OFF on) + the history rows
   __shared__ unsigned long long blk_stats[NUM_STATS];
   constexpr uint32_t STAGE_OFF = W::ROWBITS_OFF;
   constexpr uint32_t TAB_BYTES = (W::BLOB_BYTES - STAGE_OFF + 15u) & ~15u;
-  constexpr int GG = W::G * W::G;
   for (uint32_t i = threadIdx.x; i < (W::BLOB_BYTES - STAGE_OFF) / 4; i += THREADS)
     reinterpret_cast<uint32_t *>(smem)[i] = reinterpret_cast<const uint32_t *>(p.blob + STAGE_OFF)[i];
   if (threadIdx.x < NUM_STATS) blk_stats[threadIdx.x] = 0;
   __syncthreads();
   const unsigned char *sb = smem - STAGE_OFF;
   const FovTables<W> t(sb);
-  float *layers = reinterpret_cast<float *>(smem + TAB_BYTES);   // VIS_SMEM: [THREADS][VIS_STRIDE]
+  uint8_t *hrow = smem + TAB_BYTES + threadIdx.x * HIST_STRIDE;  // this thread's visit history (v4 / v5)
   RolloutCounters c;
-  for (int64_t base = (int64_t)blockIdx.x * THREADS; base < p.n; base += (int64_t)gridDim.x * THREADS) {
-    const int64_t e = base + threadIdx.x;
-    const int cnt = (int)((p.n - base) < THREADS ? (p.n - base) : THREADS);        // envs of this CTA pass
-    float *vis = nullptr;
-    if (W::NVIS > 0) {
-      if (VIS_SMEM) {                                            // the pass's layers are one contiguous block: coalesced copy in
-        const float *src = p.visit + base * GG;
-        for (int i = threadIdx.x; i < cnt * GG; i += THREADS) layers[(i / GG) * VIS_STRIDE + i % GG] = __ldcs(src + i);
-        __syncthreads();
-        vis = layers + threadIdx.x * VIS_STRIDE;
-      } else {
-        vis = p.visit + e * GG;
-      }
+  for (int64_t e = (int64_t)blockIdx.x * THREADS + threadIdx.x; e < p.n; e += (int64_t)gridDim.x * THREADS) {
+    if (W::NVIS > 0) {                                           // history in: 64 contiguous bytes per env
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(p.hist + e * HIST_MAX);
+#pragma unroll
+      for (int k = 0; k < HIST_MAX / 4; ++k) reinterpret_cast<uint32_t *>(hrow)[k] = __ldcs(src + k);
     }
-    if (e < p.n) {
-      if constexpr (W::HAS_LOC) rollout_env_v5<W, VIS_SMEM>(p, e, t, sb, c, vis);
-      else rollout_env_v2<W, VIS_SMEM>(p, e, t, c, vis);
-    }
-    if (W::NVIS > 0 && VIS_SMEM) {                               // ... and out
-      __syncthreads();
-      float *dst = p.visit + base * GG;
-      for (int i = threadIdx.x; i < cnt * GG; i += THREADS) __stcs(dst + i, layers[(i / GG) * VIS_STRIDE + i % GG]);
-      __syncthreads();
+    if constexpr (W::HAS_LOC) rollout_env_v5<W>(p, e, t, sb, c, hrow);
+    else rollout_env_v2<W>(p, e, t, c, hrow);
+    if (W::NVIS > 0) {                                           // ... and out
+      uint32_t *dst = reinterpret_cast<uint32_t *>(p.hist + e * HIST_MAX);
+#pragma unroll
+      for (int k = 0; k < HIST_MAX / 4; ++k) __stcs(dst + k, reinterpret_cast<const uint32_t *>(hrow)[k]);
     }
   }
   unsigned long long v[NUM_STATS] = {c.steps, c.ep, c.goal, (unsigned long long)(c.ep - c.goal), c.wall, c.move, c.stale, c.len};

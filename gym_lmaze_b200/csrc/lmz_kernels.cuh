@@ -52,7 +52,8 @@ struct KParams {
   uint32_t *state;              // packed per-env state
   uint32_t *goal_count;         // goalCount per env (v0; lmaze_env.py:24,195)
   uint32_t *episode;            // resets so far (RNG counter)
-  float *visit;                 // v4: state[2] visit layer, f32 [n][18*18]
+  float *visit;                 // v4 / v5: state[2] visit layer, f32 [n][18*18] -- holds the layer of envs in DIRECT mode only
+  uint8_t *hist;                // v4 / v5: visit history, u8 [n][64]: the window centre of each averaging since the reset
   void *obs;                    // f32 [win_n][C][S][S], or u8 [win_n][C][G][G] (compact), or null
   int64_t win_lo, win_n;        // obs rows hold envs [win_lo, win_lo + win_n)
   int64_t tile_begin, tile_end; // tiles (32 envs) this launch visits

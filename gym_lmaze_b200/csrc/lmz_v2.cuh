@@ -34,7 +34,6 @@ struct Fov {
     return C_ == 7 ? (b < 2 ? b : b + 1) : b;
   }
   __device__ static __forceinline__ float visit_reset(bool in_cur) { return in_cur ? 0.5f : 0.0f; }   // zeros, then :110-113
-  __device__ static __forceinline__ float visit_reset_stored(bool in_cur) { return in_cur ? 1.0f : 0.0f; }   // the same, scaled by 2^VT_RESET
   static constexpr bool MAZE_FIRST = (ID_ == 4);                       // v4 re-rolls the maze BEFORE drawing goal/ball (:91-98)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                    // 6,125 (v2) / 8,575 (v4)
   static constexpr uint32_t OBS_BYTES = OBS_FLOATS * 4;                // 24,500 / 34,300
@@ -52,7 +51,7 @@ struct Fov {
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G);     // u8 ng[5], nb[5]
   static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;                           // u16 [5]: each maze's 'X' cell
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
-  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * 2 * 368 : 0);   // + the double-buffered per-env value planes
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;   // + the double-buffered per-env value planes
   static constexpr int VT_RESET = 1;                                   // v4 reset(): zeros, then ONE averaging (lmaze_env_v4.py:110-119)
 };
 using V2 = Fov<2, 5>;
@@ -61,41 +60,45 @@ using V4 = Fov<4, 7>;
 struct V2Regs {
   int L, x, y, gx, gy, px, py, a;     // a: last action, -1 right after a reset (action plane all zero)
   uint32_t step;
-  int vt;                             // v4: scale exponent of the stored visit layer (see "visit layer" below)
+  int vt;                             // v4: entries in the visit history, or VT_DIRECT (see "visit layer" below)
 };
 
-// ---- the float visit layer of v4 / v5, stored SCALED --------------------------------------------------------------
+// ---- the float visit layer of v4 / v5, kept as its HISTORY -----------------------------------------------------------
 // Reference: state[2] = (state[2] + visitMap) / 2 over all 324 cells, visitMap = 1 on the 5x5 window around the ball
-// (lmaze_env_v4.py:116-119,211-214; lmaze_env_v5.py:308-312): EVERY cell halves on every averaging, so a literal
-// implementation reads and writes the whole 1,296-byte layer per env-step.  Halving a normal float is exact, so the
-// layer is kept as  s = v * 2^T  with ONE per-env exponent T = averagings since the last rebase:
-//     out-of-window cell:  v' = v / 2          <=>  s' = s                (no memory traffic at all)
-//     in-window cell:      v' = RN((v + 1) / 2) <=>  s' = RN(s + 2^T)      (25 cells read + written)
-//     shown value:         v  = s * 2^-T                                     (exact: power-of-two scaling of a normal)
-// RN(s + 2^T) = RN(v + 1) * 2^T because scaling by a power of two commutes with rounding while everything stays
-// normal, and RN32(v + 1) / 2 is what the reference's float64 expression rounds to (visit_average in lmz_fov.cuh).
-// "Everything stays normal" holds while T <= VT_MAX: every non-zero true value is >= 2^-T.  An env that is averaged
-// more than VT_MAX times without a reset (only possible by stepping on far past `done` with autoreset off, or after
-// lmz_set_visit, whose values carry no such bound) falls back to DIRECT mode (T field = VT_DIRECT): the layer holds
-// the true values and every averaging is the literal full pass, denormal roundings included.  reset() returns to
-// the scaled form.  lmz_get_visit / lmz_set_visit exchange TRUE values.
-constexpr int VT_MAX = 100, VT_DIRECT = 127;
+// (lmaze_env_v4.py:116-119,211-214; lmaze_env_v5.py:308-312), starting from zeros at reset().  EVERY cell changes on
+// every averaging, so a literal implementation reads and writes the whole 1,296-byte layer per env-step, and any
+// implementation that keeps the layer in memory has to touch the env's own scattered piece of it every step -- which
+// is what limits a kernel whose job is a saturated write stream (~2.5 KB of streaming per request).
+// But the layer is a pure function of WHERE the ball was at each averaging since the reset:
+//     v_cell = fold over the averagings k = 0 .. T-1 of   v <- RN32((v + [cell in window_k]) / 2),   v = 0 before k = 0
+// so per env only those window centres are stored: hist u8 [N][64], byte k = (x_k - 2) << 4 | (y_k - 2), T in the state
+// word.  An averaging APPENDS one byte; a reset sets T = 0 (v4: and appends the spawn cell, its reset averages once);
+// an observation needs the layer at 50 cells (the window at the ball and the previous window) and gets them by
+// running the fold over the T <= 64 entries in registers -- the same float32 operation sequence as the reference
+// (RN32((v + m) / 2) = fma(v, 0.5, m / 2) exactly, denormals included), so the values are bit-identical.  The 32 rows of
+// a tile are 2 KB of contiguous memory, read together with the state words a tile ahead.
+// An env whose history is full (64 averagings without a reset: only by stepping on far past `done` with autoreset
+// off) or whose layer was set through lmz_set_visit (arbitrary values have no history) falls back to DIRECT mode
+// (T field = VT_DIRECT): its layer lives in `visit f32 [N][324]` and every averaging is the literal full pass;
+// reset() returns to the history form.  lmz_get_visit / lmz_set_visit exchange the layer itself.
+constexpr int HIST_MAX = 64, VT_DIRECT = 127;
 enum : uint32_t { VOP_READ = 0, VOP_AVG = 1, VOP_RESET = 2, VOP_FULL = 3 };
 // want: 0 nothing, 1 average with the window at the ball, 2 reset.  vinfo = op:3 | T before:7 | T after:7
+// VOP_FULL with T before != VT_DIRECT: the history is full -- materialise the layer from it first, then the full pass.
 template <class W>
 __device__ __forceinline__ uint32_t visit_plan(int want, int &vt) {
   const int tpre = vt;
   uint32_t op = VOP_READ;
   if (want == 2) { op = VOP_RESET; vt = W::VT_RESET; }
   else if (want == 1) {
-    if (vt >= VT_MAX) { op = VOP_FULL; vt = VT_DIRECT; }          // direct mode, or the step that converts to it
+    if (vt >= HIST_MAX) { op = VOP_FULL; vt = VT_DIRECT; }        // direct mode, or the step that converts to it
     else { op = VOP_AVG; vt = vt + 1; }
   }
   return op | ((uint32_t)tpre << 3) | ((uint32_t)vt << 10);
 }
-__device__ __forceinline__ float visit_scale_down(int t) {           // 2^-T (1.0 in direct mode)
-  return __int_as_float((127 - (t == VT_DIRECT ? 0 : t)) << 23);
-}
+// one averaging of one cell: RN32((v + m) / 2) -- v / 2 is exact inside the fma, one rounding, as in the reference's
+// float64 expression rounded to float32 (lmz_fov.cuh, visit_average)
+__device__ __forceinline__ float visit_avg1(float v, bool in_window) { return __fmaf_rn(v, 0.5f, in_window ? 0.5f : 0.0f); }
 
 // state word: L:3 | x:5 | y:5 | gx:5 | gy:5 | step:6 ; aux word: px:5 | py:5 | a:5 | a_valid:1 | visit T:7 (v4)
 __host__ __device__ inline V2Regs v2_unpack(uint32_t s, uint32_t aux) {
@@ -222,12 +225,18 @@ using V2Lane = FovLane<5>;  // free, goal, action, previous free, previous goal
 struct FovPre {
   uint32_t w0, w1, w2;
   long long act;
+  uint4 h[4];               // v4 / v5: the env's 64 visit-history bytes
 };
 template <class W>
 __device__ __forceinline__ FovPre fov_preload(const KParams &p, int64_t e) {
   FovPre q;
   q.w0 = p.state[e]; q.w1 = p.goal_count[e]; q.w2 = W::HAS_LOC ? p.aux2[e] : 0u;
   q.act = (p.mode == MODE_STEP || p.mode == 3 /* MODE_PLANNER */) ? load_action(p.actions, p.action_dtype, e) : 0;
+  if (W::NVIS > 0 && p.mode != 3) {
+    const uint4 *hp = reinterpret_cast<const uint4 *>(p.hist + e * HIST_MAX);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.h[k] = __ldcg(hp + k);
+  }
   return q;
 }
 
@@ -323,7 +332,7 @@ __global__ void lmz_state_v2_kernel(int64_t n, uint32_t *state, uint32_t *auxw, 
                r.px != (row[6] & 31) || r.py != ((row[6] >> 5) & 31) || r.a > 24;
     if (bad) atomicAdd(errors, 1u);
     if (r.a > 24) r.a = 24;
-    r.vt = (auxw[e] >> 16) & 127;                 // the visit layer's scale exponent is not part of the row: kept
+    r.vt = (auxw[e] >> 16) & 127;                 // the visit history length is not part of the row: kept
     uint32_t s, aux;
     v2_pack(r, s, aux);
     state[e] = s; auxw[e] = aux; episode[e] = (uint32_t)row[7];

@@ -40,7 +40,6 @@ struct V5 {
   static constexpr int VIS_SLOT0 = 2, VIS_SLOT1 = 6;
   __host__ __device__ static constexpr int bit_slot(int b) { return b < 2 ? b : (b < 5 ? b + 1 : b + 2); }   // 0 1 3 4 5 7 8 9 10
   __device__ static __forceinline__ float visit_reset(bool) { return 0.0f; }   // self.state = zeros (:134), no averaging
-  __device__ static __forceinline__ float visit_reset_stored(bool) { return 0.0f; }
   static constexpr int VT_RESET = 0;
   static constexpr bool MAZE_FIRST = true;                                   // reset(): setGrid() first (:104,115-116)
   static constexpr uint32_t OBS_FLOATS = C * S * S;                          // 8,575 (foveal)
@@ -60,7 +59,7 @@ struct V5 {
   static constexpr uint32_t COUNT_OFF = BRANK_OFF + align16(NLAYOUT * G * G); // u8 ng[5], nb[5]; u16 xcell[5] at +16
   static constexpr uint32_t XCELL_OFF = COUNT_OFF + 16;
   static constexpr uint32_t BLOB_BYTES = COUNT_OFF + 32;
-  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4 + (NVIS > 0 ? 2 * 32 * 2 * 368 : 0);
+  static constexpr uint32_t SMEM_BYTES = BLOB_BYTES + 2 * 32 * VALS * 4;
 };
 
 struct V5Regs {
@@ -72,7 +71,7 @@ struct V5Regs {
   int fga;                    // hot cell of fovealGoal   (:166-168; 12 after reset, :131-132)
   uint32_t step, fstep;       // stepCount, fovealStepCount (saturating; only >= 10 / >= 50 / == 0 matter)
   int ld, gd;                 // localDone, globalDone
-  int vt;                     // scale exponent of the stored visit layer (lmz_v2.cuh, "visit layer")
+  int vt;                     // entries in the visit history, or VT_DIRECT (lmz_v2.cuh, "visit layer")
 };
 
 // w0: L:3 | x:5 | y:5 | gx:5 | gy:5 | ld:1 | gd:1 | visit T:7      w1: x1:5 | y1:5 | fx1:5 | fy1:5 | fgx:5 | fgy:5
@@ -367,7 +366,7 @@ __global__ void lmz_state_v5_kernel(int64_t n, uint32_t *state, uint32_t *aux1, 
                      r.fy1 != row[5] || r.gx != row[6] || r.gy != row[7] || r.fgx != row[8] || r.fgy != row[9] ||
                      r.lx != row[10] || r.ly != row[11] || r.fga != row[12] || row[13] < 0 || row[14] < 0 || r.L != L;
     if (bad) atomicAdd(errors, 1u);
-    r.vt = (state[e] >> 25) & 127;                  // the visit layer's scale exponent is not part of the row: kept
+    r.vt = (state[e] >> 25) & 127;                  // the visit history length is not part of the row: kept
     uint32_t w0, w1, w2;
     v5_pack(r, w0, w1, w2);
     state[e] = w0; aux1[e] = w1; aux2[e] = w2; episode[e] = (uint32_t)row[16];

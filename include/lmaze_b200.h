@@ -238,9 +238,10 @@ int lmz_get_state_dl(lmz_env *env, DLManagedTensor *out, void *stream);
 int lmz_set_state_dl(lmz_env *env, DLManagedTensor *in, void *stream);
 
 /* lmaze-v4 / v5 / v6: the float visit layer state[2] of every env (lmaze_env_v4.py:106-113,211-214; lmaze_env_v5.py:308-312),
- * f32 [N][18][18] on the device -- part of the checkpoint next to lmz_get_state.  These are the TRUE values; the handle
- * itself keeps the layer scaled by a per-env power of two.  After lmz_set_visit an env averages
- * its layer with the literal full pass until its next reset (nothing is known about how small the supplied values are). */
+ * f32 [N][18][18] on the device -- part of the checkpoint next to lmz_get_state.  The handle itself keeps the layer as
+ * its HISTORY (the window centre of every averaging since the reset, 64 bytes per env) and
+ * computes the values from it; lmz_get_visit materialises them.  A layer written with lmz_set_visit has no history:
+ * that env averages its layer in memory with the literal full pass until its next reset. */
 int lmz_get_visit(lmz_env *env, float *out, void *stream);
 int lmz_set_visit(lmz_env *env, const float *in, void *stream);
 int lmz_get_visit_dl(lmz_env *env, DLManagedTensor *out, void *stream);

@@ -284,16 +284,17 @@ def test_host_pipeline_matches_oracle(lmz, oracle_mod, variant, obs_mode):
     env.close()
 
 
-# ---------------------------------------------------------------- the SCALED visit layer (v4 / v5), edge cases
+# ---------------------------------------------------------------- the visit layer kept as its HISTORY (v4 / v5), edge cases
 def u32(t):
     return (t.detach().cpu().numpy() if torch.is_tensor(t) else t).view(np.uint32)
 
 
 @pytest.mark.parametrize("obs_mode", ["full", "compact"])
 def test_v4_visit_layer_long_episode_without_reset(lmz, oracle_mod, obs_mode):
-    """autoreset off and no reset for 330 steps: the layer is averaged 330 times in a row, far past VT_MAX = 100
-    (conversion to direct mode at the 100th averaging) and deep into the float32 denormals (values halve down to
-    2^-149 and round to zero step by step).  Whole layer + whole observation vs the oracle, bit for bit."""
+    """autoreset off and no reset for 330 steps: the layer is averaged 330 times in a row, far past the 64 entries
+    the visit history holds (the 65th averaging materialises the layer and goes to direct mode) and deep into the
+    float32 denormals (values halve down to 2^-149 and round to zero step by step).  Whole layer + whole observation
+    vs the oracle, bit for bit."""
     N, T = 777, 330
     ora = oracle_mod.OracleVec(oracle_mod.V4, N, seed=31, autoreset=False, threads=os.cpu_count() or 1)
     env = lmz.LmazeVecCuda(N, "v4", seed=31, autoreset=False, obs_mode=obs_mode)
@@ -308,12 +309,12 @@ def test_v4_visit_layer_long_episode_without_reset(lmz, oracle_mod, obs_mode):
         obs, rew, done, _ = env.step(a)
         assert np.array_equal(rbits(rew), r_ref.view(np.uint32)) and np.array_equal(done.cpu().numpy().view(np.uint8), d_ref), t
         assert np.array_equal(u32(env.expand(obs)), u32(o_ref)), t
-        if t % 20 == 19 or t in (98, 99, 100, 101, 148, 149, 150, 151):
+        if t % 20 == 19 or t in (61, 62, 63, 64, 65, 66, 148, 149, 150, 151):
             vref = ora.export_visit()
             assert np.array_equal(u32(env.get_visit()), u32(vref)), t
             small = max(small, int(((vref > 0) & (vref < 1.2e-38)).sum()))
     assert small > 0                                           # denormals really occurred
-    # a reset returns to the scaled form and everything still matches
+    # a reset returns to the history form and everything still matches
     assert np.array_equal(u32(env.expand(env.reset())), u32(ora.reset()))
     for t in range(30):
         a = torch.randint(0, 25, (N,), generator=gen)
@@ -325,8 +326,8 @@ def test_v4_visit_layer_long_episode_without_reset(lmz, oracle_mod, obs_mode):
 
 
 def test_v4_set_visit_arbitrary_values_then_steps(lmz, oracle_mod):
-    """lmz_set_visit takes TRUE values with no bound on how small they are (direct mode until the next reset):
-    tiny, denormal and > 1 values are averaged exactly like the oracle's float64 expression."""
+    """lmz_set_visit takes arbitrary values, which have no history (direct mode until the next reset): tiny and
+    denormal values are averaged exactly like the oracle's float64 expression."""
     N, T = 300, 60
     ora = oracle_mod.OracleVec(oracle_mod.V4, N, seed=2, autoreset=False)
     env = lmz.LmazeVecCuda(N, "v4", seed=2, autoreset=False)
@@ -357,7 +358,8 @@ def test_v4_set_visit_arbitrary_values_then_steps(lmz, oracle_mod):
 
 def test_v5_visit_layer_many_averagings_without_planner(lmz, oracle_mod):
     """lmaze-v5 averages the layer on EVERY step while the local episode is over (lmaze_env_v5.py:308-312): an actor
-    that keeps stepping without plannerStep averages it hundreds of times -- past VT_MAX and into the denormals."""
+    that keeps stepping without plannerStep averages it hundreds of times -- past the 64 history entries and into the
+    denormals."""
     N, T = 600, 260
     ora = oracle_mod.OracleHier(N, seed=9)
     env = lmz.LmazeHierCuda(N, "v5", seed=9, autoreset=False)
@@ -371,7 +373,7 @@ def test_v5_visit_layer_many_averagings_without_planner(lmz, oracle_mod):
         f_ref, l_ref, gr_ref, lr_ref, gd_ref, ld_ref, err = ora.step(a)
         assert np.array_equal(u32(fov), u32(f_ref)), t
         assert np.array_equal(ld.cpu().numpy(), ld_ref.astype(bool)), t
-        if t % 20 == 19 or t in (99, 100, 101, 102):
+        if t % 20 == 19 or t in (70, 71, 72, 73, 74, 75, 76):
             assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), t
     assert int(ld_ref.sum()) > N // 2                          # most envs sat in "local episode over" for ~250 steps
     vref = ora.export_visit()
@@ -415,7 +417,7 @@ def test_foveal_rollout_kernel_parity(lmz, oracle_mod, variant):
             assert np.array_equal(u32(env.get_visit()), u32(ora.export_visit())), rnd
         full = np.stack([ora.render_one(i) for i in range(N)])
         assert np.array_equal(u32(env.render_obs()), u32(full)), rnd
-    # short rollouts (T < 8) update v4's visit layer in global memory instead of a shared-memory copy: same results
+    # short rollouts too (T = 5, 1, 7)
     for T_short in (5, 1, 7):
         acts = np.array([[oracle_mod.rng_action25(seed, 3 + i, t_glob + t) for i in range(N)] for t in range(T_short)])
         rew, done = env.rollout(T_short)
@@ -472,7 +474,7 @@ def test_hier_rollout_kernel_parity(lmz, oracle_mod, philox):
         fov_ref, loc_ref, err_ref = ora.render()
         env.render_obs()
         assert np.array_equal(u32(env.obs), u32(fov_ref)) and np.array_equal(u32(env.loc_obs), u32(loc_ref))
-        if rnd == 0:                                       # a short rollout in between (visit layer updated in global memory)
+        if rnd == 0:                                       # a short rollout in between
             ga = np.array([[oracle_mod.rng_hier(seed, 40 + i, t_glob + t) for i in range(N)] for t in range(6)])
             gr6, lr6, gd6, ld6 = env.rollout(6) if philox else env.rollout(6, goals=torch.as_tensor(ga[:, :, 0]), actions=torch.as_tensor(ga[:, :, 1]))
             t_glob += 6

@@ -35,7 +35,7 @@ run("v0 full render (TMA)", 1 << 19, "v0", "lmz_env_tma_kernel", 112910, "v0_tma
 run("v0 full render (ST128)", 1 << 18, "v0", "lmz_env_st_kernel", 112910, "v0_st128", render_mode="st128").close()
 run("v3 full render (TMA)", 1 << 19, "v3", "lmz_env_tma_kernel", 62222, "v3_tma").close()
 run("v2 full render", 1 << 20, "v2", "lmz_env_fov_kernel", 24514, "v2_tma").close()
-run("v4 full render", 1 << 19, "v4", "lmz_env_fov_kernel", 34614, "v4_tma", steps=2).close()
+run("v4 full render", 1 << 19, "v4", "lmz_env_fov_kernel", 34394, "v4_tma", steps=2).close()
 n = 1 << 19
 h = lmz.LmazeHierCuda(n, "v5", seed=1)
 h.reset(); note("v5 reset", "lmz_env_fov_kernel", n)
@@ -43,7 +43,7 @@ a = torch.randint(0, 4, (4, n), device="cuda", dtype=torch.uint8)
 g = torch.randint(0, 25, (4, n), device="cuda", dtype=torch.uint8)
 for i in range(2):      # from the second plannerStep on the auto mask has its realistic (small) size
     h.plannerStep(g[i], mask="auto"); note("v5 plannerStep (auto mask) #%d" % i, "lmz_planner_kernel", n)
-    h.step(a[i], goal_plane=False); note("v5 step #%d" % i, "lmz_env_fov_kernel", n, 54400, "v5_tma" if i == 1 else None)
+    h.step(a[i], goal_plane=False); note("v5 step #%d" % i, "lmz_env_fov_kernel", n, 54020, "v5_tma" if i == 1 else None)
 rew = h.rollout(32); note("v5 rollout T=32 (planner + actor)", "lmz_fov_rollout_kernel", n)
 torch.cuda.synchronize(); h.close()
 run("v0 compact u8", 1 << 22, "v0", "lmz_env_compact_kernel", 590, obs_mode="compact").close()
@@ -56,7 +56,7 @@ for i in range(2):
     e.step(a[i]); note("v0 incremental step #%d" % i, "lmz_env_incr_kernel", 1 << 19, 406)
 torch.cuda.synchronize(); e.close()
 run("v2 compact f32 crops", 1 << 22, "v2", "lmz_fov_small_kernel", 514, obs_mode="compact").close()
-run("v4 compact f32 crops", 1 << 21, "v4", "lmz_fov_small_kernel", 1014, obs_mode="compact", steps=2).close()
+run("v4 compact f32 crops", 1 << 21, "v4", "lmz_fov_small_kernel", 794, obs_mode="compact", steps=2).close()
 e = lmz.LmazeVecCuda(1 << 22, "v0", seed=1, with_obs=False)
 e.reset(); note("v0 transition-only reset", "lmz_env_compact_kernel", 1 << 22)
 a = torch.randint(0, 4, (1 << 22,), device="cuda", dtype=torch.uint8)
