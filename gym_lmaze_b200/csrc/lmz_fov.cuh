@@ -16,17 +16,17 @@
 // Warp 0 is a dedicated producer: it runs the tile's 32 transitions (one env per lane, state in registers) and
 // expands each env's 25-bit planes into float planes in shared memory, one tile ahead of the rendering warps and
 // one tile ahead of its OWN loads (next tile's index, state words, actions).  For the variants with a float visit
-// layer (v4, v5) the same producer warp keeps the layer up to date: the layer is stored SCALED (lmz_v2.cuh, "visit
-// layer"), so an averaging step touches only the 25 cells of the window around the ball instead of all 324 -- one
-// env per lane, 50 independent loads (the window and the previous window), 25 stores -- and the two 5x5 visit crops
-// go into the same value planes.  Everything is double buffered; one __syncthreads per tile.  FEWER rendering warps
-// reach a HIGHER write bandwidth (tools/fov_sweep2.py): 1 producer + 3 rendering warps per SM for v2.
+// layer (v4, v5) the same producer warp keeps the layer: as its HISTORY (lmz_v2.cuh, "visit layer") -- 64 bytes of
+// window centres per env, loaded with the state words; an averaging appends a byte, and the two 5x5 visit crops an
+// observation shows are folded from the history in registers (bit-identical to the reference's float expression) and
+// go into the same value planes.  No layer is read or written.  Everything is double buffered; one __syncthreads per
+// tile.  FEWER rendering warps reach a HIGHER write bandwidth (tools/fov_sweep2.py): 1 producer + 3 rendering warps per SM.
 #pragma once
 #include "lmz_v2.cuh"
 #include "lmz_v5.cuh"
 
 #ifndef LMZ_VISIT_PROD
-#define LMZ_VISIT_PROD 32     // v4 / v5: producer threads (round 1 used 128 for a full-layer pass; the scaled layer needs one warp)
+#define LMZ_VISIT_PROD 32     // v4 / v5: producer threads (round 1 used 128 for a full-layer pass; the visit history needs one warp)
 #endif
 #ifndef LMZ_V2_PROD
 #define LMZ_V2_PROD 32    // v2: one dedicated producer warp (0: warp 0 produces, then renders with the others)
