@@ -38,3 +38,13 @@ def test_sass_summary_matches_the_current_kernel_sources():
     assert count(tma, "UBLKCP.S.G") >= 1 and count(tma, "UBLKCP.G.S") >= 1 and count(tma, "SYNCS") >= 1
     for l in rows.values():
         assert count(l, "HMMA") == 0 and count(l, "DFMA") == 0 and count(l, "DADD") == 0
+
+
+def test_source_hash_covers_every_kernel_source():
+    """Every file under csrc/ and include/ takes part in the hash (and in the build's staleness check)."""
+    from gym_lmaze_b200 import build
+    listed = {os.path.abspath(f) for f in build.SOURCES + build.HEADERS}
+    on_disk = set()
+    for d in (os.path.join(ROOT, "gym_lmaze_b200", "csrc"), os.path.join(ROOT, "include")):
+        on_disk |= {os.path.abspath(os.path.join(d, f)) for f in os.listdir(d) if f.endswith((".cu", ".cuh", ".h"))}
+    assert on_disk == listed, sorted(on_disk ^ listed)
