@@ -68,37 +68,45 @@ __device__ __forceinline__ uint32_t visit_cover(int h, int o) {
 }
 
 // The layer's values on TWO 5x5 windows (origins (ax, ay) and (bx, by) = centre - 2) after the first `T` averagings
-// of the history: the reference's fold, one fma per cell and entry.  `tmax` >= T is warp-uniform (the loop bound).
-__device__ __forceinline__ void visit_fold2(const VisitHist &h, int T, int tmax, int ax, int ay, int bx, int by,
+// of the history: the reference's fold, per entry and cell ONE select (the addend) and ONE fma.  `tmax` >= T is
+// warp-uniform (the loop bound); entries past this lane's T are skipped by its own predicate.
+// The loop over the history words is ROLLED on purpose (one word = 4 entries per trip, ~10 KB of code): fully
+// unrolled, the fold is 64 x ~150 instructions = 150 KB of straight-line code that every warp streams through once
+// per tile -- far beyond the instruction caches, and the compact kernel then waits for instruction FETCH
+// (ncu: `no_instruction`) instead of issuing.  Registers cannot be indexed by the trip count, so the words are
+// ROTATED through h.w[0] instead (15 moves per trip); `h` is consumed.
+__device__ __forceinline__ void visit_fold2(VisitHist &h, int T, int tmax, int ax, int ay, int bx, int by,
                                             float *va, float *vb) {
 #pragma unroll
   for (int c = 0; c < 25; ++c) { va[c] = 0.0f; vb[c] = 0.0f; }
+#pragma unroll 1
+  for (int k0 = 0; k0 < tmax; k0 += 4) {                     // (warp-uniform bound)
+    const uint32_t w = h.w[0];
 #pragma unroll
-  for (int g = 0; g < 16; ++g) {
-    if (4 * g < tmax) {                                      // (warp-uniform; no `break`: the loop must unroll completely)
-    const uint32_t w = h.w[g];
+    for (int g = 0; g < 15; ++g) h.w[g] = h.w[g + 1];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int k = 4 * g + b;
-      const bool live = k < T;
-      const uint32_t e = (w >> (8 * b)) & 255u;
-      const int hx = (int)(e >> 4) + 2, hy = (int)(e & 15u) + 2;
-      const float mul = live ? 0.5f : 1.0f;                  // entries past this lane's T leave the values alone
-      const uint32_t ra = live ? visit_cover(hx, ax) : 0u, ca = visit_cover(hy, ay);
-      const uint32_t rb = live ? visit_cover(hx, bx) : 0u, cb = visit_cover(hy, by);
-      float adda[5], addb[5];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) { adda[j] = ((ca >> j) & 1u) ? 0.5f : 0.0f; addb[j] = ((cb >> j) & 1u) ? 0.5f : 0.0f; }
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const bool ia = (ra >> i) & 1u, ib = (rb >> i) & 1u;
+      if (k0 + b < T) {
+        const uint32_t e = (w >> (8 * b)) & 255u;
+        const int hx = (int)(e >> 4), hy = (int)(e & 15u);    // centre - 2 = the entry's window origin
+        // row i of window A (absolute row ax + i) is covered by the entry iff 0 <= ax + i - hx < 5
+        const int rxa = ax - hx, rya = ay - hy, rxb = bx - hx, ryb = by - hy;
+        float adda[5], addb[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
-          va[i * 5 + j] = __fmaf_rn(va[i * 5 + j], mul, ia ? adda[j] : 0.0f);
-          vb[i * 5 + j] = __fmaf_rn(vb[i * 5 + j], mul, ib ? addb[j] : 0.0f);
+          adda[j] = ((unsigned)(rya + j) < 5u) ? 0.5f : 0.0f;
+          addb[j] = ((unsigned)(ryb + j) < 5u) ? 0.5f : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const bool ia = (unsigned)(rxa + i) < 5u, ib = (unsigned)(rxb + i) < 5u;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            va[i * 5 + j] = __fmaf_rn(va[i * 5 + j], 0.5f, ia ? adda[j] : 0.0f);
+            vb[i * 5 + j] = __fmaf_rn(vb[i * 5 + j], 0.5f, ib ? addb[j] : 0.0f);
+          }
         }
       }
-    }
     }
   }
 }

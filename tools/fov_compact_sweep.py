@@ -16,7 +16,7 @@ def run(variant, N, cap, thr=0):
             env.plannerStep(g[i % 4], mask="auto"); env.step(a[i % 4], goal_plane=False)
         else:
             env.step(a[i % 4])
-    for i in range(5):
+    for i in range(int(os.environ.get("WARM", "5"))):      # WARM=60: episodes in steady state
         step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

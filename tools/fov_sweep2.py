@@ -16,7 +16,7 @@ def run(variant, N, nbytes, thr, cap):
             env.plannerStep(g[i % 4], mask="auto"); env.step(a[i % 4], goal_plane=False)
         else:
             env.step(a[i % 4])
-    for i in range(4):
+    for i in range(int(os.environ.get("WARM", "4"))):      # WARM=60: episodes in steady state (visit histories at their usual length)
         step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

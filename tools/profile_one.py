@@ -8,7 +8,7 @@ variant = sys.argv[1]
 obs_mode = sys.argv[2] if len(sys.argv) > 2 else "full"
 n = 1 << (int(sys.argv[3]) if len(sys.argv) > 3 else 19)
 render_mode = sys.argv[4] if len(sys.argv) > 4 else "tma"
-steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3      # ncu: -s (launches to skip) chooses which of them is captured
 hier = variant == "v5"
 env = (lmz.LmazeHierCuda(n, "v5", seed=1, obs_mode=obs_mode) if hier
        else lmz.LmazeVecCuda(n, variant, seed=1, obs_mode=obs_mode, render_mode=render_mode))
