@@ -807,15 +807,18 @@ int lmz_create(const lmz_config *cfg, lmz_env **out) {
   }
   const size_t n = (size_t)cfg->num_envs;
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = cudaMalloc(&h->state, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&h->goal_count, n * sizeof(uint32_t));
+  // (the per-env state arrays are padded to whole 32-env tiles: the compact foveal kernel fetches a tile's words as
+  // fixed-size bulk copies, lmz_fov.cuh)
+  const size_t n32 = ((size_t)n + 31) & ~(size_t)31;
+  if (e == cudaSuccess) e = cudaMalloc(&h->state, n32 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->goal_count, n32 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->episode, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->blob, blob.size());
-  if (e == cudaSuccess && hier) e = cudaMalloc(&h->aux2, n * sizeof(uint32_t));
+  if (e == cudaSuccess && hier) e = cudaMalloc(&h->aux2, n32 * sizeof(uint32_t));
   if (e == cudaSuccess && (cfg->variant == LMZ_V4 || hier)) {      // state[2], the float visit layer (lmaze_env_v4.py:106-113)
     e = cudaMalloc(&h->visit, n * 324 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(h->visit, 0, n * 324 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&h->hist, n * 64);           // the visit history (lmz_v2.cuh): empty = an all-zero layer
+    if (e == cudaSuccess) e = cudaMalloc(&h->hist, n32 * 64);           // the visit history (lmz_v2.cuh): empty = an all-zero layer
     if (e == cudaSuccess) e = cudaMemset(h->hist, 0, n * 64);
   }
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, (lmz::NUM_STATS + 3) * sizeof(unsigned long long));

@@ -67,47 +67,89 @@ __device__ __forceinline__ uint32_t visit_cover(int h, int o) {
   return hi >= lo ? ((2u << hi) - (1u << lo)) : 0u;
 }
 
+// Packed float32 pairs (Blackwell FFMA2, PTX fma.rn.f32x2): two independent correctly rounded f32 fmas in one issue
+// slot -- tools/ffma2_bench.cu: 1.46x the lane-fma rate of FFMA on a B200.  Each half is an ordinary IEEE fma.rn.f32.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // The layer's values on TWO 5x5 windows (origins (ax, ay) and (bx, by) = centre - 2) after the first `T` averagings
-// of the history: the reference's fold, per entry and cell ONE select (the addend) and ONE fma.  `tmax` >= T is
-// warp-uniform (the loop bound); entries past this lane's T are skipped by its own predicate.
-// The loop over the history words is ROLLED on purpose (one word = 4 entries per trip, ~10 KB of code): fully
-// unrolled, the fold is 64 x ~150 instructions = 150 KB of straight-line code that every warp streams through once
-// per tile -- far beyond the instruction caches, and the compact kernel then waits for instruction FETCH
-// (ncu: `no_instruction`) instead of issuing.  Registers cannot be indexed by the trip count, so the words are
-// ROTATED through h.w[0] instead (15 moves per trip); `h` is consumed.
-__device__ __forceinline__ void visit_fold2(VisitHist &h, int T, int tmax, int ax, int ay, int bx, int by,
-                                            float *va, float *vb) {
+// of the history.  The reference's fold  v <- RN((v + m_k) / 2), k = 0 .. T-1  is evaluated as the WEIGHTED SUM
+//     u <- RN(u + m_k * 2^(k-T)),   u = v * 2^-(T-1-k) after entry k,
+// which is the same float32 sequence scaled by a power of two (scaling by 2^n commutes with rounding: T <= 64, so
+// nothing leaves the normal range; the product m_k * 2^(k-T) is exact) -- u after the last entry IS v, bit for bit
+// (tests: every v4 / v5 parity run compares the whole layer).  In this form an entry is ONE fma per
+// cell, fma(r_i, c_j, u): r_i = 1.0 / 0.0 (entry covers row i of the window, and k < this lane's T), c_j = 2^(k-T) /
+// 0.0 (covers column j) -- 10 + 10 selects per entry instead of one per cell, and the 50 fmas go two per instruction
+// (f2_fma; accumulator pairs: row i of a window = (0,1), (2,3), and column 4 of window A pairs with column 4 of
+// window B).  `tmax` >= T is warp-uniform (the loop bound); no branch depends on a lane's own T.
+// The loop over the history words is ROLLED on purpose (one word = 4 entries per trip): fully unrolled, the fold was
+// 64 x ~150 instructions = 150 KB of straight-line code that every warp streams through once per tile -- far beyond
+// the instruction caches; the compact kernel then waited for instruction FETCH instead of issuing (steady state,
+// v4 compact: 0.85 G env-steps/s unrolled, 4.1 G rolled).  Registers cannot be indexed by the trip count, so the
+// words are ROTATED through h.w[0] instead (15 moves per trip); `h` is consumed.
+// `Told` of the T entries come from the history words `h`; entry T-1 is `last` when T > Told (the entry this very
+// step appends: it is folded from registers, so the words never have to be modified -- a store into h.w[runtime index]
+// sends the whole array to local memory).
+__device__ __forceinline__ void visit_fold2(VisitHist &h, int Told, int T, uint32_t last, int tmax, int ax, int ay,
+                                            int bx, int by, float *va, float *vb) {
+  uint64_t acc[25];
 #pragma unroll
-  for (int c = 0; c < 25; ++c) { va[c] = 0.0f; vb[c] = 0.0f; }
+  for (int c = 0; c < 25; ++c) acc[c] = 0ull;                // (+0.0f, +0.0f)
+  const int kend = (tmax + 3) & ~3;                          // (warp-uniform)
 #pragma unroll 1
-  for (int k0 = 0; k0 < tmax; k0 += 4) {                     // (warp-uniform bound)
-    const uint32_t w = h.w[0];
+  for (int k0 = 0; k0 <= kend; k0 += 4) {                    // the trip k0 == kend folds `last`
+    const bool tail = k0 == kend;
+    const uint32_t w = tail ? last : h.w[0];
 #pragma unroll
     for (int g = 0; g < 15; ++g) h.w[g] = h.w[g + 1];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      if (k0 + b < T) {
-        const uint32_t e = (w >> (8 * b)) & 255u;
-        const int hx = (int)(e >> 4), hy = (int)(e & 15u);    // centre - 2 = the entry's window origin
-        // row i of window A (absolute row ax + i) is covered by the entry iff 0 <= ax + i - hx < 5
-        const int rxa = ax - hx, rya = ay - hy, rxb = bx - hx, ryb = by - hy;
-        float adda[5], addb[5];
+      if (tail && b > 0) break;                              // (uniform)
+      const int k = tail ? T - 1 : k0 + b;
+      const bool live = tail ? T > Told : k < Told;
+      const float wk = __uint_as_float(live ? (uint32_t)(k - T + 127) << 23 : 0u);   // 2^(k-T); 0 for a dead entry
+      const uint32_t e = (w >> (8 * b)) & 255u;
+      const int hx = (int)(e >> 4), hy = (int)(e & 15u);      // centre - 2 = the entry's window origin
+      // row i of window A (absolute row ax + i) is covered by the entry iff 0 <= ax + i - hx < 5
+      const int rxa = ax - hx, rya = ay - hy, rxb = bx - hx, ryb = by - hy;
+      float ca[5], cb[5], ra[5], rb[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          adda[j] = ((unsigned)(rya + j) < 5u) ? 0.5f : 0.0f;
-          addb[j] = ((unsigned)(ryb + j) < 5u) ? 0.5f : 0.0f;
-        }
+      for (int j = 0; j < 5; ++j) {
+        ca[j] = ((unsigned)(rya + j) < 5u) ? wk : 0.0f;
+        cb[j] = ((unsigned)(ryb + j) < 5u) ? wk : 0.0f;
+        ra[j] = ((unsigned)(rxa + j) < 5u) ? 1.0f : 0.0f;
+        rb[j] = ((unsigned)(rxb + j) < 5u) ? 1.0f : 0.0f;
+      }
+      const uint64_t ca01 = f2_pack(ca[0], ca[1]), ca23 = f2_pack(ca[2], ca[3]);
+      const uint64_t cb01 = f2_pack(cb[0], cb[1]), cb23 = f2_pack(cb[2], cb[3]);
+      const uint64_t c44 = f2_pack(ca[4], cb[4]);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const bool ia = (unsigned)(rxa + i) < 5u, ib = (unsigned)(rxb + i) < 5u;
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            va[i * 5 + j] = __fmaf_rn(va[i * 5 + j], 0.5f, ia ? adda[j] : 0.0f);
-            vb[i * 5 + j] = __fmaf_rn(vb[i * 5 + j], 0.5f, ib ? addb[j] : 0.0f);
-          }
-        }
+      for (int i = 0; i < 5; ++i) {
+        const uint64_t ra2 = f2_pack(ra[i], ra[i]), rb2 = f2_pack(rb[i], rb[i]), rab = f2_pack(ra[i], rb[i]);
+        acc[2 * i] = f2_fma(ra2, ca01, acc[2 * i]);
+        acc[2 * i + 1] = f2_fma(ra2, ca23, acc[2 * i + 1]);
+        acc[10 + 2 * i] = f2_fma(rb2, cb01, acc[10 + 2 * i]);
+        acc[11 + 2 * i] = f2_fma(rb2, cb23, acc[11 + 2 * i]);
+        acc[20 + i] = f2_fma(rab, c44, acc[20 + i]);
       }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    f2_unpack(acc[2 * i], va[i * 5], va[i * 5 + 1]);
+    f2_unpack(acc[2 * i + 1], va[i * 5 + 2], va[i * 5 + 3]);
+    f2_unpack(acc[10 + 2 * i], vb[i * 5], vb[i * 5 + 1]);
+    f2_unpack(acc[11 + 2 * i], vb[i * 5 + 2], vb[i * 5 + 3]);
+    f2_unpack(acc[20 + i], va[i * 5 + 4], vb[i * 5 + 4]);
   }
 }
 
@@ -132,10 +174,11 @@ __device__ __forceinline__ float visit_fold_cell(const VisitHist &h, int src, in
 // literal full pass over the env's layer in memory, and the averaging that finds the history full materialises the
 // layer from the history on the way.  Then every lane: append / reset its history (one 16-byte store of the chunk that
 // holds the new entry) and fold the two windows (history mode), or read them from the layer (direct mode).
+// Returns true when vc / vp hold the lane's two visit crops (the CALLER stores them into its value planes: the compact
+// kernel first waits, after the fold, for the bulk copy that is still reading those planes).
 template <class W>
-__device__ __forceinline__ void visit_step(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
-                                           uint32_t vinfo, bool want_planes, VisitHist &h, float *plane_cur,
-                                           float *plane_prev) {
+__device__ __forceinline__ bool visit_step(const KParams &p, int64_t e0, int lane, bool valid, uint32_t info,
+                                           uint32_t vinfo, bool want_planes, VisitHist &h, float *vc, float *vp) {
   constexpr int GG = W::G * W::G;
   const uint32_t op = valid ? (vinfo & 7u) : (uint32_t)VOP_READ;
   const int tpre = (vinfo >> 3) & 127, tpost = (vinfo >> 10) & 127;
@@ -160,40 +203,31 @@ __device__ __forceinline__ void visit_step(const KParams &p, int64_t e0, int lan
     }
     __syncwarp();                                           // the cooperative stores are visible to the owning lane
   }
-  if (!valid) return;
-  if (tpost == VT_DIRECT) {                                 // direct mode: the windows come from the layer in memory
-    if (!want_planes) return;
+  const bool direct = valid && tpost == VT_DIRECT;
+  const bool hmode = valid && !direct;                      // history mode
+  // history mode: a reset empties the history (v4: its first averaging is the spawn cell), an averaging appends
+  // ONE BYTE at position tpost - 1
+  const bool app = hmode && (op == VOP_AVG || (op == VOP_RESET && W::VT_RESET == 1));
+  const uint32_t last = visit_entry(bx, by);
+  if (app) p.hist[(e0 + lane) * HIST_MAX + (tpost - 1)] = (uint8_t)last;
+  const int need = (hmode && want_planes) ? tpost : 0;      // entries this lane folds ...
+  const int told = need - ((app && need > 0) ? 1 : 0);      // ... of which these come from the loaded words
+  const int tmax = __reduce_max_sync(0xffffffffu, told);
+  const bool any = __any_sync(0xffffffffu, need > 0);
+  if (any) visit_fold2(h, told, need, last, tmax, bx - 2, by - 2, px - 2, py - 2, vc, vp);   // (need == 0: all zeros)
+  if (direct && want_planes) {                              // direct mode: the windows come from the layer in memory
     const float *vis = p.visit + (e0 + lane) * GG;
 #pragma unroll
     for (int k = 0; k < 25; ++k) {
-      plane_cur[k] = __ldcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5));
-      plane_prev[k] = __ldcg(vis + (px - 2 + k / 5) * W::G + (py - 2 + k % 5));
+      vc[k] = __ldcg(vis + (bx - 2 + k / 5) * W::G + (by - 2 + k % 5));
+      vp[k] = __ldcg(vis + (px - 2 + k / 5) * W::G + (py - 2 + k % 5));
     }
-    return;
   }
-  // history mode: a reset empties the history (v4: its first averaging is the spawn cell), an averaging appends
-  const bool app = op == VOP_AVG || (op == VOP_RESET && W::VT_RESET == 1);
-  if (app) {
-    const int pos = tpost - 1;                              // 0 .. 63
-    const uint32_t ent = visit_entry(bx, by) << (8 * (pos & 3));
-    const uint32_t keep = ~(255u << (8 * (pos & 3)));
-    uint4 chunk = make_uint4(0u, 0u, 0u, 0u);
+  if (!any && !direct) {
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {
-      if (g == (pos >> 2)) h.w[g] = (h.w[g] & keep) | ent;
-      if ((g >> 2) == (pos >> 4)) {
-        if ((g & 3) == 0) chunk.x = h.w[g]; else if ((g & 3) == 1) chunk.y = h.w[g]; else if ((g & 3) == 2) chunk.z = h.w[g]; else chunk.w = h.w[g];
-      }
-    }
-    __stcg(reinterpret_cast<uint4 *>(p.hist + (e0 + lane) * HIST_MAX) + (pos >> 4), chunk);
+    for (int k = 0; k < 25; ++k) { vc[k] = 0.0f; vp[k] = 0.0f; }
   }
-  const int need = want_planes ? tpost : 0;
-  const int tmax = __reduce_max_sync(__activemask(), need);
-  if (!want_planes) return;
-  float vc[25], vp[25];
-  visit_fold2(h, tpost, tmax, bx - 2, by - 2, px - 2, py - 2, vc, vp);
-#pragma unroll
-  for (int k = 0; k < 25; ++k) { plane_cur[k] = vc[k]; plane_prev[k] = vp[k]; }
+  return valid && want_planes;
 }
 
 // lmz_get_visit / lmz_set_visit: the layer crosses the ABI as values.  get: the fold of the env's history (or the layer
@@ -259,6 +293,8 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
   pre_next.w0 = pre_next.w1 = pre_next.w2 = 0u; pre_next.act = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) pre_next.h[k] = make_uint4(0u, 0u, 0u, 0u);
+  // (Measured, tools/_gpu15.sh: making these loads unconditional and broadcasting the grabbed tile index late --
+  // both of which help the compact kernel below -- costs THIS kernel 28 % on v2, 305 -> 221 M env-steps/s.)
   auto prefetch = [&](int64_t tl) {          // warp 0: start everything tile `tl` will need
     const int64_t e = tl * 32 + lane;
     if (tl < tiles && e < p.n) pre_next = fov_preload<W>(p, e);
@@ -284,7 +320,11 @@ __global__ void __launch_bounds__(THREADS) lmz_env_fov_kernel(const KParams p) {
 #ifndef LMZ_DEBUG_NO_VISIT                   // (tuning builds only: how fast is the kernel without the visit layer?)
     if (W::NVIS > 0 && need_visit) {         // append to / fold the visit history: the two 5x5 visit crops
       VisitHist vh = visit_hist_of(pre);
-      visit_step<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vh, mv + W::VIS_SLOT0 * 25, mv + W::VIS_SLOT1 * 25);
+      float vc[25], vp[25];
+      if (visit_step<W>(p, tl * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, vh, vc, vp)) {
+#pragma unroll
+        for (int k = 0; k < 25; ++k) { mv[W::VIS_SLOT0 * 25 + k] = vc[k]; mv[W::VIS_SLOT1 * 25 + k] = vp[k]; }
+      }
     }
 #endif
     if (valid && (v.rfov || v.rloc)) {       // 25-bit planes -> float planes (lane stride VALS is odd: no bank conflicts)
@@ -396,7 +436,8 @@ struct FovSmall {
   static constexpr uint32_t TAB_BYTES = (W::BLOB_BYTES - STAGE_OFF + 15u) & ~15u;
   static constexpr uint32_t PER = W::C * 25;                            // floats per env row (the obs channels are slots 0..C-1)
   static constexpr uint32_t PERL = 4 * 25;                              // v5 local obs row
-  static constexpr uint32_t smem_bytes(int threads) { return TAB_BYTES + (threads / 32) * 32 * PER * 4; }
+  static constexpr uint32_t IN_BYTES = W::NVIS > 0 ? 2048u + 3u * 128u : 0u;   // v4 / v5: a tile's histories + 3 state-word arrays
+  static constexpr uint32_t smem_bytes(int threads) { return TAB_BYTES + (threads / 32) * (32 * PER * 4 + IN_BYTES); }
 };
 
 template <class W, int THREADS>
@@ -405,9 +446,15 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
   __shared__ __align__(8) uint64_t bar;
   using FS = FovSmall<W>;
   constexpr int WARPS = THREADS / 32;
+  __shared__ __align__(8) uint64_t in_bar[WARPS];                // v4 / v5: one input barrier per warp
   constexpr uint32_t PER = FS::PER, PERL = FS::PERL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) mbar_init(&in_bar[w], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar, W::BLOB_BYTES - FS::STAGE_OFF);
@@ -426,13 +473,6 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     if (lane == 0) tl = p.tile_begin + grab_tile(p.work);
     return __shfl_sync(0xffffffffu, tl, 0);
   };
-  auto preload = [&](int64_t tl, FovPre &q) {
-    const int64_t e = tl * 32 + lane;
-    q.w0 = q.w1 = q.w2 = 0u; q.act = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) q.h[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (tl < tiles && e < p.n) q = fov_preload<W>(p, e);
-  };
   // copy of the first `bytes` of the warp's smem tile to global (both 16-byte aligned): ONE shared -> global bulk
   // copy issued by lane 0 -- the TMA engine moves the tile's rows as one contiguous run, no LSU store is issued
   auto copy_out = [&](float *dst, uint32_t bytes) {
@@ -444,47 +484,9 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
   };
-  // Software pipeline over the warp's tiles: the transitions of tile t+1 run while the TMA engine drains tile t's rows.
-  struct Slot {
-    FovLane<W::NBIT> v;
-    VisitHist h;
-    int64_t tile;
-    bool valid;
-  };
-  int64_t ntile = grab(), nntile = grab();
-  FovPre pre;
-  preload(ntile, pre);
-  auto stage_a = [&](Slot &sl) {                                 // transitions + visit loads of the next tile
-    sl.tile = ntile;
-    const int64_t after = grab();                                // needed two tiles from now
-    const int64_t e = sl.tile * 32 + lane;
-    sl.valid = sl.tile < tiles && e < p.n;
-    FovLane<W::NBIT> &v = sl.v;
-    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
-    v.vinfo = 0; v.rfov = false; v.rloc = false;
-#pragma unroll
-    for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
-    const FovPre pre_used = pre;
-    if (sl.valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre_used);
-    if (p.mode == MODE_STEP) ws.add(sl.valid, v.o);
-    ntile = nntile; nntile = after;
-    preload(ntile, pre);                                         // the tile after's words fly meanwhile
-    if (W::NVIS > 0) sl.h = visit_hist_of(pre_used);
-  };
-  Slot cur, nxt;
-  stage_a(cur);
-  while (cur.tile < tiles) {
-    const FovLane<W::NBIT> v = cur.v;
-    const bool valid = cur.valid;
-    const int64_t tile = cur.tile;
-    const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
-    const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
+  // the tile's observation rows: bit planes -> floats in the warp's rows (the visit crops are already there), copy out
+  auto emit = [&](const FovLane<W::NBIT> &v, bool valid, int64_t tile, unsigned ff, unsigned fl) {
     float *mine = rows + lane * PER;
-    if (W::NVIS == 0) stage_a(nxt);                              // v2: the next tile's transitions overlap the draining copy
-    rows_free();                                                 // the previous tile's copy out has read the buffer
-    if (W::NVIS > 0 && need_visit)                               // append to / fold the visit history: the two crops
-      visit_step<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, cur.h, mine + W::VIS_SLOT0 * 25, mine + W::VIS_SLOT1 * 25);
-    if (W::NVIS > 0) stage_a(nxt);                               // next tile's transitions overlap the draining copy
     const int64_t row0 = tile * 32 - p.win_lo;                   // obs row of the tile's first env
     if (ff) {
       if (valid && v.rfov) {                                     // 25-bit planes -> float planes (stride PER is odd: no bank conflicts)
@@ -530,7 +532,135 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
         }
       }
     }
-    cur = nxt;
+  };
+  auto blank_lane = [](FovLane<W::NBIT> &v) {
+    v.o.st = 0; v.o.st_old = 0; v.o.render = false; v.o.done = false; v.o.cls = -1; v.o.eplen = 0; v.info = 0;
+    v.vinfo = 0; v.rfov = false; v.rloc = false;
+#pragma unroll
+    for (int b = 0; b < W::NBIT; ++b) v.mask[b] = 0;
+  };
+
+  if constexpr (W::NVIS > 0) {
+    // ---- the visit variants (v4, v5): the tile's INPUTS come through the TMA engine too ------------------------
+    // A tile's state words and visit histories are contiguous runs (128 bytes per word array, 2 KB of history), so
+    // lane 0 requests them as bulk copies into the warp's input buffer one whole tile ahead and the warp picks them up
+    // behind an mbarrier.  Loading them into registers a tile ahead does NOT work: the compiler moves a loaded
+    // register to its loop-carried home right behind the load, and that move waits for the load (ncu: 22 % of the
+    // warp's cycles in long_scoreboard at those moves and at the shuffle behind the work-counter atomic).  The
+    // atomic is issued WITHOUT the compiler's warp aggregation (grab_tile_async) two tiles ahead and its result is
+    // first touched a tile later.  The handle's state arrays are padded to whole tiles (lmz_abi.cu).
+    constexpr uint32_t IN_HIST = 0, IN_W0 = 2048, IN_W1 = 2176, IN_W2 = 2304;
+    unsigned char *inb = smem + FS::TAB_BYTES + WARPS * (32 * PER * 4) + warp * FS::IN_BYTES;
+    uint64_t *ibar = &in_bar[warp];
+    const bool need_hist = p.mode != MODE_PLANNER;
+    const bool need_act = p.mode == MODE_STEP || p.mode == MODE_PLANNER;
+    auto issue_inputs = [&](int64_t tl) {                        // lane 0
+      const int64_t e0 = tl * 32;
+      mbar_expect_tx(ibar, (need_hist ? 2048u : 0u) + (W::HAS_LOC ? 384u : 256u));
+      if (need_hist) bulk_g2s(inb + IN_HIST, p.hist + e0 * HIST_MAX, 2048u, ibar);
+      bulk_g2s(inb + IN_W0, p.state + e0, 128u, ibar);
+      bulk_g2s(inb + IN_W1, p.goal_count + e0, 128u, ibar);
+      if (W::HAS_LOC) bulk_g2s(inb + IN_W2, p.aux2 + e0, 128u, ibar);
+    };
+    auto load_act = [&](int64_t tl) -> long long {               // (unconditional: lanes past the end re-read the last action)
+      const int64_t e = tl * 32 + lane;
+      return need_act ? load_action(p.actions, p.action_dtype, e < p.n ? e : p.n - 1) : 0ll;
+    };
+    int64_t cur_t = grab(), nxt_t = grab();
+    int64_t raw = 0;                                             // lane 0: the tile after those, still in flight
+    if (lane == 0) raw = p.tile_begin + grab_tile_async(p.work);
+    long long act_next = 0;
+    if (cur_t < tiles) {
+      if (lane == 0) issue_inputs(cur_t);
+      act_next = load_act(cur_t);
+    }
+    uint32_t phase = 0;
+    while (cur_t < tiles) {
+      const int64_t tile = cur_t;
+      mbar_wait(ibar, phase);
+      phase ^= 1u;
+      FovPre pre;
+      pre.w0 = reinterpret_cast<const uint32_t *>(inb + IN_W0)[lane];
+      pre.w1 = reinterpret_cast<const uint32_t *>(inb + IN_W1)[lane];
+      pre.w2 = W::HAS_LOC ? reinterpret_cast<const uint32_t *>(inb + IN_W2)[lane] : 0u;
+      pre.act = act_next;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        pre.h[k] = need_hist ? reinterpret_cast<const uint4 *>(inb + IN_HIST)[lane * 4 + k] : make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();                                              // every lane has read the buffer: it can be refilled
+      const int64_t after = __shfl_sync(0xffffffffu, raw, 0);    // grabbed a tile ago
+      if (lane == 0) raw = p.tile_begin + grab_tile_async(p.work);
+      if (nxt_t < tiles) {
+        if (lane == 0) { fence_proxy_async(); issue_inputs(nxt_t); }
+        act_next = load_act(nxt_t);
+      }
+      const int64_t e = tile * 32 + lane;
+      const bool valid = e < p.n;
+      FovLane<W::NBIT> v;
+      blank_lane(v);
+      if (valid) v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre);
+      if (p.mode == MODE_STEP) ws.add(valid, v.o);
+      const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
+      const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
+      if (need_hist) {                                           // append to / fold the visit history: the two crops ...
+        VisitHist h = visit_hist_of(pre);
+        float vc[25], vp[25];
+        const bool have = visit_step<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, h, vc, vp);
+        rows_free();                                             // ... while the previous tile's copy out still reads the rows
+        if (have) {
+          float *mine = rows + lane * PER;
+#pragma unroll
+          for (int k = 0; k < 25; ++k) { mine[W::VIS_SLOT0 * 25 + k] = vc[k]; mine[W::VIS_SLOT1 * 25 + k] = vp[k]; }
+        }
+      } else {
+        rows_free();
+      }
+      emit(v, valid, tile, ff, fl);
+      cur_t = nxt_t; nxt_t = after;
+    }
+  } else {
+    // ---- v2: software pipeline over the warp's tiles: the transitions of tile t+1 run while the TMA engine drains
+    // tile t's rows (state words in registers, requested one tile ahead)
+    auto preload = [&](int64_t tl, FovPre &q) {
+      const int64_t e = tl * 32 + lane;
+      q.w0 = q.w1 = q.w2 = 0u; q.act = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q.h[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (tl < tiles && e < p.n) q = fov_preload<W>(p, e);
+    };
+    struct Slot {
+      FovLane<W::NBIT> v;
+      int64_t tile;
+      bool valid;
+    };
+    int64_t ntile = grab(), nntile = grab();
+    FovPre pre;
+    preload(ntile, pre);
+    auto stage_a = [&](Slot &sl) {                               // transitions of the next tile
+      sl.tile = ntile;
+      const int64_t after = grab();                              // needed two tiles from now
+      const int64_t e = sl.tile * 32 + lane;
+      sl.valid = sl.tile < tiles && e < p.n;
+      blank_lane(sl.v);
+      const FovPre pre_used = pre;
+      if (sl.valid) sl.v = fov_lane(static_cast<const W *>(nullptr), p, e, t, sb, pre_used);
+      if (p.mode == MODE_STEP) ws.add(sl.valid, sl.v.o);
+      ntile = nntile; nntile = after;
+      preload(ntile, pre);                                       // the tile after's words fly meanwhile
+    };
+    Slot cur, nxt;
+    stage_a(cur);
+    while (cur.tile < tiles) {
+      const FovLane<W::NBIT> v = cur.v;
+      const bool valid = cur.valid;
+      const int64_t tile = cur.tile;
+      const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
+      const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
+      stage_a(nxt);                                              // the next tile's transitions overlap the draining copy
+      rows_free();                                               // the previous tile's copy out has read the buffer
+      emit(v, valid, tile, ff, fl);
+      cur = nxt;
+    }
   }
   if (lane == 0) bulk_wait_all();                                // the last tile's rows have left shared memory
   if (p.mode == MODE_STEP) ws.flush(p.stats, lane);

@@ -442,6 +442,14 @@ __device__ __forceinline__ void stage_blob(unsigned char *smem, uint64_t *bar, c
 __device__ __forceinline__ int64_t grab_tile(unsigned long long *work) {
   return (int64_t)atomicAdd(&work[0], 1ull);
 }
+// The same grab as inline PTX: the compiler aggregates a result-returning atomicAdd across the warp and broadcasts the
+// result with a shuffle RIGHT BEHIND the atomic, which makes every grab synchronous; this form lets the result be
+// touched a tile later (lane 0 calls it alone).
+__device__ __forceinline__ int64_t grab_tile_async(unsigned long long *work) {
+  unsigned long long r;
+  asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(r) : "l"(work) : "memory");
+  return (int64_t)r;
+}
 __device__ __forceinline__ void finish_grabber(unsigned long long *work, unsigned long long grabbers) {
   __threadfence();
   if (atomicAdd(&work[1], 1ull) == grabbers - 1) { work[0] = 0; work[1] = 0; }
