@@ -48,7 +48,9 @@ def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=None,
+                    help="untimed steps before the timed region (default 5; 64 for v4 / v5, whose step cost grows with "
+                         "the length of the visit histories: 64 steps put the episodes in steady state)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--variant", default="v0", choices=["v0", "v2", "v3", "v4", "v5"])
@@ -60,7 +62,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the rollout / obs-to-host side measurements")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.warmup is None:
+        args.warmup = 64 if args.variant in ("v4", "v5") else 5
+    return args
 
 
 # --------------------------------------------------------------------------- clocks
@@ -295,6 +300,11 @@ def workload_config(args, note=None):
     if W < args.envs:
         cfg["window"] = ("obs tensor holds %d of %d envs; a step = 1 fused step launch + %d render-window launches, "
                          "every env's obs is written once per step" % (W, args.envs, -(-args.envs // W) - 1))
+    if args.variant in ("v4", "v5"):
+        cfg["visit_histories"] = ("%d warm-up steps before the timed region: the cost of a v4 / v5 step grows with the length "
+                                  "of the envs' visit histories (the crops are folded from them), and about 60 steps in, "
+                                  "the episodes are de-synchronised and the lengths in steady state (mean 26, warp maximum "
+                                  "45-49 of at most 52)" % args.warmup)
     if note:
         cfg["note"] = note
     return cfg
@@ -380,8 +390,8 @@ def run_ours(args):
     if windows[-1] + W > N:
         windows[-1] = N - W
     obs_bytes = env.obs[0].numel() * env.obs.element_size()
-    # v4: the visit layer is kept as its history: 64 B read + one 16 B chunk written per env-step
-    step_bytes = obs_bytes + 14 + (VISIT_HIST_BYTES + 16 if args.variant == "v4" else 0)
+    # v4: the visit layer is kept as its history: 64 B read + the appended entry (1 B) written per env-step
+    step_bytes = obs_bytes + 14 + (VISIT_HIST_BYTES + 1 if args.variant == "v4" else 0)
     if hier:
         step_bytes = 0        # filled in after the timed region from the measured localDone / planner fractions
     if args.render_mode == "incremental":
@@ -443,9 +453,9 @@ def run_ours(args):
         # 2 rewards, 4 flag bytes, action; planner launch: 3 state words read, and for the waiting envs goal +
         # state write + local obs
         fov_b, loc_b = (34300, 19600) if args.obs_mode == "full" else (700, 400)
-        step_bytes = int(fov_b + loc_b + VISIT_HIST_BYTES + 16 * ld + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
+        step_bytes = int(fov_b + loc_b + VISIT_HIST_BYTES + 1 * ld + 24 + 8 + 4 + 1 + 12 + pf * (loc_b + 12 + 1 + 2))
         hier_note = {"local_done_fraction": ld, "planner_fraction": pf,
-                     "bytes": "%d foveal + %d local obs + %d visit history read (+16 x localDone written; the layer is kept "
+                     "bytes": "%d foveal + %d local obs + %d visit history read (+1 x localDone written; the layer is kept "
                               "as its history, DESIGN.md 3.5) + state/rewards/flags/action 37 + planner launch: 12 + "
                               "planner_fraction x (%d local obs + 15)" % (fov_b, loc_b, VISIT_HIST_BYTES, loc_b)}
     achieved = N * step_bytes / (step_ms * 1e-3) / 1e9

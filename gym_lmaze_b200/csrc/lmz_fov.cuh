@@ -172,8 +172,8 @@ __device__ __forceinline__ float visit_fold_cell(const VisitHist &h, int src, in
 
 // The whole visit step of a tile.  Rare whole-layer work first, warp-cooperatively: an averaging in DIRECT mode is the
 // literal full pass over the env's layer in memory, and the averaging that finds the history full materialises the
-// layer from the history on the way.  Then every lane: append / reset its history (one 16-byte store of the chunk that
-// holds the new entry) and fold the two windows (history mode), or read them from the layer (direct mode).
+// layer from the history on the way.  Then every lane: append / reset its history (a one-byte store of the new entry)
+// and fold the two windows (history mode), or read them from the layer (direct mode).
 // Returns true when vc / vp hold the lane's two visit crops (the CALLER stores them into its value planes: the compact
 // kernel first waits, after the fold, for the bulk copy that is still reading those planes).
 template <class W>
