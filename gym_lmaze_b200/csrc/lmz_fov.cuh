@@ -436,7 +436,8 @@ struct FovSmall {
   static constexpr uint32_t TAB_BYTES = (W::BLOB_BYTES - STAGE_OFF + 15u) & ~15u;
   static constexpr uint32_t PER = W::C * 25;                            // floats per env row (the obs channels are slots 0..C-1)
   static constexpr uint32_t PERL = 4 * 25;                              // v5 local obs row
-  static constexpr uint32_t IN_BYTES = W::NVIS > 0 ? 2048u + 3u * 128u : 0u;   // v4 / v5: a tile's histories + 3 state-word arrays
+  static constexpr uint32_t IN_HIST = W::NVIS > 0 ? 2048u : 0u;                // v4 / v5: a tile's visit histories
+  static constexpr uint32_t IN_BYTES = W::NVIS > 0 ? IN_HIST + 3u * 128u : 0u;  // ... + 3 state-word arrays
   static constexpr uint32_t smem_bytes(int threads) { return TAB_BYTES + (threads / 32) * (32 * PER * 4 + IN_BYTES); }
 };
 
@@ -525,10 +526,21 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
       float *dst = reinterpret_cast<float *>(p.obs2) + row0 * (int64_t)PERL;
       if (fl == 0xffffffffu) copy_out(dst, 32 * PERL * 4);
       else {
+        // some envs of the tile (plannerStep: the envs waiting for their planner, about half of them in steady state):
+        // every local row is 400 bytes and 16-byte aligned, so each RUN of flagged envs leaves as one bulk copy
+        // (per-env 32-bit stores made the compact plannerStep launch as long as the step launch itself)
+        fence_proxy_async();
         __syncwarp();
-        for (unsigned m = fl; m; m &= m - 1) {
-          const uint32_t env = __ffs(m) - 1;
-          for (uint32_t pos = lane; pos < PERL; pos += 32) __stcs(dst + env * PERL + pos, rows[env * PERL + pos]);
+        if (lane == 0) {
+          unsigned m = fl;
+          while (m) {
+            const uint32_t lo = __ffs(m) - 1;
+            const unsigned gap = ~(m >> lo);                     // first zero above lo ends the run
+            const uint32_t len = gap ? (uint32_t)(__ffs(gap) - 1) : 32u - lo;
+            bulk_s2g(dst + lo * PERL, rows_s + lo * PERL * 4, len * PERL * 4);
+            m = (lo + len >= 32u) ? 0u : (m >> (lo + len)) << (lo + len);
+          }
+          bulk_commit();
         }
       }
     }
@@ -542,6 +554,8 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
 
   if constexpr (W::NVIS > 0) {
     // ---- the visit variants (v4, v5): the tile's INPUTS come through the TMA engine too ------------------------
+    // (v2 keeps the register pipeline below: with its two state words per env the TMA form is SLOWER, 10.9 vs 11.5 G
+    // env-steps/s, profiles/r2_ab18.txt)
     // A tile's state words and visit histories are contiguous runs (128 bytes per word array, 2 KB of history), so
     // lane 0 requests them as bulk copies into the warp's input buffer one whole tile ahead and the warp picks them up
     // behind an mbarrier.  Loading them into registers a tile ahead does NOT work: the compiler moves a loaded
@@ -549,10 +563,10 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
     // warp's cycles in long_scoreboard at those moves and at the shuffle behind the work-counter atomic).  The
     // atomic is issued WITHOUT the compiler's warp aggregation (grab_tile_async) two tiles ahead and its result is
     // first touched a tile later.  The handle's state arrays are padded to whole tiles (lmz_abi.cu).
-    constexpr uint32_t IN_HIST = 0, IN_W0 = 2048, IN_W1 = 2176, IN_W2 = 2304;
+    constexpr uint32_t IN_HIST = 0, IN_W0 = FS::IN_HIST, IN_W1 = IN_W0 + 128, IN_W2 = IN_W0 + 256;
     unsigned char *inb = smem + FS::TAB_BYTES + WARPS * (32 * PER * 4) + warp * FS::IN_BYTES;
     uint64_t *ibar = &in_bar[warp];
-    const bool need_hist = p.mode != MODE_PLANNER;
+    const bool need_hist = W::NVIS > 0 && p.mode != MODE_PLANNER;
     const bool need_act = p.mode == MODE_STEP || p.mode == MODE_PLANNER;
     auto issue_inputs = [&](int64_t tl) {                        // lane 0
       const int64_t e0 = tl * 32;
@@ -602,7 +616,7 @@ __global__ void __launch_bounds__(THREADS) lmz_fov_small_kernel(const KParams p)
       if (p.mode == MODE_STEP) ws.add(valid, v.o);
       const unsigned ff = __ballot_sync(0xffffffffu, valid && v.rfov);
       const unsigned fl = __ballot_sync(0xffffffffu, valid && v.rloc);
-      if (need_hist) {                                           // append to / fold the visit history: the two crops ...
+      if (W::NVIS > 0 && need_hist) {                            // append to / fold the visit history: the two crops ...
         VisitHist h = visit_hist_of(pre);
         float vc[25], vp[25];
         const bool have = visit_step<W>(p, tile * 32, lane, valid, v.info, v.vinfo, valid && v.rfov, h, vc, vp);
