@@ -10,7 +10,7 @@ from gym_lmaze_b200 import build, _abi
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 CUFILT = shutil.which("cu++filt") or "/usr/local/cuda/bin/cu++filt"
 OPS = ["UBLKCP.S.G", "UBLKCP.G.S", "SYNCS", "STG.E.EF.128", "STG.E.EF", "STG", "LDG", "LDS.128", "STS", "SHFL", "VOTE", "ATOM", "RED",
-       "FADD", "FMUL", "DADD", "DMUL", "DFMA", "HMMA", "UTCHMMA", "UTMALDG"]
+       "FADD", "FMUL", "FFMA2", "DADD", "DMUL", "DFMA", "HMMA", "UTCHMMA", "UTMALDG"]
 
 
 def main():
@@ -32,7 +32,7 @@ def main():
         if m:
             name = m.group(1)
             funcs[name] = []
-        elif name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             funcs[name].append(line)
     archs = sorted(set(re.findall(r"arch = (sm_\w+)", sass)))
     print("csrc_hash %s   archs %s   kernels %d   (tools/sass_summary.py)" % (build.source_hash(), ",".join(archs), len(funcs)))
