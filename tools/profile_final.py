@@ -17,7 +17,9 @@ prof.start()
 
 
 def unprofiled(fn, n):
-    """n warm-up calls outside the capture (visit variants: 60 steps put the visit histories at their steady-state length)"""
+    """n warm-up calls outside the capture.  60 steps put the visit histories of v4 / v5 near their steady-state length
+    (warp maximum ~45 of ~50); the episodes are fully de-synchronised only after ~1,000 steps (bench.py warms that long),
+    but under ncu even an uncaptured launch costs ~0.1 s: a 1,000-step warm-up per variant ran past a 13-minute limit."""
     torch.cuda.synchronize(); prof.stop()
     for i in range(n):
         fn(i)
