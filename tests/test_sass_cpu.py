@@ -55,3 +55,22 @@ def test_tma_and_vector_store_paths_are_in_the_sass(sass):
     roll = _one(funcs, "lmz_rollout_kernel", "2V0")
     assert "VOTE" in roll or "VOTEU" in roll                  # warp ballots feed the statistics
     assert "HMMA" not in "".join(funcs.values()) and "UTCHMMA" not in "".join(funcs.values())   # no tensor-core use
+
+
+def _instructions(body):
+    return [l for l in body.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
+
+
+def test_visit_fold_is_a_rolled_ffma2_loop_without_local_memory(sass):
+    """Two regressions this guards: the visit fold fully unrolled was 150 KB of code per warp and tile and
+    the compact v4 / v5 kernels waited for instruction FETCH (0.85 instead of 4+ G env-steps/s); a store into the history
+    words at a runtime index sends them to local memory.  The fold runs on packed FFMA2 pairs."""
+    _, funcs = sass
+    for needles in (("lmz_fov_small_kernel", "FovILi4ELi7", "Li128"), ("lmz_fov_small_kernel", "2V5", "Li128")):
+        body = _one(funcs, *needles)
+        n = len(_instructions(body))
+        assert n < 8000, (needles, n)                            # rolled: ~4,600 (v4) / ~5,300 (v5); unrolled: ~15,000
+        assert len(re.findall(r"\bFFMA2\b", body)) >= 100, needles   # 25 packed fmas per entry x 4 entries per trip
+        assert not re.search(r"\b(LDL|STL)\b", body) or needles[1] == "2V5", needles   # v4: no local-memory traffic at all
+    fov = _one(funcs, "lmz_env_fov_kernel", "FovILi4ELi7", "Li128")
+    assert len(re.findall(r"\bFFMA2\b", fov)) >= 100 and len(_instructions(fov)) < 10000
