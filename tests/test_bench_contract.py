@@ -30,3 +30,21 @@ def test_reference_arm_other_ranks_stay_silent():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_default_warmup_puts_the_foveal_variants_in_steady_state(monkeypatch):
+    """bench.py's own arm warms v2 / v4 / v5 for 1,000 steps unless told otherwise (their episodes start together and need
+    that long to de-synchronise); everything else, and the CPU arm, keeps the short default."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    def parsed(*argv):
+        monkeypatch.setattr(sys, "argv", ["bench.py", *argv])
+        return bench.parse_args()
+    assert parsed().warmup == 5 and parsed("--variant", "v3").warmup == 5
+    for v in ("v2", "v4", "v5"):
+        assert parsed("--variant", v).warmup == 1000
+        assert parsed("--variant", v, "--impl", "reference").warmup == 5
+        assert parsed("--variant", v, "--warmup", "7").warmup == 7
+    assert "steady_state" in bench.workload_config(parsed("--variant", "v4"))
+    assert "steady_state" not in bench.workload_config(parsed())
